@@ -1,0 +1,830 @@
+// pss_api.cu — the C ABI of libpss_b200.so (include/pss_b200.h): handle, HBM workspace, kernel
+// launches and CUDA-event timing.  No CPU fallback: every compute entry point runs the sm_100a kernels
+// in pss_sieve.cuh / pss_scan.cuh or fails.
+//
+// HBM layout per handle (grow-only, reused across calls so steady-state calls do not allocate):
+//   pattern[4]      16x-replicated pre-sieve byte patterns (9 MB total, L2 resident)
+//   base_primes     u32 primes 61 .. sqrt(hi)        (56 KB at hi = 2.28e10)
+//   bitmap          wheel-30 bit-packed sieve result, 1 byte / 30 integers (760 MB at hi = 2.28e10)
+//   chunk_counts    u32 popcount per 1 KiB bitmap chunk;  tile_counts / tile_prefix per sieve tile
+//   primes          compacted u64 primes (8 B / prime; 8 GB for the first 1e9 primes)
+//   scan state      per scan tile: status word + aggregate + inclusive limb records
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/pss_b200.h"
+#include "pss_scan.cuh"
+#include "pss_sieve.cuh"
+
+using namespace pss;
+
+namespace {
+
+struct DevBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+};
+
+constexpr u64 kMaxValue = 1ull << PSS_MAX_PRIME_BITS;
+constexpr u32 kPatternPad = 256 * 1024;   // >= largest tile
+static const u32 kPatGroups[kMaxPatterns][5] = {{7, 11, 13, 17, 19}, {23, 29, 31, 0, 0}, {37, 41, 43, 0, 0}, {47, 53, 59, 0, 0}};
+static const u32 kFirstSievePrime[kMaxPatterns + 1] = {7, 23, 37, 47, 61};
+
+struct MiscDev {   // small device-side block, one H2D / D2H per scan
+    u32 ticket;
+    u32 error_flag;
+    u32 pad[2];
+    pss_power_result results[PSS_MAX_POWER];
+    u32 carry[PSS_MAX_POWER * PSS_LIMBS];
+};
+
+}  // namespace
+
+struct pss_handle {
+    int device = 0;
+    int sm_count = 0;
+    size_t smem_optin = 0;
+    cudaStream_t stream = nullptr;
+    std::string err;
+    char name[256] = {0};
+
+    // tuning
+    u32 tile_bytes = 96 * 1024;
+    u32 sieve_threads = 512;
+    u32 n_pat = 4;
+    u32 cta_wide_div = 256;    // p < tile_bytes / div -> CTA-wide
+    u32 warp_wide_div = 8;     // p < tile_bytes / div -> warp-wide
+
+    // patterns
+    uint4* d_pat[kMaxPatterns] = {nullptr, nullptr, nullptr, nullptr};
+    u64 pat_period16[kMaxPatterns] = {0, 0, 0, 0};
+
+    // base primes
+    std::vector<u32> h_base;   // all primes >= 7 up to base_limit
+    u64 base_limit = 0;
+    DevBuf d_base;
+    u32 base_first_prime = 0;  // first sieving prime the device copy starts at
+    u32 n_base_dev = 0;
+
+    // sieve workspace / state of the last sieve
+    DevBuf bitmap, chunk_counts, tile_counts, tile_prefix;
+    u64 sv_lo = 0, sv_hi = 0, sv_B_start = 0, sv_total = 0, sv_c235 = 0;
+    u32 sv_tile_bytes = 0, sv_n_tiles = 0;
+    bool sv_valid = false;
+
+    // resident primes
+    DevBuf primes;
+    u64 n_resident = 0;
+    u64 resident_last = 0;
+
+    // scan workspace
+    DevBuf status, agg, incl, misc, prefix_out, user_vals;
+    MiscDev* h_misc = nullptr;   // pinned
+
+    cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    u64 launches = 0;
+};
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(pss_handle* h, int code, const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    if (h) h->err = buf;
+    g_err = buf;
+    return code;
+}
+
+#define CU_TRY(h, expr)                                                                                 \
+    do {                                                                                                \
+        cudaError_t e__ = (expr);                                                                       \
+        if (e__ != cudaSuccess)                                                                         \
+            return fail(h, e__ == cudaErrorMemoryAllocation ? PSS_ENOMEM : PSS_EINTERNAL, "%s: %s (%s:%d)", #expr, \
+                        cudaGetErrorString(e__), __FILE__, __LINE__);                                   \
+    } while (0)
+
+#define PSS_TRY(expr)              \
+    do {                           \
+        int rc__ = (expr);         \
+        if (rc__ != PSS_OK) return rc__; \
+    } while (0)
+
+int ensure(pss_handle* h, DevBuf& b, size_t bytes) {
+    if (bytes <= b.cap) return PSS_OK;
+    if (b.p) {
+        CU_TRY(h, cudaStreamSynchronize(h->stream));
+        CU_TRY(h, cudaFree(b.p));
+        b.p = nullptr;
+        b.cap = 0;
+    }
+    size_t want = bytes + bytes / 16 + 256;
+    cudaError_t e = cudaMalloc(&b.p, want);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        want = bytes;
+        e = cudaMalloc(&b.p, want);
+    }
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        b.p = nullptr;
+        return fail(h, PSS_ENOMEM, "cudaMalloc(%zu bytes) failed: %s", bytes, cudaGetErrorString(e));
+    }
+    b.cap = want;
+    return PSS_OK;
+}
+
+u32 env_u32(const char* name, u32 dflt) {
+    const char* s = getenv(name);
+    if (!s || !*s) return dflt;
+    return (u32)strtoul(s, nullptr, 10);
+}
+
+u64 isqrt_u64(u64 x) {
+    u64 r = (u64)std::sqrt((long double)x);
+    while (r * r > x) --r;
+    while ((r + 1) * (r + 1) <= x) ++r;
+    return r;
+}
+
+// ---- base primes (staged once, regrown only when a larger sqrt(hi) is needed) --------------------
+int ensure_base_primes(pss_handle* h, u64 hi) {
+    const u64 need = isqrt_u64(hi) + 1;
+    const u32 first = kFirstSievePrime[h->n_pat];
+    if (need > h->base_limit) {
+        // simple odd-only host sieve of [0, limit]; limit <= 2^20 for hi <= 2^40.  Staging only: these are
+        // the sieving primes, not part of the sieved range's output.
+        u64 limit = std::max<u64>(need, 1024);
+        std::vector<uint8_t> comp(limit + 1, 0);
+        for (u64 i = 3; i * i <= limit; i += 2)
+            if (!comp[i])
+                for (u64 m = i * i; m <= limit; m += 2 * i) comp[m] = 1;
+        h->h_base.clear();
+        for (u64 i = 7; i <= limit; i += 2)
+            if (!comp[i]) h->h_base.push_back((u32)i);
+        h->base_limit = limit;
+        h->base_first_prime = 0;   // force re-upload
+    }
+    if (h->base_first_prime != first) {
+        auto it = std::lower_bound(h->h_base.begin(), h->h_base.end(), first);
+        const size_t n = (size_t)(h->h_base.end() - it);
+        PSS_TRY(ensure(h, h->d_base, std::max<size_t>(n, 1) * sizeof(u32)));
+        if (n) CU_TRY(h, cudaMemcpyAsync(h->d_base.p, &*it, n * sizeof(u32), cudaMemcpyHostToDevice, h->stream));
+        CU_TRY(h, cudaStreamSynchronize(h->stream));
+        h->n_base_dev = (u32)n;
+        h->base_first_prime = first;
+    }
+    return PSS_OK;
+}
+
+int build_patterns(pss_handle* h) {
+    for (int g = 0; g < kMaxPatterns; ++g) {
+        u64 period = 1;
+        for (int k = 0; k < 5; ++k)
+            if (kPatGroups[g][k]) period *= kPatGroups[g][k];
+        const u64 bytes = 16 * period + kPatternPad;
+        CU_TRY(h, cudaMalloc(&h->d_pat[g], bytes));
+        h->pat_period16[g] = 16 * period;
+        k_build_pattern<<<h->sm_count * 8, 256, 0, h->stream>>>(reinterpret_cast<uint8_t*>(h->d_pat[g]), bytes, kPatGroups[g][0],
+                                                                 kPatGroups[g][1], kPatGroups[g][2], kPatGroups[g][3],
+                                                                 kPatGroups[g][4]);
+        CU_TRY(h, cudaGetLastError());
+    }
+    CU_TRY(h, cudaStreamSynchronize(h->stream));
+    return PSS_OK;
+}
+
+template <int THREADS>
+int launch_sieve(pss_handle* h, const SieveParams& sp) {
+    static bool attr_set = false;
+    if (!attr_set) {
+        CU_TRY(h, cudaFuncSetAttribute(k_sieve<THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(h->smem_optin - 2048)));
+        attr_set = true;
+    }
+    int occ = 1;
+    CU_TRY(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_sieve<THREADS>, THREADS, sp.tile_bytes));
+    if (occ < 1) return fail(h, PSS_EINTERNAL, "sieve tile of %u bytes does not fit shared memory", sp.tile_bytes);
+    const u32 grid = std::min<u32>(sp.n_tiles, (u32)(h->sm_count * occ));
+    k_sieve<THREADS><<<grid, THREADS, sp.tile_bytes, h->stream>>>(sp);
+    CU_TRY(h, cudaGetLastError());
+    h->launches++;
+    return PSS_OK;
+}
+
+// K1a + K1b: sieve [lo,hi) into the bitmap, count.  Leaves sv_* describing the bitmap.
+int sieve_range(pss_handle* h, u64 lo, u64 hi) {
+    h->sv_valid = false;
+    if (hi > kMaxValue) return fail(h, PSS_EINVAL, "sieve bound %llu exceeds 2^%d", (unsigned long long)hi, PSS_MAX_PRIME_BITS);
+    if (lo >= hi || hi <= 2) {
+        h->sv_lo = lo; h->sv_hi = hi; h->sv_total = 0; h->sv_c235 = 0; h->sv_n_tiles = 0; h->sv_valid = true;
+        return PSS_OK;
+    }
+    PSS_TRY(ensure_base_primes(h, hi));
+    const u64 B_start = (lo / 30) & ~15ull;
+    const u64 B_end = (hi + 29) / 30;
+    const u64 n_bytes = B_end - B_start;
+    // tile size: the tuned default, shrunk for small ranges so that every SM still gets tiles
+    u32 tile_bytes = h->tile_bytes;
+    {
+        const u64 want_tiles = (u64)h->sm_count * 4;
+        u64 per = (n_bytes + want_tiles - 1) / want_tiles;
+        per = ((per + kChunkBytes - 1) / kChunkBytes) * kChunkBytes;
+        per = std::max<u64>(per, 8 * 1024);
+        if (per < tile_bytes) tile_bytes = (u32)per;
+    }
+    const u64 n_tiles64 = (n_bytes + tile_bytes - 1) / tile_bytes;
+    if (n_tiles64 > 0x7FFFFFFFull) return fail(h, PSS_EINVAL, "range too large");
+    const u32 n_tiles = (u32)n_tiles64;
+    const u32 cpt = tile_bytes / kChunkBytes;
+
+    PSS_TRY(ensure(h, h->bitmap, (size_t)n_tiles * tile_bytes));
+    PSS_TRY(ensure(h, h->chunk_counts, (size_t)n_tiles * cpt * sizeof(u32)));
+    PSS_TRY(ensure(h, h->tile_counts, (size_t)n_tiles * sizeof(u32)));
+    PSS_TRY(ensure(h, h->tile_prefix, ((size_t)n_tiles + 1) * sizeof(u64)));
+
+    SieveParams sp;
+    memset(&sp, 0, sizeof sp);
+    sp.lo = lo;
+    sp.hi = hi;
+    sp.B_start = B_start;
+    sp.tile_bytes = tile_bytes;
+    sp.n_tiles = n_tiles;
+    sp.base_primes = static_cast<const u32*>(h->d_base.p);
+    // only primes up to sqrt(hi) are ever needed
+    {
+        const u64 lim = isqrt_u64(hi - 1);
+        auto b = std::lower_bound(h->h_base.begin(), h->h_base.end(), h->base_first_prime);
+        auto e = std::upper_bound(h->h_base.begin(), h->h_base.end(), (u32)std::min<u64>(lim, 0xFFFFFFFFull));
+        sp.n_base = (e > b) ? (u32)(e - b) : 0;
+        const u32 cta_lim = tile_bytes / std::max<u32>(h->cta_wide_div, 1);
+        const u32 warp_lim = tile_bytes / std::max<u32>(h->warp_wide_div, 1);
+        u32 nc = (u32)(std::lower_bound(b, e, cta_lim) - b);
+        nc = std::min<u32>(nc, kMaxCtaWide);
+        u32 nw = (u32)(std::lower_bound(b, e, warp_lim) - b);
+        nw = std::max(nw, nc);
+        sp.n_cta_wide = nc;
+        sp.n_warp_wide = nw;
+    }
+    sp.n_pat = h->n_pat;
+    for (u32 g = 0; g < h->n_pat; ++g) {
+        sp.pat[g] = h->d_pat[g];
+        sp.pat_period16[g] = h->pat_period16[g];
+    }
+    sp.bitmap = static_cast<u32*>(h->bitmap.p);
+    sp.chunk_counts = static_cast<u32*>(h->chunk_counts.p);
+    sp.tile_counts = static_cast<u32*>(h->tile_counts.p);
+
+    CU_TRY(h, cudaEventRecord(h->ev[0], h->stream));
+    switch (h->sieve_threads) {
+        case 256: PSS_TRY(launch_sieve<256>(h, sp)); break;
+        case 1024: PSS_TRY(launch_sieve<1024>(h, sp)); break;
+        default: PSS_TRY(launch_sieve<512>(h, sp)); break;
+    }
+    CU_TRY(h, cudaEventRecord(h->ev[1], h->stream));
+
+    u64 c235 = 0;
+    for (u64 q : {2ull, 3ull, 5ull})
+        if (q >= lo && q < hi) ++c235;
+    k_scan_tile_counts<<<1, 1024, 0, h->stream>>>(sp.tile_counts, n_tiles, c235, static_cast<u64*>(h->tile_prefix.p));
+    CU_TRY(h, cudaGetLastError());
+    h->launches++;
+    CU_TRY(h, cudaEventRecord(h->ev[2], h->stream));
+    u64 total = 0;
+    CU_TRY(h, cudaMemcpyAsync(&total, static_cast<u64*>(h->tile_prefix.p) + n_tiles, sizeof(u64), cudaMemcpyDeviceToHost, h->stream));
+    CU_TRY(h, cudaStreamSynchronize(h->stream));
+
+    h->sv_lo = lo; h->sv_hi = hi; h->sv_B_start = B_start; h->sv_total = total; h->sv_c235 = c235;
+    h->sv_tile_bytes = tile_bytes; h->sv_n_tiles = n_tiles; h->sv_valid = true;
+    return PSS_OK;
+}
+
+// K1c: compact the first min(total, cap) primes of the last sieve into the resident buffer
+int compact_resident(pss_handle* h, u64 cap) {
+    if (!h->sv_valid) return fail(h, PSS_EINTERNAL, "no sieve result to compact");
+    const u64 n_out = std::min(h->sv_total, cap);
+    h->n_resident = 0;
+    if (n_out == 0) {
+        CU_TRY(h, cudaEventRecord(h->ev[3], h->stream));
+        return PSS_OK;
+    }
+    PSS_TRY(ensure(h, h->primes, (size_t)n_out * sizeof(u64)));
+    u64* out = static_cast<u64*>(h->primes.p);
+    if (h->sv_c235) {
+        u64 small[3];
+        u32 k = 0;
+        for (u64 q : {2ull, 3ull, 5ull})
+            if (q >= h->sv_lo && q < h->sv_hi && k < n_out) small[k++] = q;
+        CU_TRY(h, cudaMemcpyAsync(out, small, k * sizeof(u64), cudaMemcpyHostToDevice, h->stream));
+        CU_TRY(h, cudaStreamSynchronize(h->stream));
+    }
+    if (h->sv_n_tiles) {
+        CompactParams cp;
+        cp.bitmap = static_cast<const u32*>(h->bitmap.p);
+        cp.chunk_counts = static_cast<const u32*>(h->chunk_counts.p);
+        cp.tile_prefix = static_cast<const u64*>(h->tile_prefix.p);
+        cp.chunks_per_tile = h->sv_tile_bytes / kChunkBytes;
+        u32 group = 8;
+        while (cp.chunks_per_tile % group) --group;
+        cp.group = group;
+        cp.n_groups = h->sv_n_tiles * (cp.chunks_per_tile / group);
+        cp.B_start = h->sv_B_start;
+        cp.out = out;
+        cp.out_cap = n_out;
+        cp.error_flag = &static_cast<MiscDev*>(h->misc.p)->error_flag;
+        CU_TRY(h, cudaMemsetAsync(cp.error_flag, 0, sizeof(u32), h->stream));
+        const u32 grid = std::min<u32>(cp.n_groups, (u32)h->sm_count * 16);
+        k_compact<<<grid, 256, 0, h->stream>>>(cp);
+        CU_TRY(h, cudaGetLastError());
+        h->launches++;
+    }
+    CU_TRY(h, cudaEventRecord(h->ev[3], h->stream));
+    u32 flag = 0;
+    u64 last = 0;
+    CU_TRY(h, cudaMemcpyAsync(&flag, &static_cast<MiscDev*>(h->misc.p)->error_flag, sizeof(u32), cudaMemcpyDeviceToHost, h->stream));
+    CU_TRY(h, cudaMemcpyAsync(&last, out + (n_out - 1), sizeof(u64), cudaMemcpyDeviceToHost, h->stream));
+    CU_TRY(h, cudaStreamSynchronize(h->stream));
+    if (flag) return fail(h, PSS_EINTERNAL, "compaction overflow (flag %u): bitmap is not a valid sieve", flag);
+    h->n_resident = n_out;
+    h->resident_last = last;
+    return PSS_OK;
+}
+
+// ---- K2/K3 dispatch --------------------------------------------------------------------------------
+template <int K, bool MULTI, int MODE, int ITEMS>
+int launch_scan_t(pss_handle* h, ScanParams& sp) {
+    using Lay = Layout<K, MULTI>;
+    constexpr int TILE = kScanThreads * ITEMS;
+    const u64 n_tiles64 = (sp.count + TILE - 1) / TILE;
+    if (n_tiles64 > 0x7FFFFFFFull) return fail(h, PSS_EINVAL, "range too large for one scan");
+    sp.n_tiles = (u32)n_tiles64;
+    PSS_TRY(ensure(h, h->status, (size_t)sp.n_tiles * sizeof(u32)));
+    PSS_TRY(ensure(h, h->agg, (size_t)sp.n_tiles * Lay::TOTAL * sizeof(u32)));
+    PSS_TRY(ensure(h, h->incl, (size_t)sp.n_tiles * Lay::TOTAL * sizeof(u32)));
+    sp.tile_status = static_cast<u32*>(h->status.p);
+    sp.tile_agg = static_cast<u32*>(h->agg.p);
+    sp.tile_incl = static_cast<u32*>(h->incl.p);
+    CU_TRY(h, cudaMemsetAsync(sp.tile_status, 0, (size_t)sp.n_tiles * sizeof(u32), h->stream));
+    static int occ = 0;
+    if (!occ) {
+        CU_TRY(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_power_scan<K, MULTI, MODE, ITEMS>, kScanThreads, 0));
+        if (occ < 1) occ = 1;
+    }
+    const u32 grid = std::min<u32>(sp.n_tiles, (u32)(h->sm_count * occ));
+    k_power_scan<K, MULTI, MODE, ITEMS><<<grid, kScanThreads, 0, h->stream>>>(sp);
+    CU_TRY(h, cudaGetLastError());
+    h->launches++;
+    return PSS_OK;
+}
+
+template <int MODE>
+int launch_scan(pss_handle* h, ScanParams& sp, u32 K, bool multi) {
+    if (!multi) {
+        switch (K) {
+            case 1: return launch_scan_t<1, false, MODE, 16>(h, sp);
+            case 2: return launch_scan_t<2, false, MODE, 16>(h, sp);
+            case 3: return launch_scan_t<3, false, MODE, 16>(h, sp);
+            case 4: return launch_scan_t<4, false, MODE, 8>(h, sp);
+            case 5: return launch_scan_t<5, false, MODE, 8>(h, sp);
+            case 6: return launch_scan_t<6, false, MODE, 8>(h, sp);
+            case 7: return launch_scan_t<7, false, MODE, 8>(h, sp);
+            case 8: return launch_scan_t<8, false, MODE, 8>(h, sp);
+        }
+    } else if constexpr (MODE != kModePrefix) {
+        switch (K) {
+            case 2: return launch_scan_t<2, true, MODE, 8>(h, sp);
+            case 3: return launch_scan_t<3, true, MODE, 8>(h, sp);
+            case 4: return launch_scan_t<4, true, MODE, 8>(h, sp);
+            case 5: return launch_scan_t<5, true, MODE, 8>(h, sp);
+            case 6: return launch_scan_t<6, true, MODE, 8>(h, sp);
+        }
+    }
+    return fail(h, PSS_EINVAL, "unsupported power configuration k=%u all_powers=%d", K, (int)multi);
+}
+
+inline u32 n_powers_of(u32 K, bool multi) { return multi ? K : 1; }
+inline u32 expo_of(u32 K, bool multi, u32 j) { return multi ? j + 1 : K; }
+
+// Core scan over device values.  carry_in: n_powers * PSS_LIMBS limbs (host) or NULL.
+int run_scan(pss_handle* h, const u64* d_vals, u64 count, u64 n_first, const u32* carry_in, u32 K, bool multi, int mode,
+             u64 n_min, u64 n_max, u32 cmp, const u32* target, u32 target_nlimbs, u32* d_prefix_out,
+             pss_power_result* out /* n_powers */) {
+    if (K < 1 || K > PSS_MAX_POWER) return fail(h, PSS_EINVAL, "power %u out of range 1..%d", K, PSS_MAX_POWER);
+    if (multi && K > 6) return fail(h, PSS_EINVAL, "all_powers supports power_max <= 6");
+    if (multi && K == 1) multi = false;
+    const u32 np = n_powers_of(K, multi);
+    static const u32 kMasks[6] = {2u, 5u, 1u, 3u, 4u, 6u};   // EQ NE LT LE GT GE over bits {lt,eq,gt}
+    if (cmp > 5) return fail(h, PSS_EINVAL, "invalid comparison operator %u", cmp);
+
+    MiscDev* hm = h->h_misc;
+    memset(hm, 0, sizeof(MiscDev));
+    for (u32 j = 0; j < np; ++j) {
+        hm->results[j].power = expo_of(K, multi, j);
+        hm->results[j].first_match_n = ~0ull;
+        if (carry_in) {
+            memcpy(&hm->carry[j * PSS_LIMBS], carry_in + j * PSS_LIMBS, PSS_LIMBS * sizeof(u32));
+            const int w = sum_limbs((int)expo_of(K, multi, j));
+            for (int i = w; i < PSS_LIMBS; ++i)
+                if (hm->carry[j * PSS_LIMBS + i]) return fail(h, PSS_EINVAL, "carry-in of power %u exceeds %d limbs", hm->results[j].power, w);
+        }
+        memcpy(hm->results[j].final_sum, &hm->carry[j * PSS_LIMBS], PSS_LIMBS * sizeof(u32));
+    }
+    ScanParams sp;
+    memset(&sp, 0, sizeof sp);
+    sp.primes = d_vals;
+    sp.count = count;
+    sp.n_first = n_first;
+    sp.n_min = n_min;
+    sp.n_max = n_max;
+    sp.cmp_mask = kMasks[cmp];
+    if (mode == kModeCompare) {
+        for (u32 i = 0; i < target_nlimbs && i < PSS_LIMBS; ++i) sp.target[i] = target[i];
+        for (u32 j = 0; j < np; ++j) {
+            const u32 w = (u32)sum_limbs((int)expo_of(K, multi, j));
+            bool over = false;
+            for (u32 i = w; i < target_nlimbs; ++i)
+                if (target[i]) over = true;
+            if (over) sp.target_over_mask |= (1u << j);
+        }
+    }
+    MiscDev* dm = static_cast<MiscDev*>(h->misc.p);
+    sp.carry_in = dm->carry;
+    sp.ticket = &dm->ticket;
+    sp.error_flag = &dm->error_flag;
+    sp.results = dm->results;
+    sp.prefix_out = d_prefix_out;
+
+    CU_TRY(h, cudaEventRecord(h->ev[4], h->stream));
+    if (count > 0) {
+        CU_TRY(h, cudaMemcpyAsync(dm, hm, sizeof(MiscDev), cudaMemcpyHostToDevice, h->stream));
+        switch (mode) {
+            case kModeReduce: PSS_TRY(launch_scan<kModeReduce>(h, sp, K, multi)); break;
+            case kModeCompare: PSS_TRY(launch_scan<kModeCompare>(h, sp, K, multi)); break;
+            default: PSS_TRY(launch_scan<kModePrefix>(h, sp, K, multi)); break;
+        }
+        CU_TRY(h, cudaEventRecord(h->ev[5], h->stream));
+        CU_TRY(h, cudaMemcpyAsync(hm, dm, sizeof(MiscDev), cudaMemcpyDeviceToHost, h->stream));
+        CU_TRY(h, cudaStreamSynchronize(h->stream));
+        if (hm->error_flag) return fail(h, PSS_EINTERNAL, "scan look-back watchdog fired (flag %u)", hm->error_flag);
+    } else {
+        CU_TRY(h, cudaEventRecord(h->ev[5], h->stream));
+        CU_TRY(h, cudaStreamSynchronize(h->stream));
+    }
+    for (u32 j = 0; j < np; ++j) {
+        out[j] = hm->results[j];
+        if (out[j].match_count == 0) out[j].first_match_n = 0, out[j].last_match_n = 0;
+    }
+    return PSS_OK;
+}
+
+double ev_ms(pss_handle* h, int a, int b) {
+    float ms = 0;
+    if (cudaEventElapsedTime(&ms, h->ev[a], h->ev[b]) != cudaSuccess) {
+        cudaGetLastError();
+        return 0.0;
+    }
+    return ms;
+}
+
+int check_handle(pss_handle* h) {
+    if (!h) return fail(nullptr, PSS_EINVAL, "null handle");
+    cudaError_t e = cudaSetDevice(h->device);
+    if (e != cudaSuccess) return fail(h, PSS_ENODEV, "cudaSetDevice(%d): %s", h->device, cudaGetErrorString(e));
+    return PSS_OK;
+}
+
+}  // namespace
+
+// =====================================================================================================
+extern "C" {
+
+int pss_abi_version(void) { return PSS_ABI_VERSION; }
+
+uint64_t pss_nth_prime_upper(uint64_t n) {
+    // Rosser: p_n < n (ln n + ln ln n) for n >= 6;  Dusart 1999: p_n <= n (ln n + ln ln n - 0.9484), n >= 39017.
+    // (the reference over-sieves by 1.3x and regrows by 1.5x instead: utils/sieve.py:574-583)
+    if (n < 6) return 15;
+    const long double x = (long double)n;
+    const long double ln = logl(x), lnln = logl(ln);
+    long double b = (n >= 39017) ? x * (ln + lnln - 0.9484L) : x * (ln + lnln);
+    return (uint64_t)b + 3;
+}
+
+int pss_open(int device, pss_handle** out) {
+    if (!out) return fail(nullptr, PSS_EINVAL, "null out pointer");
+    *out = nullptr;
+    int n_dev = 0;
+    cudaError_t e = cudaGetDeviceCount(&n_dev);
+    if (e != cudaSuccess || n_dev == 0) {
+        cudaGetLastError();
+        return fail(nullptr, PSS_ENODEV, "GPU not available: %s", e != cudaSuccess ? cudaGetErrorString(e) : "no CUDA device");
+    }
+    if (device < 0) {
+        if (cudaGetDevice(&device) != cudaSuccess) device = 0;
+    }
+    if (device >= n_dev) return fail(nullptr, PSS_ENODEV, "GPU not available: device %d of %d", device, n_dev);
+    e = cudaSetDevice(device);
+    if (e != cudaSuccess) return fail(nullptr, PSS_ENODEV, "GPU not available: cudaSetDevice(%d): %s", device, cudaGetErrorString(e));
+    cudaDeviceProp prop;
+    e = cudaGetDeviceProperties(&prop, device);
+    if (e != cudaSuccess) return fail(nullptr, PSS_ENODEV, "GPU not available: %s", cudaGetErrorString(e));
+    if (prop.major < 10)
+        return fail(nullptr, PSS_ENODEV, "GPU not available: %s is sm_%d%d, this library is built for sm_100a only", prop.name, prop.major,
+                    prop.minor);
+    pss_handle* h = new pss_handle();
+    h->device = device;
+    h->sm_count = prop.multiProcessorCount;
+    h->smem_optin = prop.sharedMemPerBlockOptin;
+    snprintf(h->name, sizeof h->name, "%s (sm_%d%d, %d SMs, %.1f GB)", prop.name, prop.major, prop.minor, prop.multiProcessorCount,
+             (double)prop.totalGlobalMem / 1e9);
+    h->tile_bytes = env_u32("PSS_TILE_BYTES", h->tile_bytes);
+    h->sieve_threads = env_u32("PSS_SIEVE_THREADS", h->sieve_threads);
+    h->n_pat = std::min<u32>(env_u32("PSS_NPAT", h->n_pat), kMaxPatterns);
+    h->cta_wide_div = env_u32("PSS_CTA_WIDE_DIV", h->cta_wide_div);
+    h->warp_wide_div = env_u32("PSS_WARP_WIDE_DIV", h->warp_wide_div);
+    h->tile_bytes = std::max<u32>(8192, std::min<u32>((h->tile_bytes / kChunkBytes) * kChunkBytes, 216 * 1024));
+    auto cleanup = [&](int rc) {
+        pss_close(h);
+        return rc;
+    };
+    if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) return cleanup(fail(nullptr, PSS_EINTERNAL, "stream create failed"));
+    for (auto& ev : h->ev)
+        if (cudaEventCreate(&ev) != cudaSuccess) return cleanup(fail(nullptr, PSS_EINTERNAL, "event create failed"));
+    if (cudaMallocHost(&h->h_misc, sizeof(MiscDev)) != cudaSuccess) return cleanup(fail(nullptr, PSS_EINTERNAL, "pinned alloc failed"));
+    int rc = ensure(h, h->misc, sizeof(MiscDev));
+    if (rc == PSS_OK) rc = build_patterns(h);
+    if (rc != PSS_OK) {
+        std::string msg = h->err;
+        pss_close(h);
+        return fail(nullptr, rc, "%s", msg.c_str());
+    }
+    *out = h;
+    return PSS_OK;
+}
+
+int pss_close(pss_handle* h) {
+    if (!h) return PSS_OK;
+    cudaSetDevice(h->device);
+    if (h->stream) cudaStreamSynchronize(h->stream);
+    for (DevBuf* b : {&h->d_base, &h->bitmap, &h->chunk_counts, &h->tile_counts, &h->tile_prefix, &h->primes, &h->status, &h->agg,
+                      &h->incl, &h->misc, &h->prefix_out, &h->user_vals})
+        if (b->p) cudaFree(b->p);
+    for (auto& p : h->d_pat)
+        if (p) cudaFree(p);
+    if (h->h_misc) cudaFreeHost(h->h_misc);
+    for (auto& ev : h->ev)
+        if (ev) cudaEventDestroy(ev);
+    if (h->stream) cudaStreamDestroy(h->stream);
+    delete h;
+    return PSS_OK;
+}
+
+const char* pss_last_error(pss_handle* h) { return h ? h->err.c_str() : g_err.c_str(); }
+
+int pss_device_info(pss_handle* h, char* buf, size_t cap) {
+    PSS_TRY(check_handle(h));
+    if (!buf || !cap) return fail(h, PSS_EINVAL, "null buffer");
+    snprintf(buf, cap, "%s", h->name);
+    return PSS_OK;
+}
+
+int pss_set_tuning(pss_handle* h, uint32_t tile_bytes, uint32_t sieve_threads, uint32_t n_patterns) {
+    PSS_TRY(check_handle(h));
+    if (tile_bytes) {
+        if (tile_bytes % kChunkBytes || tile_bytes < 8192 || tile_bytes > 216 * 1024)
+            return fail(h, PSS_EINVAL, "tile_bytes must be a multiple of %d in [8192, %d]", kChunkBytes, 216 * 1024);
+        h->tile_bytes = tile_bytes;
+    }
+    if (sieve_threads) {
+        if (sieve_threads != 256 && sieve_threads != 512 && sieve_threads != 1024) return fail(h, PSS_EINVAL, "sieve_threads must be 256, 512 or 1024");
+        h->sieve_threads = sieve_threads;
+    }
+    if (n_patterns) {
+        if (n_patterns > kMaxPatterns) return fail(h, PSS_EINVAL, "n_patterns must be <= %d", kMaxPatterns);
+        h->n_pat = n_patterns;
+    }
+    return PSS_OK;
+}
+
+int pss_count_primes(pss_handle* h, uint64_t lo, uint64_t hi_excl, uint64_t* count) {
+    PSS_TRY(check_handle(h));
+    if (!count) return fail(h, PSS_EINVAL, "null count pointer");
+    PSS_TRY(sieve_range(h, lo, hi_excl));
+    *count = h->sv_total;
+    return PSS_OK;
+}
+
+int pss_slice_sieve(pss_handle* h, uint64_t lo, uint64_t hi_excl, uint64_t* count, uint64_t* last_prime) {
+    PSS_TRY(check_handle(h));
+    PSS_TRY(sieve_range(h, lo, hi_excl));
+    PSS_TRY(compact_resident(h, ~0ull));
+    if (count) *count = h->n_resident;
+    if (last_prime) *last_prime = h->n_resident ? h->resident_last : 0;
+    return PSS_OK;
+}
+
+int pss_generate_primes(pss_handle* h, uint64_t lo, uint64_t hi_excl, uint64_t* out_host, uint64_t cap, uint64_t* count) {
+    PSS_TRY(check_handle(h));
+    if (!count) return fail(h, PSS_EINVAL, "null count pointer");
+    PSS_TRY(sieve_range(h, lo, hi_excl));
+    *count = h->sv_total;
+    if (h->sv_total > cap) return fail(h, PSS_ENOMEM, "output buffer too small: need %llu entries", (unsigned long long)h->sv_total);
+    if (h->sv_total == 0) return PSS_OK;
+    if (!out_host) return fail(h, PSS_EINVAL, "null output buffer");
+    PSS_TRY(compact_resident(h, ~0ull));
+    CU_TRY(h, cudaMemcpyAsync(out_host, h->primes.p, (size_t)h->n_resident * sizeof(u64), cudaMemcpyDeviceToHost, h->stream));
+    CU_TRY(h, cudaStreamSynchronize(h->stream));
+    return PSS_OK;
+}
+
+static int sieve_first_n(pss_handle* h, u64 n) {
+    if (n == 0) return fail(h, PSS_EINVAL, "n must be positive");
+    u64 bound = pss_nth_prime_upper(n) + 1;
+    for (int attempt = 0; attempt < 4; ++attempt) {
+        if (bound > kMaxValue) return fail(h, PSS_EINVAL, "n = %llu needs primes beyond 2^%d", (unsigned long long)n, PSS_MAX_PRIME_BITS);
+        PSS_TRY(sieve_range(h, 0, bound));
+        if (h->sv_total >= n) return compact_resident(h, n);
+        bound += bound / 2;   // cannot happen with a proven bound; kept as a guard
+    }
+    return fail(h, PSS_EINTERNAL, "prime count bound failed for n = %llu", (unsigned long long)n);
+}
+
+int pss_generate_n_primes(pss_handle* h, uint64_t n, uint64_t* out_host) {
+    PSS_TRY(check_handle(h));
+    if (n == 0) return PSS_OK;
+    if (!out_host) return fail(h, PSS_EINVAL, "null output buffer");
+    PSS_TRY(sieve_first_n(h, n));
+    CU_TRY(h, cudaMemcpyAsync(out_host, h->primes.p, (size_t)n * sizeof(u64), cudaMemcpyDeviceToHost, h->stream));
+    CU_TRY(h, cudaStreamSynchronize(h->stream));
+    return PSS_OK;
+}
+
+int pss_nth_prime(pss_handle* h, uint64_t n_1based, uint64_t* prime) {
+    PSS_TRY(check_handle(h));
+    if (n_1based == 0) return fail(h, PSS_EINVAL, "n must be positive (1-indexed)");
+    if (!prime) return fail(h, PSS_EINVAL, "null output pointer");
+    PSS_TRY(sieve_first_n(h, n_1based));
+    *prime = h->resident_last;
+    return PSS_OK;
+}
+
+int pss_power_sum(pss_handle* h, const uint64_t* values_host, uint64_t count, uint32_t power, uint32_t* limbs_out) {
+    PSS_TRY(check_handle(h));
+    if (!limbs_out) return fail(h, PSS_EINVAL, "null output");
+    memset(limbs_out, 0, PSS_LIMBS * sizeof(u32));
+    if (count == 0) return PSS_OK;
+    if (!values_host) return fail(h, PSS_EINVAL, "null input");
+    if (power == 0) {
+        limbs_out[0] = (u32)count;
+        limbs_out[1] = (u32)(count >> 32);
+        return PSS_OK;
+    }
+    if (count >= (1ull << 36)) return fail(h, PSS_EINVAL, "too many values");
+    for (u64 i = 0; i < count; ++i)
+        if (values_host[i] >= kMaxValue) return fail(h, PSS_EINVAL, "value %llu at index %llu exceeds 2^%d", (unsigned long long)values_host[i],
+                                                      (unsigned long long)i, PSS_MAX_PRIME_BITS);
+    PSS_TRY(ensure(h, h->user_vals, (size_t)count * sizeof(u64)));
+    CU_TRY(h, cudaMemcpyAsync(h->user_vals.p, values_host, (size_t)count * sizeof(u64), cudaMemcpyHostToDevice, h->stream));
+    pss_power_result r[PSS_MAX_POWER];
+    PSS_TRY(run_scan(h, static_cast<const u64*>(h->user_vals.p), count, 1, nullptr, power, false, kModeReduce, 0, 0, 0, nullptr, 0, nullptr, r));
+    memcpy(limbs_out, r[0].final_sum, PSS_LIMBS * sizeof(u32));
+    return PSS_OK;
+}
+
+int pss_primesum(pss_handle* h, uint64_t n, uint32_t power, uint32_t* limbs_out) {
+    PSS_TRY(check_handle(h));
+    if (!limbs_out) return fail(h, PSS_EINVAL, "null output");
+    memset(limbs_out, 0, PSS_LIMBS * sizeof(u32));
+    if (n == 0) return PSS_OK;
+    if (power == 0) {
+        limbs_out[0] = (u32)n;
+        limbs_out[1] = (u32)(n >> 32);
+        return PSS_OK;
+    }
+    if (power > PSS_MAX_POWER) return fail(h, PSS_EINVAL, "power %u out of range 0..%d", power, PSS_MAX_POWER);
+    PSS_TRY(sieve_first_n(h, n));
+    pss_power_result r[PSS_MAX_POWER];
+    PSS_TRY(run_scan(h, static_cast<const u64*>(h->primes.p), n, 1, nullptr, power, false, kModeReduce, 0, 0, 0, nullptr, 0, nullptr, r));
+    memcpy(limbs_out, r[0].final_sum, PSS_LIMBS * sizeof(u32));
+    return PSS_OK;
+}
+
+static void fill_stats(pss_handle* h, pss_stats* s, u64 launches0, u64 primes, bool sieved) {
+    memset(s, 0, sizeof *s);
+    if (sieved) {
+        s->ms_sieve = ev_ms(h, 0, 1);
+        s->ms_count_scan = ev_ms(h, 1, 2);
+        s->ms_compact = ev_ms(h, 2, 3);
+        s->ms_total_device = ev_ms(h, 0, 5);
+        s->sieve_lo = h->sv_lo;
+        s->sieve_hi = h->sv_hi;
+    } else {
+        s->ms_total_device = ev_ms(h, 4, 5);
+    }
+    s->ms_power_scan = ev_ms(h, 4, 5);
+    s->primes = primes;
+    s->launches = h->launches - launches0;
+}
+
+static int validate_search(pss_handle* h, const pss_search_args* a, pss_search_result* res) {
+    if (!a || !res) return fail(h, PSS_EINVAL, "null argument");
+    if (a->power_max < 1 || a->power_max > PSS_MAX_POWER) return fail(h, PSS_EINVAL, "power_max %u out of range 1..%d", a->power_max, PSS_MAX_POWER);
+    if (a->cmp > 5) return fail(h, PSS_EINVAL, "invalid comparison operator %u", a->cmp);
+    if (a->target_nlimbs && !a->target) return fail(h, PSS_EINVAL, "null target");
+    if (a->n_min < 1 || a->n_max < a->n_min) return fail(h, PSS_EINVAL, "need 1 <= n_min <= n_max");
+    return PSS_OK;
+}
+
+int pss_search(pss_handle* h, const pss_search_args* a, pss_search_result* res) {
+    PSS_TRY(check_handle(h));
+    PSS_TRY(validate_search(h, a, res));
+    const u64 launches0 = h->launches;
+    memset(res, 0, sizeof *res);
+    PSS_TRY(sieve_first_n(h, a->n_max));
+    const bool multi = a->all_powers && a->power_max > 1;
+    PSS_TRY(run_scan(h, static_cast<const u64*>(h->primes.p), a->n_max, 1, nullptr, a->power_max, multi, kModeCompare, a->n_min, a->n_max,
+                     a->cmp, a->target, a->target_nlimbs, nullptr, res->powers));
+    res->n_powers = n_powers_of(a->power_max, multi);
+    res->primes_scanned = a->n_max;
+    res->last_prime = h->resident_last;
+    fill_stats(h, &res->stats, launches0, a->n_max, true);
+    return PSS_OK;
+}
+
+int pss_slice_reduce(pss_handle* h, uint64_t first, uint64_t count, uint32_t power_max, uint32_t all_powers, uint32_t* sums_out) {
+    PSS_TRY(check_handle(h));
+    if (!sums_out) return fail(h, PSS_EINVAL, "null output");
+    if (first + count > h->n_resident) return fail(h, PSS_EINVAL, "range [%llu,+%llu) outside the %llu resident primes", (unsigned long long)first,
+                                                    (unsigned long long)count, (unsigned long long)h->n_resident);
+    const bool multi = all_powers && power_max > 1;
+    pss_power_result r[PSS_MAX_POWER];
+    PSS_TRY(run_scan(h, static_cast<const u64*>(h->primes.p) + first, count, 1, nullptr, power_max, multi, kModeReduce, 0, 0, 0, nullptr, 0, nullptr, r));
+    const u32 np = n_powers_of(power_max, multi);
+    for (u32 j = 0; j < np; ++j) memcpy(sums_out + j * PSS_LIMBS, r[j].final_sum, PSS_LIMBS * sizeof(u32));
+    return PSS_OK;
+}
+
+int pss_slice_scan(pss_handle* h, uint64_t first, uint64_t count, uint64_t n_first, const uint32_t* carry_in, const pss_search_args* a,
+                   pss_search_result* res) {
+    PSS_TRY(check_handle(h));
+    PSS_TRY(validate_search(h, a, res));
+    if (first + count > h->n_resident) return fail(h, PSS_EINVAL, "range [%llu,+%llu) outside the %llu resident primes", (unsigned long long)first,
+                                                    (unsigned long long)count, (unsigned long long)h->n_resident);
+    const u64 launches0 = h->launches;
+    memset(res, 0, sizeof *res);
+    const bool multi = a->all_powers && a->power_max > 1;
+    PSS_TRY(run_scan(h, static_cast<const u64*>(h->primes.p) + first, count, n_first, carry_in, a->power_max, multi, kModeCompare, a->n_min, a->n_max,
+                     a->cmp, a->target, a->target_nlimbs, nullptr, res->powers));
+    res->n_powers = n_powers_of(a->power_max, multi);
+    res->primes_scanned = count;
+    if (count) {
+        u64 last = 0;
+        CU_TRY(h, cudaMemcpy(&last, static_cast<const u64*>(h->primes.p) + first + count - 1, sizeof(u64), cudaMemcpyDeviceToHost));
+        res->last_prime = last;
+    }
+    fill_stats(h, &res->stats, launches0, count, false);
+    return PSS_OK;
+}
+
+int pss_slice_prefix_sums(pss_handle* h, uint64_t first, uint64_t count, uint32_t power, const uint32_t* carry_in, uint32_t* out_host) {
+    PSS_TRY(check_handle(h));
+    if (count == 0) return PSS_OK;
+    if (!out_host) return fail(h, PSS_EINVAL, "null output");
+    if (first + count > h->n_resident) return fail(h, PSS_EINVAL, "range outside the resident primes");
+    if (power < 1 || power > PSS_MAX_POWER) return fail(h, PSS_EINVAL, "power %u out of range 1..%d", power, PSS_MAX_POWER);
+    PSS_TRY(ensure(h, h->prefix_out, (size_t)count * PSS_LIMBS * sizeof(u32)));
+    pss_power_result r[PSS_MAX_POWER];
+    PSS_TRY(run_scan(h, static_cast<const u64*>(h->primes.p) + first, count, 1, carry_in, power, false, kModePrefix, 0, 0, 0, nullptr, 0,
+                     static_cast<u32*>(h->prefix_out.p), r));
+    CU_TRY(h, cudaMemcpy(out_host, h->prefix_out.p, (size_t)count * PSS_LIMBS * sizeof(u32), cudaMemcpyDeviceToHost));
+    return PSS_OK;
+}
+
+int pss_slice_primes(pss_handle* h, uint64_t first, uint64_t count, uint64_t* out_host) {
+    PSS_TRY(check_handle(h));
+    if (count == 0) return PSS_OK;
+    if (!out_host) return fail(h, PSS_EINVAL, "null output");
+    if (first + count > h->n_resident) return fail(h, PSS_EINVAL, "range outside the resident primes");
+    CU_TRY(h, cudaMemcpy(out_host, static_cast<const u64*>(h->primes.p) + first, (size_t)count * sizeof(u64), cudaMemcpyDeviceToHost));
+    return PSS_OK;
+}
+
+int pss_slice_device_buffer(pss_handle* h, void** dev_ptr, uint64_t* count) {
+    PSS_TRY(check_handle(h));
+    if (dev_ptr) *dev_ptr = h->primes.p;
+    if (count) *count = h->n_resident;
+    return PSS_OK;
+}
+
+}  // extern "C"

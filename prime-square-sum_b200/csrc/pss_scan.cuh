@@ -1,0 +1,436 @@
+// pss_scan.cuh — K2 + K3: exact multi-limb p^k, warp -> block -> grid (decoupled look-back) prefix scan
+// of the running sums S_k(n), and the fused compare of EVERY partial sum against the target.
+//
+// Replaces (behaviour, not code):
+//   primes_gpu ** power + cp.sum  (utils/gpu.py:169-232, int64 only, wraps silently)
+//   sum(int(p) ** power for p in primes)  (utils/sequences.py:75, utils/gpu.py:244-247)
+//   IncrementalSumCache.add_prime running sums  (utils/sum_cache.py:116-141)
+//   ExpressionEvaluator._compare on each n     (utils/grammar.py:686-701,770-787)
+//
+// Arithmetic: 32-bit limbs, fixed widths per power (pow_limbs/sum_limbs in pss_common.cuh), schoolbook
+// p^(e+1) = p^e * p as IMAD.WIDE.U32 + carry chains, no tensor cores (integer work, not a contraction).
+// With MULTI the powers 1..K share one chain (config "--max p:5").
+//
+// Scan: every thread owns ITEMS consecutive primes (blocked order, staged through padded shared memory
+// from coalesced loads).  pass 1: thread-local sums -> warp shuffle scan (carry-propagating adds) ->
+// warp totals in shared memory -> tile aggregate -> single-pass decoupled look-back across tiles
+// (status flag + aggregate / inclusive limb records; tiles are handed out by an atomic ticket so every
+// predecessor is resident) seeded with the slice's carry-in.  pass 2: every thread re-walks its primes
+// from its exact exclusive prefix, forming each S_k(n) and comparing it with the target limbs.
+#pragma once
+#include "pss_common.cuh"
+#include "../../include/pss_b200.h"
+
+namespace pss {
+
+constexpr int kScanThreads = 256;
+constexpr u32 kSpinLimit = 1u << 22;   // look-back watchdog (polls); sets error_flag instead of hanging
+
+enum ScanMode { kModeReduce = 0, kModeCompare = 1, kModePrefix = 2 };
+
+template <int K, bool MULTI>
+PSS_HD constexpr int lay_width(int j) { return sum_limbs(MULTI ? j + 1 : K); }
+template <int K, bool MULTI>
+PSS_HD constexpr int lay_offset(int j) {
+    int o = 0;
+    for (int i = 0; i < j; ++i) o += lay_width<K, MULTI>(i);
+    return o;
+}
+template <int K, bool MULTI>
+struct Layout {
+    static constexpr int NP = MULTI ? K : 1;
+    static constexpr int TOTAL = lay_offset<K, MULTI>(MULTI ? K : 1);
+    PSS_HD static constexpr int width(int j) { return lay_width<K, MULTI>(j); }
+    PSS_HD static constexpr int offset(int j) { return lay_offset<K, MULTI>(j); }
+};
+
+struct ScanParams {
+    const u64* primes;     // element 0 of the range to scan
+    u64 count;             // elements
+    u64 n_first;           // global 1-based prime index of element 0
+    u64 n_min, n_max;      // compare window (global indices, inclusive)
+    u32 cmp_mask;          // bit0: S<T matches, bit1: S==T, bit2: S>T
+    u32 target_over_mask;  // bit j: target >= 2^(32*width(j)) -> S_j < target always
+    u32 n_tiles;
+    u32 target[PSS_LIMBS];
+    const u32* carry_in;   // NP * PSS_LIMBS limbs (device)
+    u32* tile_status;      // n_tiles, zeroed before launch
+    u32* tile_agg;         // n_tiles * TOTAL
+    u32* tile_incl;        // n_tiles * TOTAL
+    u32* ticket;           // zeroed before launch
+    pss_power_result* results;  // NP records (device)
+    u32* prefix_out;       // kModePrefix: count * PSS_LIMBS limbs
+    u32* error_flag;
+};
+
+// acc[OFF .. OFF+W) += b[0 .. LB)
+template <int OFF, int W, int LB>
+__device__ __forceinline__ void acc_add(u32* acc, const u32* b) {
+    u64 c = 0;
+#pragma unroll
+    for (int i = 0; i < W; ++i) {
+        u64 t = (u64)acc[OFF + i] + (i < LB ? (u64)b[i] : 0ull) + c;
+        acc[OFF + i] = (u32)t;
+        c = t >> 32;
+    }
+}
+// r[0..W) = a[0..W) - b[0..LB)
+template <int W, int LB>
+__device__ __forceinline__ void limbs_sub(u32* r, const u32* a, const u32* b) {
+    u32 borrow = 0;
+#pragma unroll
+    for (int i = 0; i < W; ++i) {
+        const u64 bi = (i < LB ? (u64)b[i] : 0ull) + borrow;
+        const u64 ai = a[i];
+        r[i] = (u32)(ai - bi);
+        borrow = (ai < bi) ? 1u : 0u;
+    }
+}
+template <int W>
+__device__ __forceinline__ int limbs_cmp(const u32* a, const u32* t) {
+    int res = 0;
+#pragma unroll
+    for (int i = 0; i < W; ++i)
+        if (a[i] != t[i]) res = (a[i] < t[i]) ? -1 : 1;
+    return res;
+}
+
+template <int J, class Lay, class Op>
+__device__ __forceinline__ void for_each_power(Op& op) {
+    if constexpr (J < Lay::NP) {
+        op.template apply<Lay::offset(J), Lay::width(J), J>();
+        for_each_power<J + 1, Lay>(op);
+    }
+}
+
+struct OpShflUpAdd {   // a += shfl_up(a, delta) for lanes >= delta
+    u32* a; int delta; bool active;
+    template <int OFF, int W, int J>
+    __device__ __forceinline__ void apply() {
+        u32 o[W];
+#pragma unroll
+        for (int i = 0; i < W; ++i) o[i] = __shfl_up_sync(0xFFFFFFFFu, a[OFF + i], delta);
+        if (active) acc_add<OFF, W, W>(a, o);
+    }
+};
+struct OpShflXorAdd {  // butterfly reduction step
+    u32* a; int delta;
+    template <int OFF, int W, int J>
+    __device__ __forceinline__ void apply() {
+        u32 o[W];
+#pragma unroll
+        for (int i = 0; i < W; ++i) o[i] = __shfl_xor_sync(0xFFFFFFFFu, a[OFF + i], delta);
+        acc_add<OFF, W, W>(a, o);
+    }
+};
+struct OpAdd {         // a += b (same layout)
+    u32* a; const u32* b;
+    template <int OFF, int W, int J>
+    __device__ __forceinline__ void apply() { acc_add<OFF, W, W>(a, b + OFF); }
+};
+
+struct OpCmpInit {     // three-way compare of every power's prefix with the target
+    const u32* run; const u32* target; u32 over; int* prevc;
+    template <int OFF, int W, int J>
+    __device__ __forceinline__ void apply() {
+        prevc[J] = ((over >> J) & 1u) ? -1 : limbs_cmp<W>(run + OFF, target);
+    }
+};
+
+// ---- power chain ---------------------------------------------------------------------------------
+template <int E, int K, bool MULTI, class F>
+struct ChainStep {
+    __device__ __forceinline__ static void run(const Big<pow_limbs(E)>& pe, u32 plo, u32 phi, F& f) {
+        if constexpr (MULTI || E == K) f.template apply<E>(pe);
+        if constexpr (E < K) {
+            Big<pow_limbs(E + 1)> nx;
+            big_mul_p<pow_limbs(E + 1), pow_limbs(E)>(nx, pe, plo, phi);
+            ChainStep<E + 1, K, MULTI, F>::run(nx, plo, phi, f);
+        }
+    }
+};
+template <int K, bool MULTI, class F>
+__device__ __forceinline__ void power_chain(u64 p, F& f) {
+    Big<2> p1;
+    p1.v[0] = (u32)p;
+    p1.v[1] = (u32)(p >> 32);
+    ChainStep<1, K, MULTI, F>::run(p1, p1.v[0], p1.v[1], f);
+}
+
+template <int K, bool MULTI>
+struct AccFn {
+    using Lay = Layout<K, MULTI>;
+    u32* acc;
+    template <int E>
+    __device__ __forceinline__ void apply(const Big<pow_limbs(E)>& pe) {
+        constexpr int J = MULTI ? E - 1 : 0;
+        acc_add<Lay::offset(J), Lay::width(J), pow_limbs(E)>(acc, pe.v);
+    }
+};
+
+template <int K, bool MULTI, int MODE>
+struct Pass2Fn {
+    using Lay = Layout<K, MULTI>;
+    u32* run;
+    const ScanParams* P;
+    int* prevc;
+    u32* mcount;
+    u32* mfirst;
+    u32* mlast;
+    u64 n, p, elem;
+    u32 local_idx;
+    bool in_window;
+    template <int E>
+    __device__ __forceinline__ void apply(const Big<pow_limbs(E)>& pe) {
+        constexpr int J = MULTI ? E - 1 : 0;
+        constexpr int OFF = Lay::offset(J), W = Lay::width(J);
+        acc_add<OFF, W, pow_limbs(E)>(run, pe.v);
+        if constexpr (MODE == kModePrefix) {
+            u32* o = P->prefix_out + elem * PSS_LIMBS;
+#pragma unroll
+            for (int i = 0; i < PSS_LIMBS; ++i) o[i] = (i < W) ? run[OFF + i] : 0u;
+        } else {
+            const int c = ((P->target_over_mask >> J) & 1u) ? -1 : limbs_cmp<W>(run + OFF, P->target);
+            if (in_window && ((P->cmp_mask >> (c + 1)) & 1u)) {
+                mcount[J] += 1;
+                mfirst[J] = min(mfirst[J], local_idx);
+                mlast[J] = max(mlast[J], local_idx + 1);
+            }
+            if (prevc[J] < 0 && c >= 0) {   // the unique crossing of this power (S is strictly increasing)
+                pss_power_result* r = P->results + J;
+                r->cross_n = n;
+                r->cross_prime = p;
+                u32 before[W];
+                limbs_sub<W, pow_limbs(E)>(before, run + OFF, pe.v);
+#pragma unroll
+                for (int i = 0; i < PSS_LIMBS; ++i) {
+                    r->sum_at_cross[i] = (i < W) ? run[OFF + i] : 0u;
+                    r->sum_before_cross[i] = (i < W) ? before[i] : 0u;
+                }
+            }
+            prevc[J] = c;
+        }
+    }
+};
+
+__device__ __forceinline__ u32 ld_volatile_u32(const u32* p) { return *reinterpret_cast<const volatile u32*>(p); }
+__device__ __forceinline__ void st_volatile_u32(u32* p, u32 v) { *reinterpret_cast<volatile u32*>(p) = v; }
+
+template <int K, bool MULTI, int MODE, int ITEMS>
+__global__ void __launch_bounds__(kScanThreads) k_power_scan(const __grid_constant__ ScanParams P) {
+    using Lay = Layout<K, MULTI>;
+    constexpr int TOTAL = Lay::TOTAL, NP = Lay::NP, T = kScanThreads, NWARP = T / 32, TILE = T * ITEMS;
+    static_assert(NWARP <= 32 && (NWARP & (NWARP - 1)) == 0, "warp count must be a power of two");
+
+    __shared__ u64 s_p[TILE + T];          // element e lives at e + e / ITEMS (bank-conflict padding)
+    __shared__ u32 s_warp[NWARP][TOTAL];   // inclusive warp totals, then exclusive warp offsets
+    __shared__ u32 s_excl[TOTAL];          // tile exclusive prefix (includes carry-in)
+    __shared__ u32 s_tile;
+
+    const u32 tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+
+    for (;;) {
+        if (tid == 0) s_tile = atomicAdd(P.ticket, 1u);
+        __syncthreads();
+        const u32 tile = s_tile;
+        if (tile >= P.n_tiles) break;
+        const u64 base = (u64)tile * TILE;
+
+        // ---- coalesced load -> padded shared memory (blocked order for the owner threads)
+#pragma unroll
+        for (int r = 0; r < ITEMS; ++r) {
+            const u32 e = r * T + tid;
+            const u64 g = base + e;
+            s_p[e + e / ITEMS] = (g < P.count) ? P.primes[g] : 0ull;
+        }
+        __syncthreads();
+
+        // ---- pass 1: thread-local sums of p^k
+        u32 acc[TOTAL];
+#pragma unroll
+        for (int i = 0; i < TOTAL; ++i) acc[i] = 0;
+        {
+            AccFn<K, MULTI> fn{acc};
+#pragma unroll 2
+            for (int i = 0; i < ITEMS; ++i) power_chain<K, MULTI>(s_p[tid * (ITEMS + 1) + i], fn);
+        }
+        // ---- warp inclusive scan (multi-limb adds with carry), exclusive value for this lane
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            OpShflUpAdd op{acc, d, lane >= (u32)d};
+            for_each_power<0, Lay>(op);
+        }
+        if (lane == 31) {
+#pragma unroll
+            for (int i = 0; i < TOTAL; ++i) s_warp[warp][i] = acc[i];
+        }
+        u32 run[TOTAL];   // becomes this thread's exclusive prefix
+#pragma unroll
+        for (int i = 0; i < TOTAL; ++i) {
+            const u32 up = __shfl_up_sync(0xFFFFFFFFu, acc[i], 1);
+            run[i] = lane ? up : 0u;
+        }
+        __syncthreads();
+
+        if (warp == 0) {
+            // scan of the warp totals
+            u32 wi[TOTAL];
+#pragma unroll
+            for (int i = 0; i < TOTAL; ++i) wi[i] = (lane < NWARP) ? s_warp[lane][i] : 0u;
+#pragma unroll
+            for (int d = 1; d < NWARP; d <<= 1) {
+                OpShflUpAdd op{wi, d, lane >= (u32)d};
+                for_each_power<0, Lay>(op);
+            }
+            u32 agg[TOTAL];
+#pragma unroll
+            for (int i = 0; i < TOTAL; ++i) {
+                agg[i] = __shfl_sync(0xFFFFFFFFu, wi[i], NWARP - 1);
+                const u32 up = __shfl_up_sync(0xFFFFFFFFu, wi[i], 1);
+                if (lane < NWARP) s_warp[lane][i] = lane ? up : 0u;
+            }
+            if (tile > 0 && lane == 0) {
+                u32* a = P.tile_agg + (u64)tile * TOTAL;
+#pragma unroll
+                for (int i = 0; i < TOTAL; ++i) a[i] = agg[i];
+                __threadfence();
+                st_volatile_u32(P.tile_status + tile, 1u);
+            }
+            // ---- decoupled look-back: 32 predecessors per window
+            u32 excl[TOTAL];
+#pragma unroll
+            for (int i = 0; i < TOTAL; ++i) excl[i] = 0;
+            long long j = (long long)tile - 1;
+            for (;;) {
+                const long long idx = j - (long long)lane;
+                u32 st = 2u;
+                if (idx >= 0) {
+                    u32 spins = 0;
+                    while ((st = ld_volatile_u32(P.tile_status + idx)) == 0u) {
+                        if (++spins > kSpinLimit) {
+                            atomicExch(P.error_flag, 1u);
+                            st = 2u;
+                            break;
+                        }
+                        if (spins > 16) __nanosleep(40);
+                    }
+                }
+                const u32 incl_mask = __ballot_sync(0xFFFFFFFFu, st == 2u);
+                const int first = incl_mask ? (__ffs(incl_mask) - 1) : 32;
+                __threadfence();
+                u32 val[TOTAL];
+#pragma unroll
+                for (int i = 0; i < TOTAL; ++i) val[i] = 0;
+                if ((int)lane < first) {
+                    const u32* a = P.tile_agg + (u64)idx * TOTAL;
+#pragma unroll
+                    for (int i = 0; i < TOTAL; ++i) val[i] = ld_volatile_u32(a + i);
+                } else if ((int)lane == first) {
+                    if (idx >= 0) {
+                        const u32* a = P.tile_incl + (u64)idx * TOTAL;
+#pragma unroll
+                        for (int i = 0; i < TOTAL; ++i) val[i] = ld_volatile_u32(a + i);
+                    } else if (idx == -1) {
+                        // carry-in of the slice = "inclusive prefix of tile -1"
+#pragma unroll
+                        for (int jj = 0; jj < NP; ++jj)
+#pragma unroll
+                            for (int i = 0; i < PSS_LIMBS; ++i)
+                                if (i < Lay::width(jj)) val[Lay::offset(jj) + i] = P.carry_in[jj * PSS_LIMBS + i];
+                    }
+                }
+#pragma unroll
+                for (int d = 16; d >= 1; d >>= 1) {
+                    OpShflXorAdd op{val, d};
+                    for_each_power<0, Lay>(op);
+                }
+                {
+                    OpAdd op{excl, val};
+                    for_each_power<0, Lay>(op);
+                }
+                if (incl_mask) break;
+                j -= 32;
+            }
+            // inclusive prefix of this tile
+            {
+                OpAdd op{agg, excl};
+                for_each_power<0, Lay>(op);
+            }
+            if (lane == 0) {
+                u32* a = P.tile_incl + (u64)tile * TOTAL;
+#pragma unroll
+                for (int i = 0; i < TOTAL; ++i) {
+                    a[i] = agg[i];
+                    s_excl[i] = excl[i];
+                }
+                __threadfence();
+                st_volatile_u32(P.tile_status + tile, 2u);
+                if (tile == P.n_tiles - 1) {
+#pragma unroll
+                    for (int jj = 0; jj < NP; ++jj)
+#pragma unroll
+                        for (int i = 0; i < PSS_LIMBS; ++i)
+                            P.results[jj].final_sum[i] = (i < Lay::width(jj)) ? agg[Lay::offset(jj) + i] : 0u;
+                }
+            }
+        }
+        __syncthreads();
+
+        if constexpr (MODE != kModeReduce) {
+            // ---- pass 2: exact exclusive prefix of this thread, then every S_k(n) formed and compared
+            {
+                OpAdd op1{run, s_excl};
+                for_each_power<0, Lay>(op1);
+                OpAdd op2{run, s_warp[warp]};
+                for_each_power<0, Lay>(op2);
+            }
+            int prevc[NP];
+            u32 mcount[NP], mfirst[NP], mlast[NP];
+#pragma unroll
+            for (int jj = 0; jj < NP; ++jj) {
+                mcount[jj] = 0;
+                mfirst[jj] = 0xFFFFFFFFu;
+                mlast[jj] = 0;
+                prevc[jj] = 0;
+            }
+            if constexpr (MODE == kModeCompare) {
+                OpCmpInit op{run, P.target, P.target_over_mask, prevc};
+                for_each_power<0, Lay>(op);
+            }
+            Pass2Fn<K, MULTI, MODE> fn{run, &P, prevc, mcount, mfirst, mlast, 0, 0, 0, 0, false};
+#pragma unroll 2
+            for (int i = 0; i < ITEMS; ++i) {
+                const u64 p = s_p[tid * (ITEMS + 1) + i];
+                if (p == 0) continue;   // padding past the end of the range
+                const u32 li = tid * ITEMS + i;
+                fn.local_idx = li;
+                fn.elem = base + li;
+                fn.n = P.n_first + base + li;
+                fn.p = p;
+                fn.in_window = (fn.n >= P.n_min) && (fn.n <= P.n_max);
+                power_chain<K, MULTI>(p, fn);
+            }
+            if constexpr (MODE == kModeCompare) {
+#pragma unroll
+                for (int jj = 0; jj < NP; ++jj) {
+                    if (__any_sync(0xFFFFFFFFu, mcount[jj] != 0)) {
+                        const u32 c = __reduce_add_sync(0xFFFFFFFFu, mcount[jj]);
+                        const u32 f = __reduce_min_sync(0xFFFFFFFFu, mfirst[jj]);
+                        const u32 l = __reduce_max_sync(0xFFFFFFFFu, mlast[jj]);
+                        if (lane == 0) {
+                            pss_power_result* r = P.results + jj;
+                            atomicAdd(reinterpret_cast<unsigned long long*>(&r->match_count), (unsigned long long)c);
+                            atomicMin(reinterpret_cast<unsigned long long*>(&r->first_match_n),
+                                      (unsigned long long)(P.n_first + base + f));
+                            atomicMax(reinterpret_cast<unsigned long long*>(&r->last_match_n),
+                                      (unsigned long long)(P.n_first + base + l - 1));
+                        }
+                    }
+                }
+            }
+        }
+        __syncthreads();   // shared memory is reused by the next tile
+    }
+}
+
+}  // namespace pss

@@ -1,0 +1,314 @@
+// pss_sieve.cuh — K1: segmented, bit-packed, wheel-30 sieve of Eratosthenes for sm_100a.
+//
+// Replaces (behaviour, not code) primesieve.* / _basic_sieve / _segmented_sieve of the reference
+// (utils/sieve.py:224-327 and the primesieve call sites :499-639): "all primes in [lo, hi)".
+//
+//   k_build_pattern   once per handle: pre-sieved periodic byte patterns for the tiny primes
+//                     {7,11,13,17,19} {23,29,31} {37,41,43} {47,53,59}; 16x replicated so every tile
+//                     start (16-byte aligned) maps to a 16-byte aligned pattern offset (L2 resident).
+//   k_sieve           one shared-memory tile per CTA per segment.  Tile init = AND of the patterns
+//                     (uint4), then every base prime p >= 61 (staged once in HBM/L2) is crossed off by
+//                     shared-memory atomicAnd on the packed words: 8 strands per prime (one per wheel
+//                     residue of the cofactor), each a byte-stride-p progression with a fixed bit.
+//                     Work split by hits-per-tile: CTA-wide (densest primes), warp-wide, 8-lane groups.
+//                     Tiles are independent (first offsets are recomputed from the tile base), so any CTA
+//                     on any GPU can take any tile.  Output: bitmap tile (coalesced uint4 stores) +
+//                     per-chunk and per-tile popcounts.
+//   k_scan_tile_counts single CTA exclusive scan of the per-tile counts (<= a few 10^4 values).
+//   k_compact         popc + block scan stream compaction of bitmap chunks into the coalesced u64 prime
+//                     buffer (staged through shared memory so global stores are fully coalesced).
+#pragma once
+#include "pss_common.cuh"
+
+namespace pss {
+
+constexpr int kMaxPatterns = 4;
+constexpr int kMaxCtaWide = 64;   // primes handled by the whole CTA per tile
+
+struct SieveParams {
+    u64 lo, hi;          // value range [lo, hi)
+    u64 B_start;         // absolute byte index of bitmap byte 0 (multiple of 16)
+    u32 tile_bytes;      // multiple of kChunkBytes
+    u32 n_tiles;
+    const u32* base_primes;  // ascending, first entry = smallest prime not covered by a pattern
+    u32 n_base;
+    u32 n_cta_wide;      // base_primes[0 .. n_cta_wide) handled CTA-wide
+    u32 n_warp_wide;     // base_primes[n_cta_wide .. n_warp_wide) handled warp-wide, the rest by 8-lane groups
+    u32 n_pat;
+    const uint4* pat[kMaxPatterns];
+    u64 pat_period16[kMaxPatterns];   // 16 * period (bytes)
+    u32* bitmap;         // n_tiles * tile_bytes / 4 words
+    u32* chunk_counts;   // n_tiles * tile_bytes / kChunkBytes
+    u32* tile_counts;    // n_tiles
+};
+
+// ---- pattern construction -------------------------------------------------------------------
+// pattern byte i (absolute byte index i mod period): bit j cleared iff 30*i + R[j] is divisible by one
+// of the group's primes.  (The primes themselves are cleared too; k_sieve restores bytes 0 and 1.)
+__global__ void k_build_pattern(uint8_t* out, u64 n_bytes, u32 q0, u32 q1, u32 q2, u32 q3, u32 q4) {
+    u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    u64 stride = (u64)gridDim.x * blockDim.x;
+    const u32 qs[5] = {q0, q1, q2, q3, q4};
+    for (; i < n_bytes; i += stride) {
+        u32 m = 0xFF;
+#pragma unroll
+        for (u32 j = 0; j < 8; ++j) {
+            u64 v = i * 30ull + wheel_residue(j);
+#pragma unroll
+            for (int k = 0; k < 5; ++k)
+                if (qs[k] && (v % qs[k]) == 0) m &= ~(1u << j);
+        }
+        out[i] = (uint8_t)m;
+    }
+}
+
+__device__ __forceinline__ u32 mod_u64_u32(u64 a, u32 p) {
+    // tile byte indices fit 32 bits up to 1.28e11; keep the cheap path cheap
+    return ((a >> 32) == 0) ? ((u32)a % p) : (u32)(a % p);
+}
+
+__device__ __forceinline__ void strike(u32* tile, u32 x, u32 bit) {
+    atomicAnd(&tile[x >> 2], ~(1u << (((x & 3u) << 3) + bit)));
+}
+
+template <int THREADS>
+__global__ void __launch_bounds__(THREADS) k_sieve(const SieveParams P) {
+    extern __shared__ uint4 smem4[];
+    u32* tile = reinterpret_cast<u32*>(smem4);
+    __shared__ u32 s_r[kMaxCtaWide];
+    __shared__ u64 s_off16[kMaxPatterns];
+    __shared__ u32 s_cnt[THREADS / 32];
+
+    const u32 tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+    constexpr u32 NW = THREADS / 32;
+    const u32 tile_bytes = P.tile_bytes;
+    const u32 tile_vec = tile_bytes >> 4;
+    const u32 chunks_per_tile = tile_bytes / kChunkBytes;
+
+    for (u32 t = blockIdx.x; t < P.n_tiles; t += gridDim.x) {
+        const u64 B0 = P.B_start + (u64)t * tile_bytes;
+        // largest base prime that can still have an unmarked multiple in this tile: p*p < tile end
+        const double tile_end = (double)(B0 + tile_bytes) * 30.0;
+        const u32 plim = (u32)fmin(sqrt(tile_end) + 2.0, 4.0e9);
+
+        if (tid < P.n_pat) s_off16[tid] = (B0 % P.pat_period16[tid]) >> 4;
+        if (tid < P.n_cta_wide) s_r[tid] = mod_u64_u32(B0, P.base_primes[tid]);
+        __syncthreads();
+
+        // ---- phase A: tile init from the pre-sieved patterns
+        for (u32 i = tid; i < tile_vec; i += THREADS) {
+            uint4 v = make_uint4(~0u, ~0u, ~0u, ~0u);
+            for (u32 k = 0; k < P.n_pat; ++k) {
+                uint4 w = __ldg(P.pat[k] + s_off16[k] + i);
+                v.x &= w.x; v.y &= w.y; v.z &= w.z; v.w &= w.w;
+            }
+            smem4[i] = v;
+        }
+        __syncthreads();
+
+        // ---- phase B1: densest primes, whole CTA per prime (lane -> strand, tid/8 -> sub-sequence)
+        {
+            const u32 j = tid & 7u, sub = tid >> 3;
+            constexpr u32 NSUB = THREADS / 8;
+            for (u32 i = 0; i < P.n_cta_wide; ++i) {
+                const u32 p = P.base_primes[i];
+                if (p > plim) break;
+                u32 c, bit;
+                strand_geometry(p, j, c, bit);
+                u32 x = strand_first_offset(p, j, c, B0, s_r[i]) + sub * p;
+                const u32 stride = NSUB * p;
+                for (; x < tile_bytes; x += stride) strike(tile, x, bit);
+            }
+        }
+        // ---- phase B2: medium primes, one warp per prime (4 sub-sequences x 8 strands)
+        {
+            const u32 j = lane & 7u, sub = lane >> 3;
+            for (u32 i = P.n_cta_wide + warp; i < P.n_warp_wide; i += NW) {
+                const u32 p = P.base_primes[i];
+                if (p > plim) break;
+                const u32 r = mod_u64_u32(B0, p);
+                u32 c, bit;
+                strand_geometry(p, j, c, bit);
+                u32 x = strand_first_offset(p, j, c, B0, r) + sub * p;
+                const u32 stride = 4u * p;
+                for (; x < tile_bytes; x += stride) strike(tile, x, bit);
+            }
+        }
+        // ---- phase B3: sparse primes, 8 lanes (one per strand) per prime
+        {
+            const u32 j = tid & 7u;
+            constexpr u32 NG = THREADS / 8;
+            for (u32 i = P.n_warp_wide + (tid >> 3); i < P.n_base; i += NG) {
+                const u32 p = P.base_primes[i];
+                if (p > plim) break;
+                const u32 r = mod_u64_u32(B0, p);
+                u32 c, bit;
+                strand_geometry(p, j, c, bit);
+                u32 x = strand_first_offset(p, j, c, B0, r);
+                for (; x < tile_bytes; x += p) strike(tile, x, bit);
+            }
+        }
+        __syncthreads();
+
+        // ---- phase C: edge masks, popcounts, coalesced write-out of the bitmap tile
+        const bool interior = (B0 * 30ull >= P.lo) && ((B0 + tile_bytes) * 30ull <= P.hi) && (B0 >= 4);
+        u32 my_tile_cnt = 0;
+        uint4* gout = reinterpret_cast<uint4*>(P.bitmap) + (u64)t * tile_vec;
+        for (u32 ch = warp; ch < chunks_per_tile; ch += NW) {
+            u32 cnt = 0;
+#pragma unroll
+            for (u32 h = 0; h < 2; ++h) {
+                const u32 vi = ch * (kChunkWords / 4) + h * 32u + lane;
+                uint4 v = smem4[vi];
+                if (!interior) {
+                    u32 w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+                    for (u32 k = 0; k < 4; ++k) {
+                        const u64 Bw = B0 + (u64)vi * 16ull + 4ull * k;
+                        u32 x = w[k];
+                        if (Bw == 0) x = (x & 0xFFFF0000u) | 0xDFFEu;  // 7..59 are prime, 1 and 49 are not
+                        u32 m = edge_byte_mask(Bw, P.lo, P.hi) | (edge_byte_mask(Bw + 1, P.lo, P.hi) << 8) |
+                                (edge_byte_mask(Bw + 2, P.lo, P.hi) << 16) | (edge_byte_mask(Bw + 3, P.lo, P.hi) << 24);
+                        w[k] = x & m;
+                    }
+                    v = make_uint4(w[0], w[1], w[2], w[3]);
+                }
+                gout[vi] = v;
+                cnt += __popc(v.x) + __popc(v.y) + __popc(v.z) + __popc(v.w);
+            }
+            cnt = __reduce_add_sync(0xFFFFFFFFu, cnt);
+            if (lane == 0) P.chunk_counts[(u64)t * chunks_per_tile + ch] = cnt;
+            my_tile_cnt += cnt;  // identical in every lane
+        }
+        if (lane == 0) s_cnt[warp] = my_tile_cnt;
+        __syncthreads();
+        if (tid == 0) {
+            u32 s = 0;
+            for (u32 w = 0; w < NW; ++w) s += s_cnt[w];
+            P.tile_counts[t] = s;
+        }
+        // s_r / s_off16 / s_cnt / tile are rewritten only after the next iteration's first barrier
+        __syncthreads();
+    }
+}
+
+// ---- K1b: exclusive scan of per-tile counts (u32 -> u64), single CTA ----------------------------
+// prefix[t] = init + sum_{i<t} counts[i];  prefix[n] = grand total.
+__global__ void __launch_bounds__(1024) k_scan_tile_counts(const u32* counts, u32 n, u64 init, u64* prefix) {
+    __shared__ u64 s_warp[32];
+    __shared__ u64 s_running;
+    const u32 tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+    if (tid == 0) s_running = init;
+    __syncthreads();
+    for (u32 base = 0; base < n; base += 1024) {
+        const u32 i = base + tid;
+        const u64 v = (i < n) ? counts[i] : 0;
+        u64 incl = v;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            u64 o = __shfl_up_sync(0xFFFFFFFFu, incl, d);
+            if (lane >= (u32)d) incl += o;
+        }
+        if (lane == 31) s_warp[warp] = incl;
+        __syncthreads();
+        if (warp == 0) {
+            u64 w = s_warp[lane];
+            u64 wi = w;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                u64 o = __shfl_up_sync(0xFFFFFFFFu, wi, d);
+                if (lane >= (u32)d) wi += o;
+            }
+            s_warp[lane] = wi - w;  // exclusive warp offsets
+        }
+        __syncthreads();
+        const u64 run = s_running;
+        const u64 excl = run + s_warp[warp] + incl - v;
+        if (i < n) prefix[i] = excl;
+        __syncthreads();
+        if (tid == 1023) s_running = excl + v;
+        __syncthreads();
+    }
+    if (tid == 0) prefix[n] = s_running;
+}
+
+// ---- K1c: compaction of bitmap chunks into the u64 prime buffer ----------------------------------
+// CTA (256 threads) <-> groups of `group` consecutive chunks of one tile; thread <-> word.
+struct CompactParams {
+    const u32* bitmap;
+    const u32* chunk_counts;
+    const u64* tile_prefix;   // exclusive prefix of tile counts (includes the 2,3,5 offset)
+    u32 chunks_per_tile;
+    u32 group;                // chunks per CTA work item (divides chunks_per_tile)
+    u32 n_groups;             // total work items = n_tiles * chunks_per_tile / group
+    u64 B_start;
+    u64* out;
+    u64 out_cap;              // only indices < out_cap are written (first-n truncation)
+    u32* error_flag;
+};
+
+__global__ void __launch_bounds__(256) k_compact(const CompactParams P) {
+    __shared__ u64 stage[kMaxChunkPrimes];
+    __shared__ u32 s_wsum[8];
+    __shared__ u32 s_pre[8];
+    const u32 tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+    const u32 groups_per_tile = P.chunks_per_tile / P.group;
+
+    for (u32 g = blockIdx.x; g < P.n_groups; g += gridDim.x) {
+        const u32 t = g / groups_per_tile;
+        const u32 c0 = (g - t * groups_per_tile) * P.group;   // first chunk (within tile) of this item
+        const u64 chunk0 = (u64)t * P.chunks_per_tile + c0;
+        // prefix of the first chunk = tile prefix + counts of the tile's earlier chunks
+        u32 pre = 0;
+        for (u32 i = tid; i < c0; i += 256) pre += P.chunk_counts[(u64)t * P.chunks_per_tile + i];
+        pre = __reduce_add_sync(0xFFFFFFFFu, pre);
+        if (lane == 0) s_pre[warp] = pre;
+        __syncthreads();
+        u64 base = P.tile_prefix[t];
+#pragma unroll
+        for (u32 w = 0; w < 8; ++w) base += s_pre[w];
+        if (base >= P.out_cap) { __syncthreads(); continue; }
+
+        for (u32 c = 0; c < P.group; ++c) {
+            const u64 widx = (chunk0 + c) * kChunkWords + tid;
+            u32 w = P.bitmap[widx];
+            const u32 cnt = __popc(w);
+            u32 incl = cnt;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                u32 o = __shfl_up_sync(0xFFFFFFFFu, incl, d);
+                if (lane >= (u32)d) incl += o;
+            }
+            if (lane == 31) s_wsum[warp] = incl;
+            __syncthreads();
+            u32 woff = 0, total = 0;
+#pragma unroll
+            for (u32 k = 0; k < 8; ++k) {
+                const u32 s = s_wsum[k];
+                if (k < warp) woff += s;
+                total += s;
+            }
+            if (total > kMaxChunkPrimes) {  // cannot happen for a correctly sieved bitmap
+                if (tid == 0) atomicExch(P.error_flag, 2u);
+                total = kMaxChunkPrimes;
+            }
+            u32 off = woff + incl - cnt;
+            const u64 Bw = P.B_start + widx * 4ull;
+            while (w) {
+                const u32 b = __ffs(w) - 1;
+                w &= w - 1;
+                if (off < kMaxChunkPrimes) stage[off] = word_bit_value(Bw, b);
+                ++off;
+            }
+            __syncthreads();
+            for (u32 i = tid; i < total; i += 256) {
+                const u64 o = base + i;
+                if (o < P.out_cap) P.out[o] = stage[i];
+            }
+            base += total;
+            __syncthreads();
+        }
+    }
+}
+
+}  // namespace pss
