@@ -153,6 +153,12 @@ int pss_slice_primes(pss_handle* h, uint64_t first, uint64_t count, uint64_t* ou
 /* raw device pointer + count of the resident prime buffer (for zero-copy consumers, e.g. torch.from_blob) */
 int pss_slice_device_buffer(pss_handle* h, void** dev_ptr, uint64_t* count);
 
+/* per-kernel device time (CUDA events on the handle's stream) accumulated over all calls since the last
+ * reset; ms_total_device = sum of the four kernel phases.  (The reference only has wall-clock timing:
+ * prime-square-sum.py:342,450-457.) */
+int pss_stats_reset(pss_handle* h);
+int pss_stats_get(pss_handle* h, pss_stats* out);
+
 /* upper bound for the n-th prime used to size the sieve (n >= 1) */
 uint64_t pss_nth_prime_upper(uint64_t n);
 

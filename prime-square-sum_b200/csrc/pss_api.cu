@@ -91,6 +91,7 @@ struct pss_handle {
 
     cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     u64 launches = 0;
+    pss_stats acc = {};          // accumulated per-kernel device time since pss_stats_reset
 };
 
 namespace {
@@ -157,6 +158,15 @@ u64 isqrt_u64(u64 x) {
     while (r * r > x) --r;
     while ((r + 1) * (r + 1) <= x) ++r;
     return r;
+}
+
+double ev_ms(pss_handle* h, int a, int b) {
+    float ms = 0;
+    if (cudaEventElapsedTime(&ms, h->ev[a], h->ev[b]) != cudaSuccess) {
+        cudaGetLastError();
+        return 0.0;
+    }
+    return ms;
 }
 
 // ---- base primes (staged once, regrown only when a larger sqrt(hi) is needed) --------------------
@@ -307,6 +317,10 @@ int sieve_range(pss_handle* h, u64 lo, u64 hi) {
 
     h->sv_lo = lo; h->sv_hi = hi; h->sv_B_start = B_start; h->sv_total = total; h->sv_c235 = c235;
     h->sv_tile_bytes = tile_bytes; h->sv_n_tiles = n_tiles; h->sv_valid = true;
+    h->acc.ms_sieve += ev_ms(h, 0, 1);
+    h->acc.ms_count_scan += ev_ms(h, 1, 2);
+    h->acc.sieve_lo = lo;
+    h->acc.sieve_hi = hi;
     return PSS_OK;
 }
 
@@ -321,6 +335,7 @@ int compact_resident(pss_handle* h, u64 cap) {
     }
     PSS_TRY(ensure(h, h->primes, (size_t)n_out * sizeof(u64)));
     u64* out = static_cast<u64*>(h->primes.p);
+    CU_TRY(h, cudaEventRecord(h->ev[2], h->stream));
     if (h->sv_c235) {
         u64 small[3];
         u32 k = 0;
@@ -358,6 +373,7 @@ int compact_resident(pss_handle* h, u64 cap) {
     if (flag) return fail(h, PSS_EINTERNAL, "compaction overflow (flag %u): bitmap is not a valid sieve", flag);
     h->n_resident = n_out;
     h->resident_last = last;
+    h->acc.ms_compact += ev_ms(h, 2, 3);
     return PSS_OK;
 }
 
@@ -485,16 +501,9 @@ int run_scan(pss_handle* h, const u64* d_vals, u64 count, u64 n_first, const u32
         out[j] = hm->results[j];
         if (out[j].match_count == 0) out[j].first_match_n = 0, out[j].last_match_n = 0;
     }
+    h->acc.ms_power_scan += ev_ms(h, 4, 5);
+    h->acc.primes += count;
     return PSS_OK;
-}
-
-double ev_ms(pss_handle* h, int a, int b) {
-    float ms = 0;
-    if (cudaEventElapsedTime(&ms, h->ev[a], h->ev[b]) != cudaSuccess) {
-        cudaGetLastError();
-        return 0.0;
-    }
-    return ms;
 }
 
 int check_handle(pss_handle* h) {
@@ -720,21 +729,23 @@ int pss_primesum(pss_handle* h, uint64_t n, uint32_t power, uint32_t* limbs_out)
     return PSS_OK;
 }
 
-static void fill_stats(pss_handle* h, pss_stats* s, u64 launches0, u64 primes, bool sieved) {
+static pss_stats stats_snapshot(pss_handle* h) {
+    pss_stats s = h->acc;
+    s.launches = h->launches;
+    return s;
+}
+static void fill_stats(pss_handle* h, pss_stats* s, const pss_stats& before) {
+    const pss_stats now = stats_snapshot(h);
     memset(s, 0, sizeof *s);
-    if (sieved) {
-        s->ms_sieve = ev_ms(h, 0, 1);
-        s->ms_count_scan = ev_ms(h, 1, 2);
-        s->ms_compact = ev_ms(h, 2, 3);
-        s->ms_total_device = ev_ms(h, 0, 5);
-        s->sieve_lo = h->sv_lo;
-        s->sieve_hi = h->sv_hi;
-    } else {
-        s->ms_total_device = ev_ms(h, 4, 5);
-    }
-    s->ms_power_scan = ev_ms(h, 4, 5);
-    s->primes = primes;
-    s->launches = h->launches - launches0;
+    s->ms_sieve = now.ms_sieve - before.ms_sieve;
+    s->ms_count_scan = now.ms_count_scan - before.ms_count_scan;
+    s->ms_compact = now.ms_compact - before.ms_compact;
+    s->ms_power_scan = now.ms_power_scan - before.ms_power_scan;
+    s->ms_total_device = s->ms_sieve + s->ms_count_scan + s->ms_compact + s->ms_power_scan;
+    s->primes = now.primes - before.primes;
+    s->sieve_lo = now.sieve_lo;
+    s->sieve_hi = now.sieve_hi;
+    s->launches = now.launches - before.launches;
 }
 
 static int validate_search(pss_handle* h, const pss_search_args* a, pss_search_result* res) {
@@ -749,7 +760,7 @@ static int validate_search(pss_handle* h, const pss_search_args* a, pss_search_r
 int pss_search(pss_handle* h, const pss_search_args* a, pss_search_result* res) {
     PSS_TRY(check_handle(h));
     PSS_TRY(validate_search(h, a, res));
-    const u64 launches0 = h->launches;
+    const pss_stats before = stats_snapshot(h);
     memset(res, 0, sizeof *res);
     PSS_TRY(sieve_first_n(h, a->n_max));
     const bool multi = a->all_powers && a->power_max > 1;
@@ -758,7 +769,7 @@ int pss_search(pss_handle* h, const pss_search_args* a, pss_search_result* res) 
     res->n_powers = n_powers_of(a->power_max, multi);
     res->primes_scanned = a->n_max;
     res->last_prime = h->resident_last;
-    fill_stats(h, &res->stats, launches0, a->n_max, true);
+    fill_stats(h, &res->stats, before);
     return PSS_OK;
 }
 
@@ -781,7 +792,7 @@ int pss_slice_scan(pss_handle* h, uint64_t first, uint64_t count, uint64_t n_fir
     PSS_TRY(validate_search(h, a, res));
     if (first + count > h->n_resident) return fail(h, PSS_EINVAL, "range [%llu,+%llu) outside the %llu resident primes", (unsigned long long)first,
                                                     (unsigned long long)count, (unsigned long long)h->n_resident);
-    const u64 launches0 = h->launches;
+    const pss_stats before = stats_snapshot(h);
     memset(res, 0, sizeof *res);
     const bool multi = a->all_powers && a->power_max > 1;
     PSS_TRY(run_scan(h, static_cast<const u64*>(h->primes.p) + first, count, n_first, carry_in, a->power_max, multi, kModeCompare, a->n_min, a->n_max,
@@ -793,7 +804,7 @@ int pss_slice_scan(pss_handle* h, uint64_t first, uint64_t count, uint64_t n_fir
         CU_TRY(h, cudaMemcpy(&last, static_cast<const u64*>(h->primes.p) + first + count - 1, sizeof(u64), cudaMemcpyDeviceToHost));
         res->last_prime = last;
     }
-    fill_stats(h, &res->stats, launches0, count, false);
+    fill_stats(h, &res->stats, before);
     return PSS_OK;
 }
 
@@ -817,6 +828,21 @@ int pss_slice_primes(pss_handle* h, uint64_t first, uint64_t count, uint64_t* ou
     if (!out_host) return fail(h, PSS_EINVAL, "null output");
     if (first + count > h->n_resident) return fail(h, PSS_EINVAL, "range outside the resident primes");
     CU_TRY(h, cudaMemcpy(out_host, static_cast<const u64*>(h->primes.p) + first, (size_t)count * sizeof(u64), cudaMemcpyDeviceToHost));
+    return PSS_OK;
+}
+
+int pss_stats_reset(pss_handle* h) {
+    PSS_TRY(check_handle(h));
+    memset(&h->acc, 0, sizeof h->acc);
+    h->launches = 0;
+    return PSS_OK;
+}
+
+int pss_stats_get(pss_handle* h, pss_stats* out) {
+    PSS_TRY(check_handle(h));
+    if (!out) return fail(h, PSS_EINVAL, "null output");
+    *out = stats_snapshot(h);
+    out->ms_total_device = out->ms_sieve + out->ms_count_scan + out->ms_compact + out->ms_power_scan;
     return PSS_OK;
 }
 

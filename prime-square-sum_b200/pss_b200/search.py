@@ -1,0 +1,297 @@
+"""
+search.py — the fused query path: `does_exist / for_any  primesum(n, p) <op> <constant>`.
+
+Replaces the reference's O(n^2) host loop (utils/grammar.py:937-999 find_matches calling
+utils/sequences.py:30-75 once per n) by ONE device pass: sieve -> compaction -> power + scan + compare.
+Results are reported exactly as the reference would enumerate them: variables iterate alphabetically,
+first variable outermost (utils/grammar.py:939,977), so `primesum(n,p)` walks n outer / p inner and
+`does_exist` stops at the first hit (:987-988).
+
+Multi-GPU: the value range [2, N) is cut into G contiguous slices balanced by the
+li(x) prime-count estimate; every rank sieves and reduces its slice independently, ONE tiny allgather
+of (count, per-power sums) over NCCL gives each rank its index offset and limb carry, then the rank scans
+its slice with that carry.  Nothing else crosses NVLink.
+"""
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass, field
+from typing import Dict, Iterator, List, Optional, Sequence, Tuple
+
+from . import _lib
+
+OPS = ("==", "!=", "<", "<=", ">", ">=")
+
+
+@dataclass
+class PowerOutcome:
+    power: int
+    match_count: int
+    first_match_n: int          # 0 = none
+    last_match_n: int
+    cross_n: int                # first n with S(n) >= target (0: every scanned S(n) < target)
+    cross_prime: int
+    sum_at_cross: int
+    sum_before_cross: int
+    final_sum: int              # S(n_max)
+
+
+@dataclass
+class SearchOutcome:
+    n_min: int
+    n_max: int
+    op: str
+    target: int
+    last_prime: int
+    powers: List[PowerOutcome]
+    stats: Dict[str, float] = field(default_factory=dict)
+
+    def matches(self, limit: Optional[int] = None) -> Iterator[Tuple[int, int]]:
+        """(n, power) pairs in the reference's iteration order (n outer, p inner)."""
+        yield from _enumerate_matches(self, limit)
+
+    def first(self) -> Optional[Tuple[int, int]]:
+        for m in self.matches(limit=1):
+            return m
+        return None
+
+    def bracket(self, power: Optional[int] = None) -> Tuple[int, int]:
+        """(n_below, n_at_or_above): largest n with S(n) < target and the following index (n_max+1 if none)."""
+        po = self.powers[0] if power is None else next(p for p in self.powers if p.power == power)
+        if po.cross_n:
+            return po.cross_n - 1, po.cross_n
+        return self.n_max, self.n_max + 1
+
+
+def _cmp(a: int, b: int) -> int:
+    return (a > b) - (a < b)
+
+
+_HOLDS = {"==": lambda c: c == 0, "!=": lambda c: c != 0, "<": lambda c: c < 0, "<=": lambda c: c <= 0,
+          ">": lambda c: c > 0, ">=": lambda c: c >= 0}
+
+
+def _match_ranges(o: SearchOutcome, po: PowerOutcome) -> List[Tuple[int, int]]:
+    """Inclusive index ranges of n where S(n) <op> target.  S is strictly increasing, so the device's
+    (count, first, last, crossing) describe them completely."""
+    if po.match_count == 0:
+        return []
+    if o.op == "!=" and po.match_count != po.last_match_n - po.first_match_n + 1:
+        # everything except the single n with S(n) == target
+        eq = po.cross_n
+        out = []
+        if po.first_match_n <= eq - 1:
+            out.append((po.first_match_n, eq - 1))
+        if eq + 1 <= po.last_match_n:
+            out.append((eq + 1, po.last_match_n))
+        return out
+    return [(po.first_match_n, po.last_match_n)]
+
+
+def _enumerate_matches(o: SearchOutcome, limit: Optional[int]) -> Iterator[Tuple[int, int]]:
+    ranges = {po.power: _match_ranges(o, po) for po in o.powers}
+    if not any(ranges.values()):
+        return
+    emitted = 0
+    if len(o.powers) == 1:
+        p = o.powers[0].power
+        for lo, hi in ranges[p]:
+            for n in range(lo, hi + 1):
+                yield (n, p)
+                emitted += 1
+                if limit is not None and emitted >= limit:
+                    return
+        return
+    # several powers: merge by n (outer) then p (inner)
+    lo_all = min(r[0][0] for r in ranges.values() if r)
+    hi_all = max(r[-1][1] for r in ranges.values() if r)
+    n = lo_all
+    while n <= hi_all:
+        hit = False
+        for po in o.powers:
+            if any(lo <= n <= hi for lo, hi in ranges[po.power]):
+                hit = True
+                yield (n, po.power)
+                emitted += 1
+                if limit is not None and emitted >= limit:
+                    return
+        if not hit:
+            # jump to the next range start
+            nxt = [lo for r in ranges.values() for lo, _ in r if lo > n]
+            if not nxt:
+                return
+            n = min(nxt)
+        else:
+            n += 1
+
+
+def _outcome_from_result(res: "_lib.SearchResult", n_min, n_max, op, target) -> SearchOutcome:
+    powers = []
+    for j in range(res.n_powers):
+        r = res.powers[j]
+        powers.append(PowerOutcome(
+            power=int(r.power), match_count=int(r.match_count), first_match_n=int(r.first_match_n),
+            last_match_n=int(r.last_match_n), cross_n=int(r.cross_n), cross_prime=int(r.cross_prime),
+            sum_at_cross=_lib.limbs_to_int(r.sum_at_cross), sum_before_cross=_lib.limbs_to_int(r.sum_before_cross),
+            final_sum=_lib.limbs_to_int(r.final_sum)))
+    s = res.stats
+    stats = {"ms_sieve": s.ms_sieve, "ms_count_scan": s.ms_count_scan, "ms_compact": s.ms_compact,
+             "ms_power_scan": s.ms_power_scan, "ms_total_device": s.ms_total_device, "primes": int(s.primes),
+             "sieve_lo": int(s.sieve_lo), "sieve_hi": int(s.sieve_hi), "launches": int(s.launches)}
+    return SearchOutcome(n_min, n_max, op, target, int(res.last_prime), powers, stats)
+
+
+def search(target: int, n_max: int, power: int = 2, n_min: int = 1, op: str = "==",
+           all_powers: bool = False, handle: Optional["_lib.Handle"] = None) -> SearchOutcome:
+    """Single-GPU fused search.  `all_powers=True` evaluates every p in 1..power in the same pass."""
+    if op not in OPS:
+        raise ValueError(f"unknown comparison operator {op!r}")
+    if target < 0:
+        raise ValueError("target must be non-negative")
+    h = handle or _lib.default_handle()
+    res = h.search(n_min, n_max, power, target, op, all_powers)
+    return _outcome_from_result(res, n_min, n_max, op, target)
+
+
+def does_exist(target: int, n_max: int, power: int = 2, n_min: int = 1, op: str = "==",
+               all_powers: bool = False) -> Optional[Dict[str, int]]:
+    """`does_exist primesum(n,p) <op> target`: the first match as the reference's variable dict, or None."""
+    m = search(target, n_max, power, n_min, op, all_powers).first()
+    if m is None:
+        return None
+    return {"n": m[0], "p": m[1]} if all_powers else {"n": m[0]}
+
+
+def for_any(target: int, n_max: int, power: int = 2, n_min: int = 1, op: str = "==",
+            all_powers: bool = False, limit: Optional[int] = None) -> Iterator[Dict[str, int]]:
+    for n, p in search(target, n_max, power, n_min, op, all_powers).matches(limit):
+        yield {"n": n, "p": p} if all_powers else {"n": n}
+
+
+# ------------------------------------------------------------------------------- multi-GPU
+def li(x: float) -> float:
+    """Offset logarithmic integral estimate of pi(x) (asymptotic series; only used to balance slices)."""
+    if x < 3:
+        return 0.0
+    lx = math.log(x)
+    s, term = 0.0, 1.0
+    for k in range(1, 12):
+        term *= k / lx
+        if term < 1e-6:
+            break
+        s += term
+    return x / lx * (1.0 + s)
+
+
+def partition_range(hi_excl: int, parts: int, lo: int = 0) -> List[Tuple[int, int]]:
+    """Cut [lo, hi_excl) into `parts` contiguous slices of ~equal prime count; interior cuts are multiples
+    of 480 (16 bitmap bytes) so every slice starts on a 16-byte aligned bitmap byte."""
+    if parts <= 1 or hi_excl - lo < 480 * parts * 4:
+        return [(lo, hi_excl)] + [(hi_excl, hi_excl)] * (parts - 1)
+    total = li(hi_excl) - li(lo)
+    cuts = [lo]
+    for g in range(1, parts):
+        want = li(lo) + total * g / parts
+        a, b = cuts[-1], hi_excl
+        for _ in range(64):
+            mid = (a + b) / 2
+            if li(mid) < want:
+                a = mid
+            else:
+                b = mid
+        c = int(b) // 480 * 480
+        cuts.append(min(max(c, cuts[-1]), hi_excl))
+    cuts.append(hi_excl)
+    return [(cuts[i], cuts[i + 1]) for i in range(parts)]
+
+
+def combine_slices(counts: Sequence[int], sums: Sequence[Sequence[int]], rank: int) -> Tuple[int, List[int]]:
+    """Exclusive prefix over ranks of (count, per-power sums): the rank's index offset and limb carry."""
+    n_before = sum(counts[:rank])
+    np_ = len(sums[0]) if sums else 0
+    carry = [sum(sums[r][j] for r in range(rank)) for j in range(np_)]
+    return n_before, carry
+
+
+def merge_outcomes(parts: Sequence[Optional[SearchOutcome]], n_min: int, n_max: int, op: str, target: int) -> SearchOutcome:
+    """Merge per-rank scan outcomes (ranks in value order; None for ranks that had nothing to scan)."""
+    parts = [p for p in parts if p is not None]
+    if not parts:
+        raise ValueError("no slice scanned anything")
+    powers = []
+    for j, p0 in enumerate(parts[0].powers):
+        recs = [p.powers[j] for p in parts]
+        cross = next((r for r in recs if r.cross_n), None)
+        matched = [r for r in recs if r.match_count]
+        powers.append(PowerOutcome(
+            power=p0.power, match_count=sum(r.match_count for r in recs),
+            first_match_n=min((r.first_match_n for r in matched), default=0),
+            last_match_n=max((r.last_match_n for r in matched), default=0),
+            cross_n=cross.cross_n if cross else 0, cross_prime=cross.cross_prime if cross else 0,
+            sum_at_cross=cross.sum_at_cross if cross else 0, sum_before_cross=cross.sum_before_cross if cross else 0,
+            final_sum=recs[-1].final_sum))
+    stats = {}
+    for k in parts[0].stats:
+        vals = [p.stats.get(k, 0) for p in parts]
+        stats[k] = max(vals) if k.startswith("ms_") else (sum(vals) if k in ("primes", "launches") else vals[0])
+    return SearchOutcome(n_min, n_max, op, target, parts[-1].last_prime, powers, stats)
+
+
+def _np(power: int, all_powers: bool) -> int:
+    return power if (all_powers and power > 1) else 1
+
+
+def distributed_search(target: int, n_max: int, power: int = 2, n_min: int = 1, op: str = "==",
+                       all_powers: bool = False, group=None, handle: Optional["_lib.Handle"] = None,
+                       gather=None) -> SearchOutcome:
+    """One process per GPU (torch.distributed, NCCL).  Every rank returns the merged outcome.
+
+    `gather(obj) -> list` may be injected (tests drive the host logic over gloo); by default the two
+    exchanges go through torch.distributed: the (count, sums) allgather as a uint32 CUDA tensor over NCCL,
+    the final merge as an object gather.
+    """
+    import torch
+    import torch.distributed as dist
+
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    rank = dist.get_rank(group) if dist.is_initialized() else 0
+    h = handle or _lib.default_handle()
+    if world == 1:
+        return search(target, n_max, power, n_min, op, all_powers, handle=h)
+
+    hi = h.nth_prime_upper(n_max) + 1
+    lo_g, hi_g = partition_range(hi, world)[rank]
+    count_g, _ = h.slice_sieve(lo_g, hi_g)
+    np_ = _np(power, all_powers)
+    sums_g = h.slice_reduce(0, count_g, power, all_powers) if count_g else [0] * np_
+
+    # ---- the one exchange: 8 B count + np_ * 48 B of limbs per rank
+    payload = [count_g & 0xFFFFFFFF, count_g >> 32]
+    for s in sums_g:
+        payload.extend(int(x) for x in _lib.int_to_limbs(s, _lib.PSS_LIMBS))
+    if gather is not None:
+        rows = gather(payload)
+    else:
+        dev = torch.device("cuda", torch.cuda.current_device()) if dist.get_backend(group) == "nccl" else torch.device("cpu")
+        mine = torch.tensor(payload, dtype=torch.int64, device=dev)
+        allv = torch.empty(world * len(payload), dtype=torch.int64, device=dev)
+        dist.all_gather_into_tensor(allv, mine, group=group)
+        rows = allv.view(world, -1).cpu().tolist()
+    counts = [r[0] | (r[1] << 32) for r in rows]
+    sums = [[_lib.limbs_to_int(r[2 + j * _lib.PSS_LIMBS: 2 + (j + 1) * _lib.PSS_LIMBS]) for j in range(np_)] for r in rows]
+    if sum(counts) < n_max:
+        raise RuntimeError("prime count bound violated")
+    n_before, carry = combine_slices(counts, sums, rank)
+
+    # ---- local scan with the carry; the rank holding n_max truncates, later ranks skip
+    local = None
+    take = min(count_g, max(0, n_max - n_before))
+    if take > 0:
+        res = h.slice_scan(0, take, n_before + 1, carry, n_min, n_max, power, target, op, all_powers)
+        local = _outcome_from_result(res, n_min, n_max, op, target)
+    if gather is not None:
+        outs = gather(local)
+    else:
+        outs = [None] * world
+        dist.all_gather_object(outs, local, group=group)
+    return merge_outcomes(outs, n_min, n_max, op, target)

@@ -1,0 +1,329 @@
+"""GPU parity tests: the CUDA path through the C ABI (ctypes) against the oracle and the reference's
+golden vectors.  Bit-exact everywhere (integer work): prime arrays, counts, every partial sum, match index,
+bracket.  Run on the GPU box with `pytest -m gpu`."""
+import hashlib
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def sha_u64(a):
+    return hashlib.sha256(np.ascontiguousarray(a, dtype="<u8").tobytes()).hexdigest()
+
+
+# ------------------------------------------------------------------------------------- K1 sieve
+def test_native_library_loaded(handle):
+    from pss_b200 import _lib
+    assert os.path.exists(_lib.LIB_PATH)
+    info = handle.device_info()
+    assert "sm_10" in info, info
+
+
+def test_generate_primes_golden(handle, golden):
+    from pss_b200 import sieve
+    for row in golden["generate_primes"]:
+        p = sieve.generate_primes(row["limit"])
+        assert p.dtype == np.int64
+        assert len(p) == row["count"], row
+        assert sha_u64(p) == row["sha256"], row
+        if row["primes"] is not None:
+            assert [int(x) for x in p] == row["primes"]
+
+
+def test_ranges_golden(handle, golden):
+    from pss_b200 import sieve
+    for row in golden["generate_primes_range"]:
+        p = sieve.generate_primes_range(row["start"], row["stop"])
+        assert len(p) == row["count"] and sha_u64(p) == row["sha256"], row
+        assert handle.count_primes(row["start"], row["stop"]) == row["count"]
+
+
+def test_first_n_nth_count_golden(handle, golden):
+    from pss_b200 import sieve
+    for row in golden["generate_n_primes"]:
+        p = sieve.generate_n_primes(row["n"])
+        assert len(p) == row["count"] and sha_u64(p) == row["sha256"], row
+    for row in golden["nth_prime"]:
+        assert sieve.nth_prime(row["n"]) == row["p"]
+    for row in golden["prime_count"]:
+        assert sieve.prime_count(row["limit"]) == row["count"]
+    # reference KATs: tests/test_sieve.py:29-44
+    assert [sieve.prime_count(10 ** k) for k in range(1, 7)] == [4, 25, 168, 1229, 9592, 78498]
+    with pytest.raises(ValueError):
+        sieve.nth_prime(0)
+
+
+@pytest.mark.parametrize("tile,threads,npat", [(8192, 256, 4), (98304, 512, 4), (65536, 1024, 2), (16384, 512, 0),
+                                               (216 * 1024, 1024, 4), (32768, 256, 1), (49152, 512, 3)])
+def test_sieve_tunings_vs_oracle(orc, tile, threads, npat):
+    """Every tile size / block size / pattern count gives the same primes (segment-size independence,
+    the analogue of tests/test_sieve.py:80-120)."""
+    from pss_b200 import _lib
+    os.environ["PSS_NPAT"] = str(npat)
+    try:
+        h = _lib.Handle(-1)
+    finally:
+        del os.environ["PSS_NPAT"]
+    h.set_tuning(tile, threads, 0)
+    for lo, hi in [(0, 3_000_000), (0, 61), (59, 62), (3600, 3800), (10 ** 9, 10 ** 9 + 2_000_000),
+                   (2 ** 32 - 10 ** 6, 2 ** 32 + 10 ** 6), (22_801_000_000, 22_801_763_490), (2 ** 39, 2 ** 39 + 500_000)]:
+        got = h.generate_primes(lo, hi).astype(np.uint64)
+        exp = orc.c_primes_range(lo, hi)
+        assert np.array_equal(got, exp), (lo, hi, len(got), len(exp))
+    h.close()
+
+
+def test_sieve_medium_vs_oracle(handle, orc):
+    exp = orc.c_primes_range(0, 2 * 10 ** 8)
+    got = handle.generate_primes(0, 2 * 10 ** 8).astype(np.uint64)
+    assert np.array_equal(got, exp)
+    assert handle.count_primes(0, 10 ** 9) == 50847534          # pi(1e9)  
+
+
+# ------------------------------------------------------------------------------- K2 power sums
+def test_power_sum_kats(handle):
+    from pss_b200 import gpu
+    small = np.array([2, 3, 5, 7, 11, 13, 17], dtype=np.int64)
+    assert [gpu.power_sum(small, k) for k in (1, 2, 3)] == [58, 666, 8944]      # tests/test_gpu.py:20-23
+    assert gpu.power_sum(np.array([], dtype=np.int64), 2) == 0                   # tests/test_gpu.py:67-69
+    for k in range(0, 9):
+        assert gpu.power_sum(small, k) == sum(int(p) ** k for p in small)
+    big = np.array([1_000_000_007, 2 ** 40 - 87, 22_801_763_489], dtype=np.int64)
+    for k in range(1, 9):
+        assert gpu.power_sum(big, k) == sum(int(p) ** k for p in big)
+    with pytest.raises(ValueError):
+        gpu.power_sum(np.array([2 ** 41], dtype=np.int64), 2)
+
+
+def test_primesum_golden(handle, golden):
+    from pss_b200 import sequences
+    for row in golden["primesum"]:
+        got = sequences.primesum_direct(row["n"], row["k"])
+        assert str(got) == row["value"], (row["n"], row["k"])
+
+
+def test_primesum_operator_semantics(handle):
+    from pss_b200 import primesum
+    assert [primesum(n, 2) for n in range(1, 8)] == [4, 13, 38, 87, 208, 377, 666]
+    assert primesum(3, 1) == 10 and primesum(4, 1) == 17 and primesum(1, 3) == 8 and primesum(2, 3) == 35
+    assert primesum(0, 2) == 0 and primesum(9, 0) == 9 and primesum(7.0, 2) == 666
+    with pytest.raises(ValueError, match="non-negative"):
+        primesum(-1, 2)
+    with pytest.raises(ValueError, match="integral"):
+        primesum(7.5, 2)
+    with pytest.raises(TypeError):
+        primesum("7", 2)
+
+
+def test_every_partial_sum(handle, orc, golden):
+    """every S_k(n), n <= 5000 and across several scan tiles, bit-exact"""
+    n = 70000
+    handle.slice_sieve(0, handle.nth_prime_upper(n) + 1)
+    primes = orc.c_first_n_primes(n)
+    for row in golden["prefix_sums"]:
+        k = row["k"]
+        sums = handle.slice_prefix_sums(0, 5000, k)
+        h = hashlib.sha256()
+        for s in sums:
+            h.update(str(s).encode() + b"\n")
+        assert h.hexdigest() == row["sha256_decimal_lines"], k
+    for k in (1, 2, 3, 5, 8):
+        got = handle.slice_prefix_sums(0, n, k)
+        assert got == orc.c_prefix_sums(primes, k), k
+        # window with a carry, not tile aligned
+        carry = got[12344]
+        assert handle.slice_prefix_sums(12345, 20000, k, carry) == got[12345:32345]
+
+
+# ------------------------------------------------------------------------------- K3 scan + compare
+def test_find_matches_golden(handle, golden):
+    """the reference evaluator's own answers (utils/grammar.py find_matches) for constant targets"""
+    from pss_b200 import search
+    for case in golden["find_matches"]:
+        expr, bounds = case["expr"], case["bounds"]
+        if "tri(m)" in expr:
+            continue
+        quant, rest = expr.split(" ", 1)
+        lhs, op, rhs = rest.rsplit(" ", 2)
+        target = int(rhs)
+        if "(n,p)" in lhs:
+            it = search.for_any(target, bounds["n"], power=bounds["p"], op=op, all_powers=True)
+        else:
+            k = int(lhs.split(",")[1].rstrip(")"))
+            it = search.for_any(target, bounds["n"], power=k, op=op)
+        res = list(it)
+        if quant == "does_exist":
+            res = res[:1]
+        assert res == case["matches"], expr
+
+
+@pytest.mark.parametrize("k,multi", [(1, False), (2, False), (3, False), (4, False), (5, False), (6, False), (7, False),
+                                     (8, False), (2, True), (3, True), (5, True), (6, True)])
+def test_synthetic_hits_and_brackets(handle, orc, k, multi):
+    """No trisum(666) config can match: validate match index / bracket with synthetic targets
+    at thread, warp, tile and range boundaries."""
+    from pss_b200 import search
+    n_max = 40000
+    primes = orc.c_first_n_primes(n_max)
+    powers = list(range(1, k + 1)) if multi else [k]
+    sums = {p: orc.c_prefix_sums(primes, p) for p in powers}
+    items = 16 if (k <= 3 and not multi) else 8
+    tile = 256 * items
+    hits = sorted({1, 2, 7, items, items + 1, 32 * items, 32 * items + 1, tile - 1, tile, tile + 1, 3 * tile, 3 * tile + 1,
+                   n_max - 1, n_max})
+    for hit in hits:
+        p = powers[hit % len(powers)]
+        target = sums[p][hit - 1]
+        out = search.search(target, n_max, power=k, all_powers=multi)
+        assert out.first() == (hit, p) or (multi and out.first()[0] <= hit), (hit, p, out.first())
+        po = next(x for x in out.powers if x.power == p)
+        assert (po.match_count, po.first_match_n, po.cross_n) == (1, hit, hit)
+        assert po.sum_at_cross == target and po.cross_prime == int(primes[hit - 1])
+        assert po.sum_before_cross == (sums[p][hit - 2] if hit > 1 else 0)
+        assert po.final_sum == sums[p][-1]
+        # near miss: bracket only
+        out = search.search(target + 1, n_max, power=k, all_powers=multi)
+        po = next(x for x in out.powers if x.power == p)
+        if hit < n_max:
+            assert po.match_count == 0 and po.cross_n == hit + 1 and po.sum_before_cross == target
+            assert out.bracket(p) == (hit, hit + 1)
+        else:
+            assert po.match_count == 0 and po.cross_n == 0 and out.bracket(p) == (n_max, n_max + 1)
+    # window limits: a hit below n_min is not a match
+    target = sums[powers[0]][99]
+    out = search.search(target, n_max, power=k, n_min=101, all_powers=multi)
+    assert out.powers[0].match_count == 0 and out.powers[0].cross_n == 100
+    # other operators against the oracle
+    for op in ("!=", "<", "<=", ">", ">="):
+        o = orc.c_scan_compare(primes, 1, powers[0], 0, target, op, 50, 20000)
+        out = search.search(target, 20000, power=k, n_min=50, op=op, all_powers=multi)
+        po = out.powers[0]
+        assert (po.match_count, po.first_match_n, po.last_match_n) == (o["match_count"], o["first_match_n"], o["last_match_n"]), op
+        got = [n for n, pp in out.matches() if pp == powers[0]]
+        exp = [n for n in range(50, 20001) if {"!=": sums[powers[0]][n - 1] != target, "<": sums[powers[0]][n - 1] < target,
+                                                "<=": sums[powers[0]][n - 1] <= target, ">": sums[powers[0]][n - 1] > target,
+                                                ">=": sums[powers[0]][n - 1] >= target}[op]]
+        assert got == exp, op
+
+
+def test_trisum666_configs_small(handle, orc):
+    """config C1 and the C3/C4 shape at a size the oracle finishes in seconds: no match, bracket = n_max"""
+    from pss_b200 import search
+    T = orc.trisum(666)
+    assert search.does_exist(666, 1_000_000) == {"n": 7}                      # C1
+    n_max = 10 ** 6
+    primes = orc.c_first_n_primes(n_max)
+    for k in (2, 3, 4, 5):
+        out = search.search(T, n_max, power=k)
+        assert out.first() is None and out.bracket() == (n_max, n_max + 1)
+        assert out.powers[0].final_sum == orc.c_power_sums(primes, [k])[0]
+        assert out.last_prime == 15485863
+    out = search.search(T, n_max, power=5, n_min=5 * 10 ** 5, all_powers=True)   # C5 shape
+    assert out.first() is None
+    assert [p.final_sum for p in out.powers] == orc.c_power_sums(primes, [1, 2, 3, 4, 5])
+
+
+def test_slices_compose(handle, orc):
+    """the multi-GPU decomposition on one device: slices scanned with carries == one scan"""
+    from pss_b200 import search
+    n_max = 300000
+    hi = handle.nth_prime_upper(n_max) + 1
+    primes = orc.c_first_n_primes(n_max)
+    sums = orc.c_prefix_sums(primes[:200001], 3)
+    target = sums[200000]   # S_3(200001)
+    whole = search.search(target, n_max, power=3)
+    parts, counts, ssums = [], [], []
+    slices = search.partition_range(hi, 4)
+    for lo, hi_g in slices:
+        c, _ = handle.slice_sieve(lo, hi_g)
+        counts.append(c)
+        ssums.append(handle.slice_reduce(0, c, 3) if c else [0])
+    assert sum(counts) >= n_max
+    for g, (lo, hi_g) in enumerate(slices):
+        n_before, carry = search.combine_slices(counts, ssums, g)
+        take = min(counts[g], max(0, n_max - n_before))
+        if take == 0:
+            parts.append(None)
+            continue
+        handle.slice_sieve(lo, hi_g)
+        res = handle.slice_scan(0, take, n_before + 1, carry, 1, n_max, 3, target, "==")
+        parts.append(search._outcome_from_result(res, 1, n_max, "==", target))
+    merged = search.merge_outcomes(parts, 1, n_max, "==", target)
+    assert merged.first() == whole.first() == (200001, 3)
+    assert merged.powers[0].final_sum == whole.powers[0].final_sum == orc.c_power_sums(primes, [3])[0]
+    assert merged.powers[0].sum_before_cross == sums[199999]
+    assert merged.last_prime == whole.last_prime == int(primes[-1])
+
+
+def test_sum_cache_device_advance(handle, orc, tmp_path):
+    from pss_b200.sum_cache import IncrementalSumCache
+    c = IncrementalSumCache(powers=[2, 3, 4])
+    for p in orc.first_n_primes(100):   # tests/test_cache_integration.py:30-50 — 666 at exactly n = 7
+        c.add_prime(int(p))
+        if c.get_prime_count() == 7:
+            assert c.get_sum(2) == 666
+    c.advance_to(50000)
+    primes = orc.c_first_n_primes(50000)
+    assert c.get_prime_count() == 50000 and c.get_last_prime() == int(primes[-1])
+    assert [c.get_sum(k) for k in (2, 3, 4)] == orc.c_power_sums(primes, [2, 3, 4])
+    c.save_checkpoint(tmp_path / "s.npz")
+    d = IncrementalSumCache.load_checkpoint(tmp_path / "s.npz")
+    d.advance_to(120000)
+    primes = orc.c_first_n_primes(120000)
+    assert [d.get_sum(k) for k in (2, 3, 4)] == orc.c_power_sums(primes, [2, 3, 4])
+
+
+# ------------------------------------------------------------------------------- at scale
+def test_at_scale_1e8(handle, golden):
+    """n = 1e8 (config C2's stream; reference _basic_sieve + cpu_power_sum row)"""
+    from pss_b200 import search
+    row = next(r for r in golden["at_scale"] if r["n"] == 10 ** 8)
+    T = int(golden["trisum"][-1]["value"])
+    out = search.search(T, 10 ** 8, power=5, all_powers=True)
+    assert out.last_prime == row["p_n"]
+    assert [str(p.final_sum) for p in out.powers] == [row["sums"][str(k)] for k in range(1, 6)]
+    assert out.first() is None
+    ptr, cnt = handle.slice_device_buffer()
+    assert cnt == 10 ** 8
+    got = handle.slice_primes(0, 10 ** 8)
+    assert sha_u64(got) == row["sha256_primes_le_u64"]
+
+
+def test_at_scale_1e9_c3(handle, golden):
+    """config C3: does_exist primesum(n,2) == trisum(666), n <= 1e9 — no match, bracket n = 1e9, exact S_2"""
+    from pss_b200 import search
+    row = next(r for r in golden["at_scale"] if r["n"] == 10 ** 9)
+    T = int(golden["trisum"][-1]["value"])
+    out = search.search(T, 10 ** 9, power=2)
+    assert out.first() is None and out.bracket() == (10 ** 9, 10 ** 9 + 1)
+    assert out.last_prime == row["p_n"] == 22801763489
+    assert str(out.powers[0].final_sum) == row["sums"]["2"]
+    assert out.powers[0].final_sum % 6 == (10 ** 9 + 5) % 6
+    # sampled partial sums at the Appendix-B checkpoints through synthetic hit targets
+    for r in golden["at_scale"]:
+        tgt = int(r["sums"]["2"])
+        o = search.search(tgt, 10 ** 9, power=2)
+        assert o.first() == (r["n"], 2), r["n"]
+        assert o.powers[0].cross_prime == r["p_n"]
+        break   # one extra full pass keeps the GPU test time bounded; the others run in bench --verify
+
+
+def test_at_scale_c4_c5(handle, golden):
+    """C4: k=3 n<=5e7, k=4 n<=1e7, k=5 n<=5e6;  C5 shape: all powers 1..5 at n = 1e9"""
+    from pss_b200 import search
+    T = int(golden["trisum"][-1]["value"])
+    ex = golden["at_scale_extra"]
+    out = search.search(T, 5 * 10 ** 7, power=3)
+    assert str(out.powers[0].final_sum) == ex["S_5e7"][2] and out.first() is None and out.last_prime == ex["p_5e7"]
+    out = search.search(T, 5 * 10 ** 6, power=5)
+    assert str(out.powers[0].final_sum) == ex["S_5e6"][4] and out.first() is None
+    p1e7 = {r["k"]: r["value"] for r in golden["primesum"] if r["n"] == 10 ** 7}
+    out = search.search(T, 10 ** 7, power=4)
+    assert str(out.powers[0].final_sum) == p1e7[4] and out.first() is None
+    row = next(r for r in golden["at_scale"] if r["n"] == 10 ** 9)
+    out = search.search(T, 10 ** 9, power=5, n_min=5 * 10 ** 7, all_powers=True)
+    assert [str(p.final_sum) for p in out.powers] == [row["sums"][str(k)] for k in range(1, 6)]
+    assert out.first() is None
