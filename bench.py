@@ -1,0 +1,353 @@
+#!/usr/bin/env python
+"""
+bench.py — headline benchmark of the hot path (BASELINE.json metric):
+    primes sieved + power-summed per second, bit-exact, on 1/2/4/8 B200.
+
+A "step" is one complete pass of the hot path over the workload
+    C3:  does_exist primesum(n,2) == trisum(666), n in [1, 1e9]        (BASELINE.json configs[2])
+i.e. sieve [0, 2.28e10) -> compaction of the first 1e9 primes -> exact p^2 -> decoupled look-back scan ->
+compare of every partial sum with the 325-bit target.  Inputs are only the query parameters: nothing is
+pre-computed or cached between steps (the bitmap and prime buffers are rewritten every step; both are far
+larger than L2).
+
+  value      primes / device time (CUDA events on the library's launch stream, summed over the step's
+             kernels, max over ranks), inputs resident.
+  e2e        the same metric through the public Python API (ctypes -> C ABI with host buffers): wall clock
+             around K calls, barrier + synchronize on both sides, max over ranks.
+  roofline   dominant kernel vs the measured HBM copy bandwidth (MEASURED_PEAKS.json), plus the kernel-local
+             roofs SURVEY §8(d) asks for (shared-memory cross-off rate, IMAD rate) under "kernels".
+  cpu_baseline  oracle port (oracle/oracle.c = restatement of the reference's _segmented_sieve + exact
+             power sums) on all host cores, bounded sample, rank 0 at N=1 only.
+
+--impl reference times that CPU port alone (the reference itself is pure Python and O(n^2) on this query;
+its linear pieces are what oracle.c restates).
+
+Multi-GPU (torchrun, one rank per GPU): the fixed 1e9-prime job is split by value range -> "strong" scaling.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(ROOT, "prime-square-sum_b200"))
+sys.path.insert(0, ROOT)
+
+TRISUM_666 = 37005443752611483714216385166550857181329086284892731078593232926279977894581784762614450464857290
+WORKLOADS = {
+    # name: (n_max, power, all_powers, n_min, expected final sums by power, expected p_n)
+    "C3": dict(n_max=10 ** 9, power=2, all_powers=False, n_min=1, p_n=22801763489,
+               sums={2: 168072405102068540986037048787}),
+    "C5": dict(n_max=10 ** 9, power=5, all_powers=True, n_min=5 * 10 ** 7, p_n=22801763489,
+               sums={1: 11138479445180240497, 2: 168072405102068540986037048787,
+                     3: 2863851545705647609829761010496201443383,
+                     4: 52128134804553784574781038633583251938565663646639,
+                     5: 989096022025420928255871308724946762578387567802486376275087}),
+    "C2": dict(n_max=10 ** 8, power=2, all_powers=False, n_min=1, p_n=2038074743,
+               sums={2: 133759354162117403400944283}),
+    "small": dict(n_max=10 ** 6, power=2, all_powers=False, n_min=1, p_n=15485863,
+                  sums={2: 76304519151822049179}),
+}
+CROSSOFFS_PER_PRIME = {"C3": 10.11, "C5": 10.11, "C2": 8.43, "small": 5.0}   # SURVEY §8(d) X(N)/n
+IMAD_PER_PRIME = {1: 0, 2: 4, 3: 10, 4: 18, 5: 28}
+MISC_BYTES = 1936   # sizeof(MiscDev): ticket/flag + 8 result records + carry limbs, one H2D and one D2H per scan
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            d = json.load(f)
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json)", d
+    return 6650.0, "fallback (B200_PROFILING.md)", {}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    def __init__(self, gpu_index=0):
+        self.proc = None
+        self.gpu_index = gpu_index
+        self.path = os.path.join(ROOT, "gpurun_out", f"clocks_bench_{os.getpid()}.csv")
+
+    def start(self):
+        try:
+            os.makedirs(os.path.dirname(self.path), exist_ok=True)
+            self.f = open(self.path, "w")
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.gpu_index),
+                 "--query-gpu=clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+                 "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+                 "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap",
+                 "--format=csv,noheader,nounits", "-lms", "100"], stdout=self.f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.proc is None:
+            return out
+        try:
+            self.proc.terminate()
+            self.proc.wait(timeout=5)
+            self.f.close()
+            sm, reasons, mx = [], set(), None
+            for line in open(self.path):
+                parts = [x.strip() for x in line.split(",")]
+                if len(parts) < 8:
+                    continue
+                try:
+                    sm.append(float(parts[0]))
+                    mx = float(parts[1])
+                except ValueError:
+                    continue
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), parts[4:8]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            if sm:
+                sm.sort()
+                # median of the upper half = clocks under load (idle samples between steps pull the plain median down)
+                out = {"sm_mhz": sm[len(sm) // 2], "sm_mhz_max_seen": sm[-1], "sm_max_mhz": mx, "reasons": sorted(reasons),
+                       "samples": len(sm)}
+        except Exception:
+            pass
+        return out
+
+
+def cpu_baseline(workload, seconds=12.0, threads=None):
+    """Oracle port on all host cores: sieve + exact power sums over value blocks spread evenly across the
+    workload's range, time-bounded.  Returns primes/s."""
+    from concurrent.futures import ThreadPoolExecutor
+    from oracle import oracle as orc
+    orc.lib()
+    w = WORKLOADS[workload]
+    hi = w["p_n"] + 1
+    powers = list(range(1, w["power"] + 1)) if w["all_powers"] else [w["power"]]
+    cores = threads or len(os.sched_getaffinity(0))
+    block = 1 << 24
+    n_blocks_total = hi // block
+    # evenly spaced sample of blocks (same density profile as the full range), processed until time is up
+    order = [(i * 7919) % n_blocks_total for i in range(n_blocks_total)]
+    lock = threading.Lock()
+    state = {"next": 0, "primes": 0, "blocks": 0}
+    t0 = time.perf_counter()
+    deadline = t0 + seconds
+
+    def worker():
+        while time.perf_counter() < deadline:
+            with lock:
+                i = state["next"]
+                state["next"] += 1
+            if i >= len(order):
+                return
+            b = order[i]
+            n, _, _ = orc.c_block_sieve_sum(b * block, (b + 1) * block, powers, 1 << 18)
+            with lock:
+                state["primes"] += n
+                state["blocks"] += 1
+
+    with ThreadPoolExecutor(cores) as ex:
+        for f in [ex.submit(worker) for _ in range(cores)]:
+            f.result()
+    dt = time.perf_counter() - t0
+    return {
+        "value": state["primes"] / dt, "unit": "primes/s", "cores": cores, "kind": "port",
+        "sample": f"{state['blocks']} value blocks of 2^24 spread evenly over [0, {hi}) "
+                  f"({state['primes']} primes, powers {powers}) in {dt:.1f} s; oracle/oracle.c "
+                  "(restatement of utils/sieve.py:_segmented_sieve + exact sum p^k), one block per thread",
+    }
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    w = args.workload
+    vals, last = [], None
+    for i in range(args.warmup + args.steps):
+        r = cpu_baseline(w, seconds=args.cpu_seconds)
+        if i >= args.warmup:
+            vals.append(r["value"])
+        last = r
+    v = sum(vals) / len(vals)
+    last["value"] = v
+    line = {
+        "impl": "reference", "metric": "primes sieved+power-summed/sec (bit-exact)", "value": v, "unit": "primes/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": args.cpu_seconds * 1e3,
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "u64 -> 32-bit limbs (exact)",
+        "data": "synthetic (the primes themselves; no external data)",
+        "config": workload_config(w, args.gpus), "cpu_baseline": last,
+        "e2e": {"value": v, "unit": "primes/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+def workload_config(name, gpus):
+    w = WORKLOADS[name]
+    return {
+        "workload": f"{name}: does_exist primesum(n,{'p<=' if w['all_powers'] else ''}{w['power']}) == trisum(666), "
+                    f"n in [{w['n_min']}, {w['n_max']}] (sieve [0, {w['p_n'] + 1}), {w['n_max']} primes)",
+        "n_max": w["n_max"], "power": w["power"], "all_powers": w["all_powers"],
+        "partition": f"value range split into {gpus} li(x)-balanced slices" if gpus > 1 else "single slice",
+        "l2": "inputs larger than L2 (bitmap 760 MB + primes 8 GB rewritten every step; no flush needed)",
+    }
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="C3", choices=sorted(WORKLOADS))
+    ap.add_argument("--cpu-seconds", type=float, default=12.0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "b200":
+        args.warmup = 3   # timing rule: at least 3 warm-up steps (allocations, pattern build, clocks)
+
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+    import torch.distributed as dist
+    from pss_b200 import _lib, search
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    os.environ["PSS_DEVICE"] = str(local_rank)
+    h = _lib.default_handle()
+
+    w = WORKLOADS[args.workload]
+    target = TRISUM_666
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def step():
+        if world > 1:
+            return search.distributed_search(target, w["n_max"], power=w["power"], n_min=w["n_min"],
+                                             all_powers=w["all_powers"], handle=h)
+        return search.search(target, w["n_max"], power=w["power"], n_min=w["n_min"], all_powers=w["all_powers"], handle=h)
+
+    for _ in range(args.warmup):
+        out = step()
+    # bit-exactness gate on the warmed-up result (golden: SURVEY Appendix B / tests/golden)
+    assert out.first() is None and out.bracket() == (w["n_max"], w["n_max"] + 1), "unexpected match"
+    assert out.last_prime == w["p_n"], (out.last_prime, w["p_n"])
+    for po in out.powers:
+        assert po.final_sum == w["sums"][po.power], f"S_{po.power} mismatch"
+
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    per_step_dev = []
+    kern = {"ms_sieve": 0.0, "ms_count_scan": 0.0, "ms_compact": 0.0, "ms_power_scan": 0.0}
+    launches = 0
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        h.stats_reset()
+        out = step()
+        s = h.stats()
+        per_step_dev.append(s["ms_total_device"])
+        for k in kern:
+            kern[k] += s[k]
+        launches += s["launches"]
+    barrier()
+    wall = time.perf_counter() - t0
+    clocks = sampler.stop() if rank == 0 else None
+
+    dev_ms = sum(per_step_dev)
+    if world > 1:
+        t = torch.tensor([dev_ms, wall * 1e3, kern["ms_sieve"], kern["ms_count_scan"], kern["ms_compact"], kern["ms_power_scan"],
+                          float(launches)], dtype=torch.float64, device="cuda")
+        tmax = t.clone()
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        tsum = t.clone()
+        dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
+        dev_ms, wall_ms = float(tmax[0]), float(tmax[1])
+        kern = {k: float(tmax[2 + i]) for i, k in enumerate(["ms_sieve", "ms_count_scan", "ms_compact", "ms_power_scan"])}
+        launches = int(tsum[6])
+    else:
+        wall_ms = wall * 1e3
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    n_primes = w["n_max"]
+    K = args.steps
+    value = n_primes * K / (dev_ms * 1e-3)
+    e2e_value = n_primes * K / (wall_ms * 1e-3)
+    peak, peak_src, peaks = load_peaks()
+    # per-kernel averages per step (max over ranks); each rank handles ~1/world of the primes
+    per = {k: v / K for k, v in kern.items()}
+    primes_per_launch = n_primes / world
+    np_ = w["power"] if w["all_powers"] else 1
+    imad = sum(IMAD_PER_PRIME.get(k, 0) for k in ([w["power"]] if not w["all_powers"] else [w["power"]]))
+    kernels = {
+        "k_sieve": {"ms": per["ms_sieve"], "hbm_GBps_algorithmic": 8 * primes_per_launch / (per["ms_sieve"] * 1e-3) / 1e9 if per["ms_sieve"] else None,
+                    "smem_crossoffs_per_s": CROSSOFFS_PER_PRIME[args.workload] * primes_per_launch / (per["ms_sieve"] * 1e-3) if per["ms_sieve"] else None,
+                    "smem_peak_accesses_per_s": 148 * 32 * 1.965e9, "integers_per_s": (w["p_n"] + 1) / world / (per["ms_sieve"] * 1e-3) if per["ms_sieve"] else None},
+        "k_scan_tile_counts": {"ms": per["ms_count_scan"]},
+        "k_compact": {"ms": per["ms_compact"], "hbm_GBps_algorithmic": 8 * primes_per_launch / (per["ms_compact"] * 1e-3) / 1e9 if per["ms_compact"] else None},
+        "k_power_scan": {"ms": per["ms_power_scan"], "hbm_GBps_algorithmic": 8 * primes_per_launch / (per["ms_power_scan"] * 1e-3) / 1e9 if per["ms_power_scan"] else None,
+                         "imad_per_s": imad * primes_per_launch * (2 if world > 1 else 1) / (per["ms_power_scan"] * 1e-3) if per["ms_power_scan"] else None,
+                         "imad_peak_per_s": 148 * 64 * 1.965e9},
+    }
+    dominant = max(("k_sieve", "k_compact", "k_power_scan"), key=lambda k: kernels[k]["ms"])
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    if os.path.exists(tp):
+        try:
+            traffic = json.load(open(tp)).get(dominant, {}).get("dram_bytes_per_launch")
+        except Exception:
+            traffic = None
+    achieved = kernels[dominant]["hbm_GBps_algorithmic"]
+    roofline = {
+        "bound": "hbm", "kernel": dominant, "achieved": achieved, "peak": peak, "unit": "GB/s",
+        "frac": achieved / peak if achieved else None, "traffic": traffic, "peak_source": peak_src,
+        "algorithmic_bytes_per_unit": "8 B per prime per kernel (u64 written once by K1, read once by K3); 16 B per prime for the path",
+        "path_achieved_GBps": 16 * n_primes / (dev_ms / K * 1e-3) / 1e9,
+        "path_frac": 16 * n_primes / (dev_ms / K * 1e-3) / 1e9 / peak,
+        "kernels": kernels,
+        "note": "the path is bound by the sieve's shared-memory cross-offs and the integer pipe, not HBM (SURVEY §8d); "
+                "kernel-local roofs are under kernels",
+    }
+    line = {
+        "metric": "primes sieved+power-summed/sec (bit-exact)", "value": value, "unit": "primes/s", "n_gpus": world,
+        "steps": K, "warmup": args.warmup, "ms_per_step": dev_ms / K, "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "u64 -> 32-bit limbs (exact integer)",
+        "data": "synthetic (the primes themselves; no external data)",
+        "config": workload_config(args.workload, world),
+        "clocks": clocks,
+        "e2e": {"value": e2e_value, "unit": "primes/s", "ms_per_step": wall_ms / K,
+                "h2d_bytes_per_step": (MISC_BYTES + 4 * 11) * (2 if world > 1 else 1),
+                "d2h_bytes_per_step": (MISC_BYTES + 8 + 8 + 4) * (2 if world > 1 else 1),
+                "api": "pss_b200.search.search -> ctypes -> pss_search (host args, host results)"},
+        "gpu_launches": launches,
+        "roofline": roofline,
+        "verified": "final sums, p_n and no-match/bracket checked against tests/golden (bit-exact)",
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        line["cpu_baseline"] = cpu_baseline(args.workload, seconds=args.cpu_seconds)
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
