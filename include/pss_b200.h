@@ -81,6 +81,8 @@ typedef struct pss_stats {
     uint64_t primes;        /* primes power-summed */
     uint64_t sieve_lo, sieve_hi; /* value range sieved */
     uint64_t launches;      /* kernels launched by this call */
+    double ms_bitmap_reduce;  /* fused path: per-tile (count, sums) from the bitmap + column prefix scan (part of ms_power_scan) */
+    double ms_bitmap_compare; /* fused path: re-walk with exact prefixes + compare (part of ms_power_scan) */
 } pss_stats;
 
 /* ---- fused search: replaces the O(n^2) host loop utils/grammar.py:937-999 (find_matches) over
@@ -131,6 +133,19 @@ int pss_primesum(pss_handle* h, uint64_t n, uint32_t power, uint32_t* limbs_out 
 
 /* ---- K1+K2+K3 fused search (single GPU) ---------------------------------------------------- */
 int pss_search(pss_handle* h, const pss_search_args* args, pss_search_result* res);
+
+/* search path selection: 0 (default) = fused, K2/K3 read the sieve's bit-packed output directly;
+ * 1 = materialised, K1c compacts u64 primes first (the layout generate_primes / slice_* serve). */
+int pss_set_search_path(pss_handle* h, int materialised);
+
+/* fused slice API (multi-GPU phase A / B without a u64 prime buffer):
+ * sieve [lo,hi) + per-tile sums; returns the slice's prime count and sum p^k per power record */
+int pss_slice_sieve_sums(pss_handle* h, uint64_t lo, uint64_t hi_excl, uint32_t power_max, uint32_t all_powers,
+                         uint64_t* count, uint32_t* sums_out /* n_powers * PSS_LIMBS */);
+/* compare every partial sum of the slice sieved by pss_slice_sieve_sums; its first prime has global index
+ * n_first, carry_in = sums of all primes before it; stops at args->n_max */
+int pss_slice_scan_bitmap(pss_handle* h, uint64_t n_first, const uint32_t* carry_in, const pss_search_args* args,
+                          pss_search_result* res);
 
 /* ---- slice API: the multi-GPU decomposition (one handle per rank).  The per-slice state
  *      (prime_count, last_prime, {k: S_k}) is exactly IncrementalSumCache's

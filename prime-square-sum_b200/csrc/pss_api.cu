@@ -21,6 +21,7 @@
 #include <vector>
 
 #include "../../include/pss_b200.h"
+#include "pss_bscan.cuh"
 #include "pss_scan.cuh"
 #include "pss_sieve.cuh"
 
@@ -44,6 +45,7 @@ struct MiscDev {   // small device-side block, one H2D / D2H per scan
     u32 pad[2];
     pss_power_result results[PSS_MAX_POWER];
     u32 carry[PSS_MAX_POWER * PSS_LIMBS];
+    u64 last_prime;
 };
 
 }  // namespace
@@ -60,8 +62,8 @@ struct pss_handle {
     u32 tile_bytes = 96 * 1024;
     u32 sieve_threads = 512;
     u32 n_pat = 4;
-    u32 cta_wide_div = 256;    // p < tile_bytes / div -> CTA-wide
-    u32 warp_wide_div = 8;     // p < tile_bytes / div -> warp-wide
+    u32 warp_wide_div = 32;    // p < tile_bytes / div -> one warp per prime, else 8 lanes per prime
+    int search_path = 0;       // 0: fused (scan straight from the bitmap), 1: materialised u64 primes
 
     // patterns
     uint4* d_pat[kMaxPatterns] = {nullptr, nullptr, nullptr, nullptr};
@@ -70,7 +72,7 @@ struct pss_handle {
     // base primes
     std::vector<u32> h_base;   // all primes >= 7 up to base_limit
     u64 base_limit = 0;
-    DevBuf d_base;
+    DevBuf d_base, d_base_inv, d_base_strand;
     u32 base_first_prime = 0;  // first sieving prime the device copy starts at
     u32 n_base_dev = 0;
 
@@ -84,6 +86,14 @@ struct pss_handle {
     DevBuf primes;
     u64 n_resident = 0;
     u64 resident_last = 0;
+
+    // fused path: column-major tile records of the last bitmap reduce and their prefixes
+    DevBuf cols, col_prefix;
+    bool bs_valid = false;
+    u32 bs_K = 0, bs_n_tiles = 0, bs_total_cols = 0;
+    bool bs_multi = false;
+    u64 bs_col_stride = 0, bs_count = 0;
+    u32 bs_sums[PSS_MAX_POWER * PSS_LIMBS] = {0};   // slice sums per power record (normalised limbs)
 
     // scan workspace
     DevBuf status, agg, incl, misc, prefix_out, user_vals;
@@ -190,8 +200,24 @@ int ensure_base_primes(pss_handle* h, u64 hi) {
     if (h->base_first_prime != first) {
         auto it = std::lower_bound(h->h_base.begin(), h->h_base.end(), first);
         const size_t n = (size_t)(h->h_base.end() - it);
+        std::vector<u32> inv(std::max<size_t>(n, 1)), strand(std::max<size_t>(n, 1) * 8);
+        for (size_t i = 0; i < n; ++i) {
+            const u32 p = it[i];
+            inv[i] = (u32)((1ull << 32) / p);
+            for (u32 j = 0; j < 8; ++j) {
+                u32 c, bit;
+                strand_geometry(p, j, c, bit);
+                strand[i * 8 + j] = c | (bit << 24);
+            }
+        }
         PSS_TRY(ensure(h, h->d_base, std::max<size_t>(n, 1) * sizeof(u32)));
-        if (n) CU_TRY(h, cudaMemcpyAsync(h->d_base.p, &*it, n * sizeof(u32), cudaMemcpyHostToDevice, h->stream));
+        PSS_TRY(ensure(h, h->d_base_inv, std::max<size_t>(n, 1) * sizeof(u32)));
+        PSS_TRY(ensure(h, h->d_base_strand, std::max<size_t>(n, 1) * 8 * sizeof(u32)));
+        if (n) {
+            CU_TRY(h, cudaMemcpyAsync(h->d_base.p, &*it, n * sizeof(u32), cudaMemcpyHostToDevice, h->stream));
+            CU_TRY(h, cudaMemcpyAsync(h->d_base_inv.p, inv.data(), n * sizeof(u32), cudaMemcpyHostToDevice, h->stream));
+            CU_TRY(h, cudaMemcpyAsync(h->d_base_strand.p, strand.data(), n * 8 * sizeof(u32), cudaMemcpyHostToDevice, h->stream));
+        }
         CU_TRY(h, cudaStreamSynchronize(h->stream));
         h->n_base_dev = (u32)n;
         h->base_first_prime = first;
@@ -236,6 +262,7 @@ int launch_sieve(pss_handle* h, const SieveParams& sp) {
 // K1a + K1b: sieve [lo,hi) into the bitmap, count.  Leaves sv_* describing the bitmap.
 int sieve_range(pss_handle* h, u64 lo, u64 hi) {
     h->sv_valid = false;
+    h->bs_valid = false;
     if (hi > kMaxValue) return fail(h, PSS_EINVAL, "sieve bound %llu exceeds 2^%d", (unsigned long long)hi, PSS_MAX_PRIME_BITS);
     if (lo >= hi || hi <= 2) {
         h->sv_lo = lo; h->sv_hi = hi; h->sv_total = 0; h->sv_c235 = 0; h->sv_n_tiles = 0; h->sv_valid = true;
@@ -271,21 +298,18 @@ int sieve_range(pss_handle* h, u64 lo, u64 hi) {
     sp.B_start = B_start;
     sp.tile_bytes = tile_bytes;
     sp.n_tiles = n_tiles;
-    sp.base_primes = static_cast<const u32*>(h->d_base.p);
+    sp.base_p = static_cast<const u32*>(h->d_base.p);
+    sp.base_inv = static_cast<const u32*>(h->d_base_inv.p);
+    sp.base_strand = static_cast<const u32*>(h->d_base_strand.p);
+    sp.wide_index = (B_start + (u64)n_tiles * tile_bytes > 0xFFFFFFFFull) ? 1u : 0u;
     // only primes up to sqrt(hi) are ever needed
     {
         const u64 lim = isqrt_u64(hi - 1);
         auto b = std::lower_bound(h->h_base.begin(), h->h_base.end(), h->base_first_prime);
         auto e = std::upper_bound(h->h_base.begin(), h->h_base.end(), (u32)std::min<u64>(lim, 0xFFFFFFFFull));
         sp.n_base = (e > b) ? (u32)(e - b) : 0;
-        const u32 cta_lim = tile_bytes / std::max<u32>(h->cta_wide_div, 1);
         const u32 warp_lim = tile_bytes / std::max<u32>(h->warp_wide_div, 1);
-        u32 nc = (u32)(std::lower_bound(b, e, cta_lim) - b);
-        nc = std::min<u32>(nc, kMaxCtaWide);
-        u32 nw = (u32)(std::lower_bound(b, e, warp_lim) - b);
-        nw = std::max(nw, nc);
-        sp.n_cta_wide = nc;
-        sp.n_warp_wide = nw;
+        sp.n_warp_wide = (e > b) ? (u32)(std::lower_bound(b, e, warp_lim) - b) : 0;
     }
     sp.n_pat = h->n_pat;
     for (u32 g = 0; g < h->n_pat; ++g) {
@@ -506,6 +530,200 @@ int run_scan(pss_handle* h, const u64* d_vals, u64 count, u64 n_first, const u32
     return PSS_OK;
 }
 
+
+// ---- fused path: K2/K3 straight from the bitmap -------------------------------------------------------
+template <int K, bool MULTI, int MODE>
+int launch_bscan_t(pss_handle* h, const BScanParams& bp) {
+    static int occ = 0;
+    if (!occ) {
+        CU_TRY(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_bitmap_scan<K, MULTI, MODE>, kBsThreads, 0));
+        if (occ < 1) occ = 1;
+    }
+    const u32 grid = std::min<u32>(bp.n_tiles, (u32)(h->sm_count * occ));
+    k_bitmap_scan<K, MULTI, MODE><<<grid, kBsThreads, 0, h->stream>>>(bp);
+    CU_TRY(h, cudaGetLastError());
+    h->launches++;
+    return PSS_OK;
+}
+
+template <int MODE>
+int launch_bscan(pss_handle* h, const BScanParams& bp, u32 K, bool multi) {
+    if (!multi) {
+        switch (K) {
+            case 1: return launch_bscan_t<1, false, MODE>(h, bp);
+            case 2: return launch_bscan_t<2, false, MODE>(h, bp);
+            case 3: return launch_bscan_t<3, false, MODE>(h, bp);
+            case 4: return launch_bscan_t<4, false, MODE>(h, bp);
+            case 5: return launch_bscan_t<5, false, MODE>(h, bp);
+            case 6: return launch_bscan_t<6, false, MODE>(h, bp);
+            case 7: return launch_bscan_t<7, false, MODE>(h, bp);
+            case 8: return launch_bscan_t<8, false, MODE>(h, bp);
+        }
+    } else {
+        switch (K) {
+            case 2: return launch_bscan_t<2, true, MODE>(h, bp);
+            case 3: return launch_bscan_t<3, true, MODE>(h, bp);
+            case 4: return launch_bscan_t<4, true, MODE>(h, bp);
+            case 5: return launch_bscan_t<5, true, MODE>(h, bp);
+            case 6: return launch_bscan_t<6, true, MODE>(h, bp);
+        }
+    }
+    return fail(h, PSS_EINVAL, "unsupported power configuration k=%u all_powers=%d", K, (int)multi);
+}
+
+u32 total_limbs_of(u32 K, bool multi) {
+    u32 t = 0;
+    for (u32 j = 0; j < n_powers_of(K, multi); ++j) t += (u32)sum_limbs((int)expo_of(K, multi, j));
+    return t;
+}
+
+void fill_bscan_common(pss_handle* h, BScanParams& bp) {
+    memset(&bp, 0, sizeof bp);
+    bp.bitmap = static_cast<const u32*>(h->bitmap.p);
+    bp.n_words = (u64)h->sv_n_tiles * h->sv_tile_bytes / 4;
+    bp.B_start = h->sv_B_start;
+    bp.n_tiles = (u32)((bp.n_words + kBsTileWords - 1) / kBsTileWords);
+    bp.n_small = 0;
+    for (u64 q : {2ull, 3ull, 5ull})
+        if (q >= h->sv_lo && q < h->sv_hi) bp.small_primes[bp.n_small++] = q;
+    bp.col_stride = (u64)bp.n_tiles + 1;
+}
+
+// phase A of the fused path: per-tile (count, sums) records, column prefixes, slice totals
+int bitmap_reduce(pss_handle* h, u32 K, bool multi) {
+    if (!h->sv_valid) return fail(h, PSS_EINTERNAL, "no sieve result");
+    if (K < 1 || K > PSS_MAX_POWER) return fail(h, PSS_EINVAL, "power %u out of range 1..%d", K, PSS_MAX_POWER);
+    if (multi && K > 6) return fail(h, PSS_EINVAL, "all_powers supports power_max <= 6");
+    if (multi && K == 1) multi = false;
+    h->bs_valid = false;
+    const u32 np = n_powers_of(K, multi), total = total_limbs_of(K, multi), ncols = 1 + total;
+    memset(h->bs_sums, 0, sizeof h->bs_sums);
+    h->bs_count = 0;
+    h->bs_K = K; h->bs_multi = multi; h->bs_total_cols = ncols;
+    if (h->sv_n_tiles == 0) {   // empty range
+        h->bs_n_tiles = 0; h->bs_col_stride = 1; h->bs_valid = true;
+        return PSS_OK;
+    }
+    BScanParams bp;
+    fill_bscan_common(h, bp);
+    PSS_TRY(ensure(h, h->cols, (size_t)ncols * bp.col_stride * sizeof(u32)));
+    PSS_TRY(ensure(h, h->col_prefix, (size_t)ncols * bp.col_stride * sizeof(u64)));
+    bp.cols = static_cast<u32*>(h->cols.p);
+    bp.col_prefix = static_cast<const u64*>(h->col_prefix.p);
+    CU_TRY(h, cudaEventRecord(h->ev[4], h->stream));
+    PSS_TRY(launch_bscan<kBsReduce>(h, bp, K, multi));
+    k_scan_columns<<<ncols, 1024, 0, h->stream>>>(bp.cols, static_cast<u64*>(h->col_prefix.p), bp.n_tiles, bp.col_stride);
+    CU_TRY(h, cudaGetLastError());
+    h->launches++;
+    CU_TRY(h, cudaEventRecord(h->ev[5], h->stream));
+    std::vector<u64> totals(ncols);
+    CU_TRY(h, cudaMemcpy2DAsync(totals.data(), sizeof(u64), static_cast<const u64*>(h->col_prefix.p) + bp.n_tiles, bp.col_stride * sizeof(u64),
+                                sizeof(u64), ncols, cudaMemcpyDeviceToHost, h->stream));
+    CU_TRY(h, cudaStreamSynchronize(h->stream));
+    h->acc.ms_power_scan += ev_ms(h, 4, 5);
+    h->acc.ms_bitmap_reduce += ev_ms(h, 4, 5);
+    // normalise the deferred-carry column totals into limbs
+    h->bs_count = totals[0];
+    u32 col = 1;
+    for (u32 j = 0; j < np; ++j) {
+        const u32 w = (u32)sum_limbs((int)expo_of(K, multi, j));
+        u64 c = 0;
+        for (u32 i = 0; i < w; ++i, ++col) {
+            const u64 v = totals[col];
+            const u64 lo = (v & 0xFFFFFFFFull) + (c & 0xFFFFFFFFull);
+            h->bs_sums[j * PSS_LIMBS + i] = (u32)lo;
+            c = (v >> 32) + (c >> 32) + (lo >> 32);
+        }
+    }
+    if (h->bs_count != h->sv_total)
+        return fail(h, PSS_EINTERNAL, "bitmap reduce counted %llu primes, sieve counted %llu", (unsigned long long)h->bs_count,
+                    (unsigned long long)h->sv_total);
+    h->bs_n_tiles = bp.n_tiles;
+    h->bs_col_stride = bp.col_stride;
+    h->bs_valid = true;
+    return PSS_OK;
+}
+
+void limbs_add(u32* a, const u32* b) {
+    u64 c = 0;
+    for (int i = 0; i < PSS_LIMBS; ++i) {
+        const u64 t = (u64)a[i] + b[i] + c;
+        a[i] = (u32)t;
+        c = t >> 32;
+    }
+}
+
+// phase B of the fused path: compare every partial sum, seeded with carry_in (host limbs or NULL)
+int bitmap_compare(pss_handle* h, u64 n_first, const u32* carry_in, const pss_search_args* a, pss_search_result* res) {
+    const bool multi = a->all_powers && a->power_max > 1;
+    const u32 K = a->power_max;
+    if (!h->bs_valid || h->bs_K != K || h->bs_multi != multi)
+        return fail(h, PSS_EINVAL, "pss_slice_sieve_sums must be called first with the same power configuration");
+    const u32 np = n_powers_of(K, multi);
+    static const u32 kMasks[6] = {2u, 5u, 1u, 3u, 4u, 6u};
+    MiscDev* hm = h->h_misc;
+    memset(hm, 0, sizeof(MiscDev));
+    for (u32 j = 0; j < np; ++j) {
+        hm->results[j].power = expo_of(K, multi, j);
+        hm->results[j].first_match_n = ~0ull;
+        if (carry_in) {
+            memcpy(&hm->carry[j * PSS_LIMBS], carry_in + j * PSS_LIMBS, PSS_LIMBS * sizeof(u32));
+            const int w = sum_limbs((int)expo_of(K, multi, j));
+            for (int i = w; i < PSS_LIMBS; ++i)
+                if (hm->carry[j * PSS_LIMBS + i]) return fail(h, PSS_EINVAL, "carry-in of power %u exceeds %d limbs", hm->results[j].power, w);
+        }
+    }
+    const u64 scanned = (a->n_max >= n_first) ? std::min<u64>(h->bs_count, a->n_max - n_first + 1) : 0;
+    CU_TRY(h, cudaEventRecord(h->ev[4], h->stream));
+    if (scanned > 0) {
+        BScanParams bp;
+        fill_bscan_common(h, bp);
+        bp.cols = static_cast<u32*>(h->cols.p);
+        bp.col_prefix = static_cast<const u64*>(h->col_prefix.p);
+        bp.n_first = n_first;
+        bp.n_min = a->n_min;
+        bp.n_max = a->n_max;
+        bp.cmp_mask = kMasks[a->cmp];
+        for (u32 i = 0; i < a->target_nlimbs && i < PSS_LIMBS; ++i) bp.target[i] = a->target[i];
+        for (u32 j = 0; j < np; ++j) {
+            const u32 w = (u32)sum_limbs((int)expo_of(K, multi, j));
+            for (u32 i = w; i < a->target_nlimbs; ++i)
+                if (a->target[i]) bp.target_over_mask |= (1u << j);
+        }
+        MiscDev* dm = static_cast<MiscDev*>(h->misc.p);
+        bp.carry_in = dm->carry;
+        bp.results = dm->results;
+        bp.last_prime_out = &dm->last_prime;
+        bp.error_flag = &dm->error_flag;
+        CU_TRY(h, cudaMemcpyAsync(dm, hm, sizeof(MiscDev), cudaMemcpyHostToDevice, h->stream));
+        PSS_TRY(launch_bscan<kBsCompare>(h, bp, K, multi));
+        CU_TRY(h, cudaEventRecord(h->ev[5], h->stream));
+        CU_TRY(h, cudaMemcpyAsync(hm, dm, sizeof(MiscDev), cudaMemcpyDeviceToHost, h->stream));
+        CU_TRY(h, cudaStreamSynchronize(h->stream));
+    } else {
+        CU_TRY(h, cudaEventRecord(h->ev[5], h->stream));
+        CU_TRY(h, cudaStreamSynchronize(h->stream));
+    }
+    h->acc.ms_power_scan += ev_ms(h, 4, 5);
+    h->acc.ms_bitmap_compare += ev_ms(h, 4, 5);
+    h->acc.primes += scanned;
+    const bool reached_n_max = scanned > 0 && (n_first + scanned - 1 == a->n_max);
+    for (u32 j = 0; j < np; ++j) {
+        res->powers[j] = hm->results[j];
+        if (res->powers[j].match_count == 0) res->powers[j].first_match_n = 0, res->powers[j].last_match_n = 0;
+        if (!reached_n_max) {   // slice exhausted before n_max: S(last scanned) = carry + slice sums
+            u32 fs[PSS_LIMBS];
+            memcpy(fs, &hm->carry[j * PSS_LIMBS], sizeof fs);
+            if (scanned) limbs_add(fs, &h->bs_sums[j * PSS_LIMBS]);
+            memcpy(res->powers[j].final_sum, fs, sizeof fs);
+        }
+    }
+    res->n_powers = np;
+    res->primes_scanned = scanned;
+    res->last_prime = reached_n_max ? hm->last_prime : 0;
+    return PSS_OK;
+}
+
 int check_handle(pss_handle* h) {
     if (!h) return fail(nullptr, PSS_EINVAL, "null handle");
     cudaError_t e = cudaSetDevice(h->device);
@@ -560,7 +778,7 @@ int pss_open(int device, pss_handle** out) {
     h->tile_bytes = env_u32("PSS_TILE_BYTES", h->tile_bytes);
     h->sieve_threads = env_u32("PSS_SIEVE_THREADS", h->sieve_threads);
     h->n_pat = std::min<u32>(env_u32("PSS_NPAT", h->n_pat), kMaxPatterns);
-    h->cta_wide_div = env_u32("PSS_CTA_WIDE_DIV", h->cta_wide_div);
+    if (const char* sp_ = getenv("PSS_SEARCH_PATH")) h->search_path = (strcmp(sp_, "materialised") == 0 || strcmp(sp_, "materialized") == 0) ? 1 : 0;
     h->warp_wide_div = env_u32("PSS_WARP_WIDE_DIV", h->warp_wide_div);
     h->tile_bytes = std::max<u32>(8192, std::min<u32>((h->tile_bytes / kChunkBytes) * kChunkBytes, 216 * 1024));
     auto cleanup = [&](int rc) {
@@ -586,7 +804,7 @@ int pss_close(pss_handle* h) {
     if (!h) return PSS_OK;
     cudaSetDevice(h->device);
     if (h->stream) cudaStreamSynchronize(h->stream);
-    for (DevBuf* b : {&h->d_base, &h->bitmap, &h->chunk_counts, &h->tile_counts, &h->tile_prefix, &h->primes, &h->status, &h->agg,
+    for (DevBuf* b : {&h->d_base, &h->d_base_inv, &h->d_base_strand, &h->cols, &h->col_prefix, &h->bitmap, &h->chunk_counts, &h->tile_counts, &h->tile_prefix, &h->primes, &h->status, &h->agg,
                       &h->incl, &h->misc, &h->prefix_out, &h->user_vals})
         if (b->p) cudaFree(b->p);
     for (auto& p : h->d_pat)
@@ -741,6 +959,8 @@ static void fill_stats(pss_handle* h, pss_stats* s, const pss_stats& before) {
     s->ms_count_scan = now.ms_count_scan - before.ms_count_scan;
     s->ms_compact = now.ms_compact - before.ms_compact;
     s->ms_power_scan = now.ms_power_scan - before.ms_power_scan;
+    s->ms_bitmap_reduce = now.ms_bitmap_reduce - before.ms_bitmap_reduce;
+    s->ms_bitmap_compare = now.ms_bitmap_compare - before.ms_bitmap_compare;
     s->ms_total_device = s->ms_sieve + s->ms_count_scan + s->ms_compact + s->ms_power_scan;
     s->primes = now.primes - before.primes;
     s->sieve_lo = now.sieve_lo;
@@ -762,13 +982,52 @@ int pss_search(pss_handle* h, const pss_search_args* a, pss_search_result* res) 
     PSS_TRY(validate_search(h, a, res));
     const pss_stats before = stats_snapshot(h);
     memset(res, 0, sizeof *res);
-    PSS_TRY(sieve_first_n(h, a->n_max));
     const bool multi = a->all_powers && a->power_max > 1;
-    PSS_TRY(run_scan(h, static_cast<const u64*>(h->primes.p), a->n_max, 1, nullptr, a->power_max, multi, kModeCompare, a->n_min, a->n_max,
-                     a->cmp, a->target, a->target_nlimbs, nullptr, res->powers));
-    res->n_powers = n_powers_of(a->power_max, multi);
-    res->primes_scanned = a->n_max;
-    res->last_prime = h->resident_last;
+    if (h->search_path == 1) {
+        // materialised path: K1c compaction into u64 primes, K2/K3 with decoupled look-back
+        PSS_TRY(sieve_first_n(h, a->n_max));
+        PSS_TRY(run_scan(h, static_cast<const u64*>(h->primes.p), a->n_max, 1, nullptr, a->power_max, multi, kModeCompare, a->n_min, a->n_max,
+                         a->cmp, a->target, a->target_nlimbs, nullptr, res->powers));
+        res->n_powers = n_powers_of(a->power_max, multi);
+        res->primes_scanned = a->n_max;
+        res->last_prime = h->resident_last;
+    } else {
+        // fused path: the bit-packed sieve output is scanned directly
+        const u64 bound = pss_nth_prime_upper(a->n_max) + 1;
+        if (bound > kMaxValue) return fail(h, PSS_EINVAL, "n = %llu needs primes beyond 2^%d", (unsigned long long)a->n_max, PSS_MAX_PRIME_BITS);
+        PSS_TRY(sieve_range(h, 0, bound));
+        if (h->sv_total < a->n_max) return fail(h, PSS_EINTERNAL, "prime count bound failed for n = %llu", (unsigned long long)a->n_max);
+        PSS_TRY(bitmap_reduce(h, a->power_max, multi));
+        PSS_TRY(bitmap_compare(h, 1, nullptr, a, res));
+    }
+    fill_stats(h, &res->stats, before);
+    return PSS_OK;
+}
+
+int pss_set_search_path(pss_handle* h, int materialised) {
+    PSS_TRY(check_handle(h));
+    h->search_path = materialised ? 1 : 0;
+    return PSS_OK;
+}
+
+int pss_slice_sieve_sums(pss_handle* h, uint64_t lo, uint64_t hi_excl, uint32_t power_max, uint32_t all_powers, uint64_t* count,
+                         uint32_t* sums_out) {
+    PSS_TRY(check_handle(h));
+    PSS_TRY(sieve_range(h, lo, hi_excl));
+    const bool multi = all_powers && power_max > 1;
+    PSS_TRY(bitmap_reduce(h, power_max, multi));
+    if (count) *count = h->bs_count;
+    if (sums_out) memcpy(sums_out, h->bs_sums, (size_t)n_powers_of(power_max, multi) * PSS_LIMBS * sizeof(u32));
+    return PSS_OK;
+}
+
+int pss_slice_scan_bitmap(pss_handle* h, uint64_t n_first, const uint32_t* carry_in, const pss_search_args* a, pss_search_result* res) {
+    PSS_TRY(check_handle(h));
+    PSS_TRY(validate_search(h, a, res));
+    if (n_first < 1) return fail(h, PSS_EINVAL, "n_first must be >= 1");
+    const pss_stats before = stats_snapshot(h);
+    memset(res, 0, sizeof *res);
+    PSS_TRY(bitmap_compare(h, n_first, carry_in, a, res));
     fill_stats(h, &res->stats, before);
     return PSS_OK;
 }

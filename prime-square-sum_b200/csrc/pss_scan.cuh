@@ -168,11 +168,11 @@ struct AccFn {
     }
 };
 
-template <int K, bool MULTI, int MODE>
+template <int K, bool MULTI, int MODE, class PT = ScanParams>
 struct Pass2Fn {
     using Lay = Layout<K, MULTI>;
     u32* run;
-    const ScanParams* P;
+    const PT* P;
     int* prevc;
     u32* mcount;
     u32* mfirst;

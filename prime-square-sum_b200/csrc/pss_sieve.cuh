@@ -10,7 +10,9 @@
 //                     (uint4), then every base prime p >= 61 (staged once in HBM/L2) is crossed off by
 //                     shared-memory atomicAnd on the packed words: 8 strands per prime (one per wheel
 //                     residue of the cofactor), each a byte-stride-p progression with a fixed bit.
-//                     Work split by hits-per-tile: CTA-wide (densest primes), warp-wide, 8-lane groups.
+//                     Work split by hits-per-tile: warp-wide (dense primes) and 8-lane groups (sparse primes);
+//                     per-prime reciprocal and strand geometry are staged once so the per-(prime, tile)
+//                     set-up is a dozen instructions.
 //                     Tiles are independent (first offsets are recomputed from the tile base), so any CTA
 //                     on any GPU can take any tile.  Output: bitmap tile (coalesced uint4 stores) +
 //                     per-chunk and per-tile popcounts.
@@ -23,17 +25,21 @@
 namespace pss {
 
 constexpr int kMaxPatterns = 4;
-constexpr int kMaxCtaWide = 64;   // primes handled by the whole CTA per tile
 
 struct SieveParams {
     u64 lo, hi;          // value range [lo, hi)
     u64 B_start;         // absolute byte index of bitmap byte 0 (multiple of 16)
     u32 tile_bytes;      // multiple of kChunkBytes
     u32 n_tiles;
-    const u32* base_primes;  // ascending, first entry = smallest prime not covered by a pattern
+    // base primes staged once in HBM (L2 resident): ascending, first entry = smallest prime not covered
+    // by a pattern.  Per prime: p, floor(2^32/p) for the mul-hi modulo, and per strand j the packed
+    // geometry  c_j | bit_j << 24  (c_j = floor(p*R[j]/30) < p < 2^24).
+    const u32* base_p;
+    const u32* base_inv;
+    const u32* base_strand;   // n_base * 8
     u32 n_base;
-    u32 n_cta_wide;      // base_primes[0 .. n_cta_wide) handled CTA-wide
-    u32 n_warp_wide;     // base_primes[n_cta_wide .. n_warp_wide) handled warp-wide, the rest by 8-lane groups
+    u32 n_warp_wide;     // base primes [0, n_warp_wide) handled warp-wide, the rest by 8-lane groups
+    u32 wide_index;      // 1: tile byte indices may exceed 2^32 -> 64-bit modulo path
     u32 n_pat;
     const uint4* pat[kMaxPatterns];
     u64 pat_period16[kMaxPatterns];   // 16 * period (bytes)
@@ -62,20 +68,26 @@ __global__ void k_build_pattern(uint8_t* out, u64 n_bytes, u32 q0, u32 q1, u32 q
     }
 }
 
-__device__ __forceinline__ u32 mod_u64_u32(u64 a, u32 p) {
-    // tile byte indices fit 32 bits up to 1.28e11; keep the cheap path cheap
-    return ((a >> 32) == 0) ? ((u32)a % p) : (u32)(a % p);
+// r = B0 mod p.  32-bit byte indices (hi < 1.28e11): one mul-hi with the staged reciprocal.
+__device__ __forceinline__ u32 tile_mod(u64 B0, u32 p, u32 inv, bool wide) {
+    if (wide) return (u32)(B0 % p);
+    const u32 b = (u32)B0;
+    u32 r = b - __umulhi(b, inv) * p;   // in [0, 2p)
+    if (r >= p) r -= p;
+    return r;
 }
 
-__device__ __forceinline__ void strike(u32* tile, u32 x, u32 bit) {
-    atomicAnd(&tile[x >> 2], ~(1u << (((x & 3u) << 3) + bit)));
+// first byte offset of the strand inside the tile: (c - r) mod p, never the prime itself (cofactor 1)
+__device__ __forceinline__ u32 first_hit(u32 p, u32 c, u32 r, bool is_strand0, u64 B0) {
+    u32 x = (c >= r) ? (c - r) : (c + p - r);
+    if (is_strand0 && B0 <= (u64)c) x += p;
+    return x;
 }
 
 template <int THREADS>
 __global__ void __launch_bounds__(THREADS) k_sieve(const SieveParams P) {
     extern __shared__ uint4 smem4[];
     u32* tile = reinterpret_cast<u32*>(smem4);
-    __shared__ u32 s_r[kMaxCtaWide];
     __shared__ u64 s_off16[kMaxPatterns];
     __shared__ u32 s_cnt[THREADS / 32];
 
@@ -84,6 +96,8 @@ __global__ void __launch_bounds__(THREADS) k_sieve(const SieveParams P) {
     const u32 tile_bytes = P.tile_bytes;
     const u32 tile_vec = tile_bytes >> 4;
     const u32 chunks_per_tile = tile_bytes / kChunkBytes;
+    const bool wide = P.wide_index != 0;
+    char* tile_b = reinterpret_cast<char*>(tile);
 
     for (u32 t = blockIdx.x; t < P.n_tiles; t += gridDim.x) {
         const u64 B0 = P.B_start + (u64)t * tile_bytes;
@@ -92,10 +106,9 @@ __global__ void __launch_bounds__(THREADS) k_sieve(const SieveParams P) {
         const u32 plim = (u32)fmin(sqrt(tile_end) + 2.0, 4.0e9);
 
         if (tid < P.n_pat) s_off16[tid] = (B0 % P.pat_period16[tid]) >> 4;
-        if (tid < P.n_cta_wide) s_r[tid] = mod_u64_u32(B0, P.base_primes[tid]);
         __syncthreads();
 
-        // ---- phase A: tile init from the pre-sieved patterns
+        // ---- phase A: tile init from the pre-sieved patterns (L2-resident, aligned uint4 loads)
         for (u32 i = tid; i < tile_vec; i += THREADS) {
             uint4 v = make_uint4(~0u, ~0u, ~0u, ~0u);
             for (u32 k = 0; k < P.n_pat; ++k) {
@@ -106,46 +119,40 @@ __global__ void __launch_bounds__(THREADS) k_sieve(const SieveParams P) {
         }
         __syncthreads();
 
-        // ---- phase B1: densest primes, whole CTA per prime (lane -> strand, tid/8 -> sub-sequence)
-        {
-            const u32 j = tid & 7u, sub = tid >> 3;
-            constexpr u32 NSUB = THREADS / 8;
-            for (u32 i = 0; i < P.n_cta_wide; ++i) {
-                const u32 p = P.base_primes[i];
-                if (p > plim) break;
-                u32 c, bit;
-                strand_geometry(p, j, c, bit);
-                u32 x = strand_first_offset(p, j, c, B0, s_r[i]) + sub * p;
-                const u32 stride = NSUB * p;
-                for (; x < tile_bytes; x += stride) strike(tile, x, bit);
-            }
-        }
-        // ---- phase B2: medium primes, one warp per prime (4 sub-sequences x 8 strands)
+        // ---- phase B2: dense primes, one warp per prime: lane -> (strand j, sub-sequence), stride 4p.
+        //      The stride is a multiple of 4 bytes, so the word-aligned address advances by a constant and
+        //      the bit mask is loop invariant: 4 instructions per cross-off.
         {
             const u32 j = lane & 7u, sub = lane >> 3;
-            for (u32 i = P.n_cta_wide + warp; i < P.n_warp_wide; i += NW) {
-                const u32 p = P.base_primes[i];
+            for (u32 i = warp; i < P.n_warp_wide; i += NW) {
+                const u32 p = __ldg(P.base_p + i);
                 if (p > plim) break;
-                const u32 r = mod_u64_u32(B0, p);
-                u32 c, bit;
-                strand_geometry(p, j, c, bit);
-                u32 x = strand_first_offset(p, j, c, B0, r) + sub * p;
+                const u32 r = tile_mod(B0, p, __ldg(P.base_inv + i), wide);
+                const u32 cb = __ldg(P.base_strand + i * 8u + j);
+                u32 x = first_hit(p, cb & 0xFFFFFFu, r, j == 0, B0) + sub * p;
+                const u32 mask = ~(1u << (((x & 3u) << 3) + (cb >> 24)));
                 const u32 stride = 4u * p;
-                for (; x < tile_bytes; x += stride) strike(tile, x, bit);
+                for (u32 xa = x & ~3u; xa < tile_bytes; xa += stride)
+                    atomicAnd(reinterpret_cast<u32*>(tile_b + xa), mask);
             }
         }
-        // ---- phase B3: sparse primes, 8 lanes (one per strand) per prime
+        // ---- phase B3: sparse primes, 8 lanes (one per strand) per prime, stride p (odd): the byte
+        //      position inside the word advances by p & 3, i.e. the mask rotates by a per-prime constant.
         {
             const u32 j = tid & 7u;
             constexpr u32 NG = THREADS / 8;
             for (u32 i = P.n_warp_wide + (tid >> 3); i < P.n_base; i += NG) {
-                const u32 p = P.base_primes[i];
+                const u32 p = __ldg(P.base_p + i);
                 if (p > plim) break;
-                const u32 r = mod_u64_u32(B0, p);
-                u32 c, bit;
-                strand_geometry(p, j, c, bit);
-                u32 x = strand_first_offset(p, j, c, B0, r);
-                for (; x < tile_bytes; x += p) strike(tile, x, bit);
+                const u32 r = tile_mod(B0, p, __ldg(P.base_inv + i), wide);
+                const u32 cb = __ldg(P.base_strand + i * 8u + j);
+                u32 x = first_hit(p, cb & 0xFFFFFFu, r, j == 0, B0);
+                u32 mask = ~(1u << (((x & 3u) << 3) + (cb >> 24)));
+                const u32 rot = (p & 3u) << 3;
+                for (; x < tile_bytes; x += p) {
+                    atomicAnd(reinterpret_cast<u32*>(tile_b + (x & ~3u)), mask);
+                    mask = __funnelshift_l(mask, mask, rot);
+                }
             }
         }
         __syncthreads();
@@ -187,7 +194,7 @@ __global__ void __launch_bounds__(THREADS) k_sieve(const SieveParams P) {
             for (u32 w = 0; w < NW; ++w) s += s_cnt[w];
             P.tile_counts[t] = s;
         }
-        // s_r / s_off16 / s_cnt / tile are rewritten only after the next iteration's first barrier
+        // s_off16 / s_cnt / tile are rewritten only after the next iteration's first barrier
         __syncthreads();
     }
 }

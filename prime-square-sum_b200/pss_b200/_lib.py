@@ -41,6 +41,7 @@ class Stats(ctypes.Structure):
         ("ms_sieve", ctypes.c_double), ("ms_count_scan", ctypes.c_double), ("ms_compact", ctypes.c_double),
         ("ms_power_scan", ctypes.c_double), ("ms_total_device", ctypes.c_double),
         ("primes", u64), ("sieve_lo", u64), ("sieve_hi", u64), ("launches", u64),
+        ("ms_bitmap_reduce", ctypes.c_double), ("ms_bitmap_compare", ctypes.c_double),
     ]
 
 
@@ -64,6 +65,7 @@ EXPORTS = [
     "pss_power_sum", "pss_primesum", "pss_search",
     "pss_slice_sieve", "pss_slice_reduce", "pss_slice_scan", "pss_slice_prefix_sums", "pss_slice_primes",
     "pss_slice_device_buffer", "pss_nth_prime_upper", "pss_stats_reset", "pss_stats_get",
+    "pss_set_search_path", "pss_slice_sieve_sums", "pss_slice_scan_bitmap",
 ]
 
 _cdll = None
@@ -102,6 +104,9 @@ def load_library() -> ctypes.CDLL:
     L.pss_slice_prefix_sums.argtypes = [H, u64, u64, u32, pu32, pu32]
     L.pss_slice_primes.argtypes = [H, u64, u64, pu64]
     L.pss_slice_device_buffer.argtypes = [H, ctypes.POINTER(ctypes.c_void_p), pu64]
+    L.pss_set_search_path.argtypes = [H, ctypes.c_int]
+    L.pss_slice_sieve_sums.argtypes = [H, u64, u64, u32, u32, pu64, pu32]
+    L.pss_slice_scan_bitmap.argtypes = [H, u64, pu32, ctypes.POINTER(SearchArgs), ctypes.POINTER(SearchResult)]
     L.pss_stats_reset.argtypes = [H]
     L.pss_stats_get.argtypes = [H, ctypes.POINTER(Stats)]
     L.pss_nth_prime_upper.argtypes = [u64]
@@ -113,6 +118,13 @@ def load_library() -> ctypes.CDLL:
         raise RuntimeError("libpss_b200.so ABI version mismatch")
     _cdll = L
     return L
+
+
+def stats_to_dict(s: "Stats") -> dict:
+    return {"ms_sieve": s.ms_sieve, "ms_count_scan": s.ms_count_scan, "ms_compact": s.ms_compact,
+            "ms_power_scan": s.ms_power_scan, "ms_bitmap_reduce": s.ms_bitmap_reduce,
+            "ms_bitmap_compare": s.ms_bitmap_compare, "ms_total_device": s.ms_total_device, "primes": int(s.primes),
+            "sieve_lo": int(s.sieve_lo), "sieve_hi": int(s.sieve_hi), "launches": int(s.launches)}
 
 
 def int_to_limbs(x: int, n: Optional[int] = None) -> np.ndarray:
@@ -289,9 +301,31 @@ class Handle:
     def stats(self) -> dict:
         s = Stats()
         self._check(self._L.pss_stats_get(self._h, ctypes.byref(s)))
-        return {"ms_sieve": s.ms_sieve, "ms_count_scan": s.ms_count_scan, "ms_compact": s.ms_compact,
-                "ms_power_scan": s.ms_power_scan, "ms_total_device": s.ms_total_device, "primes": int(s.primes),
-                "sieve_lo": int(s.sieve_lo), "sieve_hi": int(s.sieve_hi), "launches": int(s.launches)}
+        return stats_to_dict(s)
+
+    def set_search_path(self, materialised: bool):
+        self._check(self._L.pss_set_search_path(self._h, 1 if materialised else 0))
+
+    def slice_sieve_sums(self, lo: int, hi_excl: int, power_max: int, all_powers: bool = False):
+        """fused phase A: (count, [sum p^k per power record]) of the primes in [lo, hi)"""
+        np_ = power_max if (all_powers and power_max > 1) else 1
+        cnt = u64(0)
+        out = np.zeros(np_ * PSS_LIMBS, dtype=np.uint32)
+        self._check(self._L.pss_slice_sieve_sums(self._h, lo, hi_excl, power_max, 1 if all_powers else 0, ctypes.byref(cnt), _pu32(out)))
+        return int(cnt.value), [limbs_to_int(out[j * PSS_LIMBS:(j + 1) * PSS_LIMBS]) for j in range(np_)]
+
+    def slice_scan_bitmap(self, n_first: int, carry: Sequence[int], n_min: int, n_max: int, power_max: int, target: int,
+                          op: str = "==", all_powers: bool = False) -> SearchResult:
+        """fused phase B over the slice left resident by slice_sieve_sums"""
+        a, keep = self._make_args(n_min, n_max, power_max, all_powers, op, target)
+        np_ = power_max if (all_powers and power_max > 1) else 1
+        cin = np.zeros(np_ * PSS_LIMBS, dtype=np.uint32)
+        for j in range(np_):
+            cin[j * PSS_LIMBS:(j + 1) * PSS_LIMBS] = int_to_limbs(int(carry[j]) if carry else 0, PSS_LIMBS)
+        res = SearchResult()
+        self._check(self._L.pss_slice_scan_bitmap(self._h, n_first, _pu32(cin), ctypes.byref(a), ctypes.byref(res)))
+        del keep
+        return res
 
     def nth_prime_upper(self, n: int) -> int:
         return int(self._L.pss_nth_prime_upper(n))

@@ -134,10 +134,7 @@ def _outcome_from_result(res: "_lib.SearchResult", n_min, n_max, op, target) -> 
             last_match_n=int(r.last_match_n), cross_n=int(r.cross_n), cross_prime=int(r.cross_prime),
             sum_at_cross=_lib.limbs_to_int(r.sum_at_cross), sum_before_cross=_lib.limbs_to_int(r.sum_before_cross),
             final_sum=_lib.limbs_to_int(r.final_sum)))
-    s = res.stats
-    stats = {"ms_sieve": s.ms_sieve, "ms_count_scan": s.ms_count_scan, "ms_compact": s.ms_compact,
-             "ms_power_scan": s.ms_power_scan, "ms_total_device": s.ms_total_device, "primes": int(s.primes),
-             "sieve_lo": int(s.sieve_lo), "sieve_hi": int(s.sieve_hi), "launches": int(s.launches)}
+    stats = _lib.stats_to_dict(res.stats)
     return SearchOutcome(n_min, n_max, op, target, int(res.last_prime), powers, stats)
 
 
@@ -261,9 +258,9 @@ def distributed_search(target: int, n_max: int, power: int = 2, n_min: int = 1, 
 
     hi = h.nth_prime_upper(n_max) + 1
     lo_g, hi_g = partition_range(hi, world)[rank]
-    count_g, _ = h.slice_sieve(lo_g, hi_g)
     np_ = _np(power, all_powers)
-    sums_g = h.slice_reduce(0, count_g, power, all_powers) if count_g else [0] * np_
+    # fused phase A: sieve + per-tile sums (no u64 prime buffer); leaves the slice's bitmap resident
+    count_g, sums_g = h.slice_sieve_sums(lo_g, hi_g, power, all_powers)
 
     # ---- the one exchange: 8 B count + np_ * 48 B of limbs per rank
     payload = [count_g & 0xFFFFFFFF, count_g >> 32]
@@ -287,7 +284,7 @@ def distributed_search(target: int, n_max: int, power: int = 2, n_min: int = 1, 
     local = None
     take = min(count_g, max(0, n_max - n_before))
     if take > 0:
-        res = h.slice_scan(0, take, n_before + 1, carry, n_min, n_max, power, target, op, all_powers)
+        res = h.slice_scan_bitmap(n_before + 1, carry, n_min, n_max, power, target, op, all_powers)
         local = _outcome_from_result(res, n_min, n_max, op, target)
     if gather is not None:
         outs = gather(local)

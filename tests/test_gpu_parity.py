@@ -139,7 +139,15 @@ def test_every_partial_sum(handle, orc, golden):
 
 
 # ------------------------------------------------------------------------------- K3 scan + compare
-def test_find_matches_golden(handle, golden):
+@pytest.fixture(params=["fused", "materialised"])
+def search_path(request, handle):
+    """both query paths: fused (K2/K3 read the sieve bitmap) and materialised (K1c u64 primes + look-back scan)"""
+    handle.set_search_path(request.param == "materialised")
+    yield request.param
+    handle.set_search_path(False)
+
+
+def test_find_matches_golden(handle, golden, search_path):
     """the reference evaluator's own answers (utils/grammar.py find_matches) for constant targets"""
     from pss_b200 import search
     for case in golden["find_matches"]:
@@ -162,7 +170,7 @@ def test_find_matches_golden(handle, golden):
 
 @pytest.mark.parametrize("k,multi", [(1, False), (2, False), (3, False), (4, False), (5, False), (6, False), (7, False),
                                      (8, False), (2, True), (3, True), (5, True), (6, True)])
-def test_synthetic_hits_and_brackets(handle, orc, k, multi):
+def test_synthetic_hits_and_brackets(handle, orc, k, multi, search_path):
     """No trisum(666) config can match: validate match index / bracket with synthetic targets
     at thread, warp, tile and range boundaries."""
     from pss_b200 import search
@@ -172,8 +180,10 @@ def test_synthetic_hits_and_brackets(handle, orc, k, multi):
     sums = {p: orc.c_prefix_sums(primes, p) for p in powers}
     items = 16 if (k <= 3 and not multi) else 8
     tile = 256 * items
-    hits = sorted({1, 2, 7, items, items + 1, 32 * items, 32 * items + 1, tile - 1, tile, tile + 1, 3 * tile, 3 * tile + 1,
-                   n_max - 1, n_max})
+    # thread / warp / tile boundaries of the materialised scan; the fused scan's tile boundaries fall at data
+    # dependent indices (one tile = 737 280 integers), 3, 4 and the range ends exercise its 2-3-5 head
+    hits = sorted({1, 2, 3, 4, 7, items, items + 1, 32 * items, 32 * items + 1, tile - 1, tile, tile + 1, 3 * tile,
+                   3 * tile + 1, n_max - 1, n_max})
     for hit in hits:
         p = powers[hit % len(powers)]
         target = sums[p][hit - 1]
@@ -209,7 +219,7 @@ def test_synthetic_hits_and_brackets(handle, orc, k, multi):
         assert got == exp, op
 
 
-def test_trisum666_configs_small(handle, orc):
+def test_trisum666_configs_small(handle, orc, search_path):
     """config C1 and the C3/C4 shape at a size the oracle finishes in seconds: no match, bracket = n_max"""
     from pss_b200 import search
     T = orc.trisum(666)
@@ -224,6 +234,61 @@ def test_trisum666_configs_small(handle, orc):
     out = search.search(T, n_max, power=5, n_min=5 * 10 ** 5, all_powers=True)   # C5 shape
     assert out.first() is None
     assert [p.final_sum for p in out.powers] == orc.c_power_sums(primes, [1, 2, 3, 4, 5])
+
+
+def test_fused_tile_boundaries(handle, orc):
+    """fused path: hits on the first / last prime of several 737 280-integer scan tiles and sieve tiles"""
+    from pss_b200 import search
+    n_max = 400000
+    primes = orc.c_first_n_primes(n_max)
+    sums = orc.c_prefix_sums(primes, 2)
+    hits = set()
+    for boundary in (737280, 2 * 737280, 98304 * 30, 5 * 737280):
+        idx = int(np.searchsorted(primes, boundary))   # primes[idx] is the first prime >= boundary
+        hits.update({idx, idx + 1, idx + 2})
+    for hit in sorted(hits):
+        out = search.search(sums[hit - 1], n_max, power=2)
+        assert out.first() == (hit, 2), hit
+        po = out.powers[0]
+        assert po.cross_prime == int(primes[hit - 1]) and po.sum_before_cross == sums[hit - 2]
+        assert po.final_sum == sums[-1] and out.last_prime == int(primes[-1])
+
+
+def test_fused_slices_compose(handle, orc):
+    """fused multi-GPU decomposition on one device: slice_sieve_sums / slice_scan_bitmap with carries"""
+    from pss_b200 import search
+    n_max = 300000
+    hi = handle.nth_prime_upper(n_max) + 1
+    primes = orc.c_first_n_primes(n_max)
+    for power, multi in ((3, False), (4, True)):
+        powers = list(range(1, power + 1)) if multi else [power]
+        sums = orc.c_prefix_sums(primes[:200001], powers[-1])
+        target = sums[200000]
+        slices = search.partition_range(hi, 4)
+        info = [handle.slice_sieve_sums(lo, hi_g, power, multi) for lo, hi_g in slices]
+        counts = [c for c, _ in info]
+        ssums = [s for _, s in info]
+        assert sum(counts) >= n_max
+        # slice totals against the oracle
+        off = 0
+        for (c, sm) in info[:3]:
+            assert sm == orc.c_power_sums(primes[off:off + c], powers)
+            off += c
+        parts = []
+        for g, (lo, hi_g) in enumerate(slices):
+            n_before, carry = search.combine_slices(counts, ssums, g)
+            take = min(counts[g], max(0, n_max - n_before))
+            if take == 0:
+                parts.append(None)
+                continue
+            handle.slice_sieve_sums(lo, hi_g, power, multi)
+            res = handle.slice_scan_bitmap(n_before + 1, carry, 1, n_max, power, target, "==", multi)
+            parts.append(search._outcome_from_result(res, 1, n_max, "==", target))
+        merged = search.merge_outcomes(parts, 1, n_max, "==", target)
+        assert merged.first() == (200001, powers[-1])
+        assert [p.final_sum for p in merged.powers] == orc.c_power_sums(primes, powers)
+        assert merged.powers[-1].sum_before_cross == sums[199999]
+        assert merged.last_prime == int(primes[-1])
 
 
 def test_slices_compose(handle, orc):
@@ -286,13 +351,13 @@ def test_at_scale_1e8(handle, golden):
     assert out.last_prime == row["p_n"]
     assert [str(p.final_sum) for p in out.powers] == [row["sums"][str(k)] for k in range(1, 6)]
     assert out.first() is None
+    got = handle.generate_n_primes(10 ** 8)
     ptr, cnt = handle.slice_device_buffer()
     assert cnt == 10 ** 8
-    got = handle.slice_primes(0, 10 ** 8)
     assert sha_u64(got) == row["sha256_primes_le_u64"]
 
 
-def test_at_scale_1e9_c3(handle, golden):
+def test_at_scale_1e9_c3(handle, golden, search_path):
     """config C3: does_exist primesum(n,2) == trisum(666), n <= 1e9 — no match, bracket n = 1e9, exact S_2"""
     from pss_b200 import search
     row = next(r for r in golden["at_scale"] if r["n"] == 10 ** 9)
