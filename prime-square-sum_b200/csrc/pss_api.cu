@@ -77,7 +77,7 @@ struct pss_handle {
     u32 n_base_dev = 0;
 
     // sieve workspace / state of the last sieve
-    DevBuf bitmap, chunk_counts, tile_counts, tile_prefix;
+    DevBuf bitmap, chunk_counts, tile_counts, tile_prefix, tile_nact;
     u64 sv_lo = 0, sv_hi = 0, sv_B_start = 0, sv_total = 0, sv_c235 = 0;
     u32 sv_tile_bytes = 0, sv_n_tiles = 0;
     bool sv_valid = false;
@@ -88,7 +88,7 @@ struct pss_handle {
     u64 resident_last = 0;
 
     // fused path: column-major tile records of the last bitmap reduce and their prefixes
-    DevBuf cols, col_prefix;
+    DevBuf cols, col_prefix, thread_rec;
     bool bs_valid = false;
     u32 bs_K = 0, bs_n_tiles = 0, bs_total_cols = 0;
     bool bs_multi = false;
@@ -310,6 +310,17 @@ int sieve_range(pss_handle* h, u64 lo, u64 hi) {
         sp.n_base = (e > b) ? (u32)(e - b) : 0;
         const u32 warp_lim = tile_bytes / std::max<u32>(h->warp_wide_div, 1);
         sp.n_warp_wide = (e > b) ? (u32)(std::lower_bound(b, e, warp_lim) - b) : 0;
+        // per tile: how many base primes satisfy p*p < tile end (ascending in t)
+        std::vector<u32> nact(n_tiles);
+        for (u32 t = 0; t < n_tiles; ++t) {
+            const u64 tile_end = std::min<u64>((B_start + (u64)(t + 1) * tile_bytes) * 30ull, hi);
+            const u64 pl = isqrt_u64(tile_end - 1);
+            nact[t] = (e > b) ? (u32)(std::upper_bound(b, e, (u32)std::min<u64>(pl, 0xFFFFFFFFull)) - b) : 0;
+        }
+        PSS_TRY(ensure(h, h->tile_nact, (size_t)n_tiles * sizeof(u32)));
+        CU_TRY(h, cudaMemcpyAsync(h->tile_nact.p, nact.data(), (size_t)n_tiles * sizeof(u32), cudaMemcpyHostToDevice, h->stream));
+        CU_TRY(h, cudaStreamSynchronize(h->stream));   // nact is a stack-lifetime staging buffer
+        sp.tile_nact = static_cast<const u32*>(h->tile_nact.p);
     }
     sp.n_pat = h->n_pat;
     for (u32 g = 0; g < h->n_pat; ++g) {
@@ -587,6 +598,8 @@ void fill_bscan_common(pss_handle* h, BScanParams& bp) {
     for (u64 q : {2ull, 3ull, 5ull})
         if (q >= h->sv_lo && q < h->sv_hi) bp.small_primes[bp.n_small++] = q;
     bp.col_stride = (u64)bp.n_tiles + 1;
+    bp.thread_stride = (u64)bp.n_tiles * kBsThreads;
+    bp.thread_rec = static_cast<u32*>(h->thread_rec.p);
 }
 
 // phase A of the fused path: per-tile (count, sums) records, column prefixes, slice totals
@@ -606,6 +619,8 @@ int bitmap_reduce(pss_handle* h, u32 K, bool multi) {
     }
     BScanParams bp;
     fill_bscan_common(h, bp);
+    PSS_TRY(ensure(h, h->thread_rec, (size_t)ncols * bp.thread_stride * sizeof(u32)));
+    bp.thread_rec = static_cast<u32*>(h->thread_rec.p);
     PSS_TRY(ensure(h, h->cols, (size_t)ncols * bp.col_stride * sizeof(u32)));
     PSS_TRY(ensure(h, h->col_prefix, (size_t)ncols * bp.col_stride * sizeof(u64)));
     bp.cols = static_cast<u32*>(h->cols.p);
@@ -804,7 +819,7 @@ int pss_close(pss_handle* h) {
     if (!h) return PSS_OK;
     cudaSetDevice(h->device);
     if (h->stream) cudaStreamSynchronize(h->stream);
-    for (DevBuf* b : {&h->d_base, &h->d_base_inv, &h->d_base_strand, &h->cols, &h->col_prefix, &h->bitmap, &h->chunk_counts, &h->tile_counts, &h->tile_prefix, &h->primes, &h->status, &h->agg,
+    for (DevBuf* b : {&h->d_base, &h->d_base_inv, &h->d_base_strand, &h->cols, &h->col_prefix, &h->thread_rec, &h->tile_nact, &h->bitmap, &h->chunk_counts, &h->tile_counts, &h->tile_prefix, &h->primes, &h->status, &h->agg,
                       &h->incl, &h->misc, &h->prefix_out, &h->user_vals})
         if (b->p) cudaFree(b->p);
     for (auto& p : h->d_pat)

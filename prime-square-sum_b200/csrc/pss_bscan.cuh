@@ -36,6 +36,10 @@ struct BScanParams {
     u32* cols;
     const u64* col_prefix;   // exclusive prefixes, same layout, (n_tiles + 1) entries per column
     u64 col_stride;
+    // per-thread records of the reduce pass (count, sums), column major over global thread ids, so that
+    // the compare pass needs no second power pass to rebuild its block scan
+    u32* thread_rec;         // col c of global thread g at thread_rec[c * thread_stride + g]
+    u64 thread_stride;
     // compare mode
     u64 n_first;             // global 1-based index of the slice's first prime
     u64 n_min, n_max;
@@ -48,22 +52,39 @@ struct BScanParams {
     u32* error_flag;
 };
 
-// Decode loop: one prime per iteration for every lane that still has one (lanes own equal word counts,
-// so the trip counts differ only by the local density fluctuation).
+// Words are staged BIT-REVERSED: the lowest prime of a word is its most significant set bit m (one FLO).
+// Original bit b = 31 - m, so the integer offset inside the word is 30*(b/8) + R[b%8]
+//   = (R[7 - m%8] + 90) - 30*(m/8);  the bracketed byte table sits in two registers and is read with one
+// PRMT (selector nibbles 1..3 = sign replication of a byte < 128, i.e. zero: no masking needed).
+__device__ __forceinline__ u32 msb_value_offset(u32 m) {
+    // R reversed + 90: j = 0..7 -> 29,23,19,17,13,11,7,1 (+90) = 119,113,109,107,103,101,97,91
+    // (inline PTX: the __byte_perm intrinsic masks the selector to 3 bits per nibble and would drop the
+    // sign-replication flags)
+    u32 r;
+    asm("prmt.b32 %0, %1, %2, %3;" : "=r"(r) : "r"(0x6B6D7177u), "r"(0x5B616567u), "r"((m & 7u) | 0x8880u));
+    return r - 30u * (m >> 3);
+}
+
+// Decode loop: one prime per iteration for every lane that still has one (lanes own equal word counts, so
+// the trip counts differ only by the local density fluctuation).  The refill of an exhausted word is
+// branch-free (unconditional shared-memory load + selects) so the warp never splits around the power chain.
 template <class F>
-__device__ __forceinline__ void walk_words(const u32* my_words, u64 value_base, const u32* s_lut, F& f) {
-    u32 wi = 0, w = 0;
-    u64 wbase = value_base;
+__device__ __forceinline__ void walk_words(const u32* my_words, u64 value_base, F& f) {
+    u32 wi = 0, w = 0, woff = 0;
     for (;;) {
-        while (w == 0) {
-            if (wi == kWordsPerThread) return;
-            w = my_words[wi];
-            wbase = value_base + (u64)wi * 120ull;
-            ++wi;
+        const bool need = (w == 0);
+        const u32 idx = min(wi, (u32)(kWordsPerThread - 1));
+        const u32 nw = my_words[idx];
+        w = need ? ((wi < (u32)kWordsPerThread) ? nw : 0u) : w;
+        woff = need ? idx * 120u : woff;
+        wi += need ? 1u : 0u;
+        if (w == 0) {                       // empty word (rare) or end of this thread's range
+            if (wi > (u32)kWordsPerThread) return;
+            continue;
         }
-        const u32 b = __ffs(w) - 1;
-        w &= w - 1;
-        if (!f(wbase + s_lut[b])) return;
+        const u32 m = 31u - (u32)__clz(w);
+        w ^= (1u << m);
+        if (!f(value_base + (woff + msb_value_offset(m)))) return;
     }
 }
 
@@ -82,16 +103,16 @@ struct BsCmpFn {
     using Lay = Layout<K, MULTI>;
     Pass2Fn<K, MULTI, kModeCompare, BScanParams> inner;
     const BScanParams* P;
-    u64 n;           // index of the next prime
-    u64 tile_n0;     // index of the tile's first prime
+    u64 tile_n0;     // global index of the tile's first prime
+    u32 li;          // tile-local index of the next prime
+    u32 lmin, lmax;  // window [n_min, n_max] in tile-local indices (saturated)
     __device__ __forceinline__ bool operator()(u64 p) {
-        if (n > P->n_max) return false;
-        inner.n = n;
+        if (li > lmax) return false;
         inner.p = p;
-        inner.local_idx = (u32)(n - tile_n0);
-        inner.in_window = (n >= P->n_min);
+        inner.local_idx = li;
+        inner.in_window = (li >= lmin);
         power_chain<K, MULTI>(p, inner);
-        if (n == P->n_max) {   // exactly one thread in the grid: S(n_max) and p_{n_max}
+        if (li == lmax && tile_n0 + li == P->n_max) {   // exactly one thread in the grid: S(n_max), p_{n_max}
             *P->last_prime_out = p;
 #pragma unroll
             for (int jj = 0; jj < Lay::NP; ++jj)
@@ -99,7 +120,7 @@ struct BsCmpFn {
                 for (int i = 0; i < PSS_LIMBS; ++i)
                     P->results[jj].final_sum[i] = (i < Lay::width(jj)) ? inner.run[Lay::offset(jj) + i] : 0u;
         }
-        ++n;
+        ++li;
         return true;
     }
 };
@@ -111,13 +132,11 @@ __global__ void __launch_bounds__(kBsThreads) k_bitmap_scan(const __grid_constan
     constexpr int WPT = kWordsPerThread, PAD = WPT + 1;
 
     __shared__ u32 s_words[T * PAD];
-    __shared__ u32 s_lut[32];
     __shared__ u32 s_warp[NWARP][TOTAL + 1];   // [..][TOTAL] = count
     __shared__ u32 s_excl[TOTAL];
     __shared__ u64 s_tile_n0;
 
     const u32 tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
-    if (tid < 32) s_lut[tid] = (tid >> 3) * 30u + wheel_residue(tid & 7u);
 
     for (u32 tile = blockIdx.x; tile < P.n_tiles; tile += gridDim.x) {
         if constexpr (MODE == kBsCompare) {
@@ -135,7 +154,8 @@ __global__ void __launch_bounds__(kBsThreads) k_bitmap_scan(const __grid_constan
             if (wq + 4 <= P.n_words) v = __ldg(g4 + q);
             const u32 wl = 4u * q;                // first word (tile local); 4 | WPT so one owner thread
             const u32 dst = (wl / WPT) * PAD + (wl % WPT);
-            s_words[dst] = v.x; s_words[dst + 1] = v.y; s_words[dst + 2] = v.z; s_words[dst + 3] = v.w;
+            s_words[dst] = __brev(v.x); s_words[dst + 1] = __brev(v.y);
+            s_words[dst + 2] = __brev(v.z); s_words[dst + 3] = __brev(v.w);
         }
         __syncthreads();
 
@@ -143,20 +163,29 @@ __global__ void __launch_bounds__(kBsThreads) k_bitmap_scan(const __grid_constan
         const u64 value_base = (P.B_start + 4ull * (word0 + (u64)tid * WPT)) * 30ull;
         const bool has_small = (tile == 0 && tid == 0 && P.n_small > 0);
 
-        // ---- pass 1: thread-local count and sums
+        // ---- pass 1: thread-local count and sums (reduce pass: decode + powers; compare pass: reload the
+        //      reduce pass's per-thread record)
         u32 acc[TOTAL];
-#pragma unroll
-        for (int i = 0; i < TOTAL; ++i) acc[i] = 0;
         u32 cnt = 0;
+        const u64 gthread = (u64)tile * T + tid;
+        if constexpr (MODE == kBsReduce) {
 #pragma unroll
-        for (int i = 0; i < WPT; ++i) cnt += __popc(my_words[i]);
-        {
+            for (int i = 0; i < TOTAL; ++i) acc[i] = 0;
+#pragma unroll
+            for (int i = 0; i < WPT; ++i) cnt += __popc(my_words[i]);
             BsAccFn<K, MULTI> fn{acc};
             if (has_small) {
                 for (u32 i = 0; i < P.n_small; ++i) fn(P.small_primes[i]);
                 cnt += P.n_small;
             }
-            walk_words(my_words, value_base, s_lut, fn);
+            walk_words(my_words, value_base, fn);
+            P.thread_rec[gthread] = cnt;
+#pragma unroll
+            for (int i = 0; i < TOTAL; ++i) P.thread_rec[(u64)(1 + i) * P.thread_stride + gthread] = acc[i];
+        } else {
+            cnt = __ldg(P.thread_rec + gthread);
+#pragma unroll
+            for (int i = 0; i < TOTAL; ++i) acc[i] = __ldg(P.thread_rec + (u64)(1 + i) * P.thread_stride + gthread);
         }
 
         if constexpr (MODE == kBsReduce) {
@@ -279,12 +308,15 @@ __global__ void __launch_bounds__(kBsThreads) k_bitmap_scan(const __grid_constan
                 for_each_power<0, Lay>(op);
             }
             const u64 tile_n0 = s_tile_n0;
-            BsCmpFn<K, MULTI> fn{{run, &P, prevc, mcount, mfirst, mlast, 0, 0, 0, 0, false}, &P,
-                                 tile_n0 + s_warp[warp][TOTAL] + cexc, tile_n0};
+            // window in tile-local indices: a tile holds < 2^20 primes, so saturating to u32 is exact
+            const u32 lmin = (P.n_min > tile_n0) ? (u32)min(P.n_min - tile_n0, (u64)0xFFFFFFFFull) : 0u;
+            const u32 lmax = (u32)min(P.n_max - tile_n0, (u64)0xFFFFFFFEull);   // n_max >= tile_n0 (checked above)
+            BsCmpFn<K, MULTI> fn{{run, &P, prevc, mcount, mfirst, mlast, tile_n0, 0, 0, 0, false}, &P, tile_n0,
+                                 s_warp[warp][TOTAL] + cexc, lmin, lmax};
             bool go = true;
             if (has_small)
                 for (u32 i = 0; i < P.n_small && go; ++i) go = fn(P.small_primes[i]);
-            if (go) walk_words(my_words, value_base, s_lut, fn);
+            if (go) walk_words(my_words, value_base, fn);
 #pragma unroll
             for (int jj = 0; jj < NP; ++jj) {
                 if (__any_sync(0xFFFFFFFFu, mcount[jj] != 0)) {

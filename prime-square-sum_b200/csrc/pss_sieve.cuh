@@ -39,6 +39,8 @@ struct SieveParams {
     const u32* base_strand;   // n_base * 8
     u32 n_base;
     u32 n_warp_wide;     // base primes [0, n_warp_wide) handled warp-wide, the rest by 8-lane groups
+    const u32* tile_nact;     // per tile: number of base primes with p*p < tile end (the only ones that can
+                              // still cross something off there)
     u32 wide_index;      // 1: tile byte indices may exceed 2^32 -> 64-bit modulo path
     u32 n_pat;
     const uint4* pat[kMaxPatterns];
@@ -101,10 +103,6 @@ __global__ void __launch_bounds__(THREADS) k_sieve(const SieveParams P) {
 
     for (u32 t = blockIdx.x; t < P.n_tiles; t += gridDim.x) {
         const u64 B0 = P.B_start + (u64)t * tile_bytes;
-        // largest base prime that can still have an unmarked multiple in this tile: p*p < tile end
-        const double tile_end = (double)(B0 + tile_bytes) * 30.0;
-        const u32 plim = (u32)fmin(sqrt(tile_end) + 2.0, 4.0e9);
-
         if (tid < P.n_pat) s_off16[tid] = (B0 % P.pat_period16[tid]) >> 4;
         __syncthreads();
 
@@ -119,16 +117,28 @@ __global__ void __launch_bounds__(THREADS) k_sieve(const SieveParams P) {
         }
         __syncthreads();
 
+        const u32 nact = __ldg(P.tile_nact + t);
         // ---- phase B2: dense primes, one warp per prime: lane -> (strand j, sub-sequence), stride 4p.
         //      The stride is a multiple of 4 bytes, so the word-aligned address advances by a constant and
-        //      the bit mask is loop invariant: 4 instructions per cross-off.
+        //      the bit mask is loop invariant.  The next prime's table entries are prefetched (L2 latency).
         {
             const u32 j = lane & 7u, sub = lane >> 3;
-            for (u32 i = warp; i < P.n_warp_wide; i += NW) {
-                const u32 p = __ldg(P.base_p + i);
-                if (p > plim) break;
-                const u32 r = tile_mod(B0, p, __ldg(P.base_inv + i), wide);
-                const u32 cb = __ldg(P.base_strand + i * 8u + j);
+            const u32 nw = min(P.n_warp_wide, nact);
+            u32 i = warp, p_n = 0, inv_n = 0, cb_n = 0;
+            if (i < nw) {
+                p_n = __ldg(P.base_p + i);
+                inv_n = __ldg(P.base_inv + i);
+                cb_n = __ldg(P.base_strand + i * 8u + j);
+            }
+            while (i < nw) {
+                const u32 p = p_n, inv = inv_n, cb = cb_n;
+                i += NW;
+                if (i < nw) {
+                    p_n = __ldg(P.base_p + i);
+                    inv_n = __ldg(P.base_inv + i);
+                    cb_n = __ldg(P.base_strand + i * 8u + j);
+                }
+                const u32 r = tile_mod(B0, p, inv, wide);
                 u32 x = first_hit(p, cb & 0xFFFFFFu, r, j == 0, B0) + sub * p;
                 const u32 mask = ~(1u << (((x & 3u) << 3) + (cb >> 24)));
                 const u32 stride = 4u * p;
@@ -141,11 +151,21 @@ __global__ void __launch_bounds__(THREADS) k_sieve(const SieveParams P) {
         {
             const u32 j = tid & 7u;
             constexpr u32 NG = THREADS / 8;
-            for (u32 i = P.n_warp_wide + (tid >> 3); i < P.n_base; i += NG) {
-                const u32 p = __ldg(P.base_p + i);
-                if (p > plim) break;
-                const u32 r = tile_mod(B0, p, __ldg(P.base_inv + i), wide);
-                const u32 cb = __ldg(P.base_strand + i * 8u + j);
+            u32 i = P.n_warp_wide + (tid >> 3), p_n = 0, inv_n = 0, cb_n = 0;
+            if (i < nact) {
+                p_n = __ldg(P.base_p + i);
+                inv_n = __ldg(P.base_inv + i);
+                cb_n = __ldg(P.base_strand + i * 8u + j);
+            }
+            while (i < nact) {
+                const u32 p = p_n, inv = inv_n, cb = cb_n;
+                i += NG;
+                if (i < nact) {
+                    p_n = __ldg(P.base_p + i);
+                    inv_n = __ldg(P.base_inv + i);
+                    cb_n = __ldg(P.base_strand + i * 8u + j);
+                }
+                const u32 r = tile_mod(B0, p, inv, wide);
                 u32 x = first_hit(p, cb & 0xFFFFFFu, r, j == 0, B0);
                 u32 mask = ~(1u << (((x & 3u) << 3) + (cb >> 24)));
                 const u32 rot = (p & 3u) << 3;
