@@ -271,9 +271,9 @@ def distributed_search(target: int, n_max: int, power: int = 2, n_min: int = 1, 
     else:
         dev = torch.device("cuda", torch.cuda.current_device()) if dist.get_backend(group) == "nccl" else torch.device("cpu")
         mine = torch.tensor(payload, dtype=torch.int64, device=dev)
-        allv = torch.empty(world * len(payload), dtype=torch.int64, device=dev)
-        dist.all_gather_into_tensor(allv, mine, group=group)
-        rows = allv.view(world, -1).cpu().tolist()
+        parts = [torch.empty_like(mine) for _ in range(world)]
+        dist.all_gather(parts, mine, group=group)       # NCCL over NVLink on the GPU box, gloo in CPU tests
+        rows = [t.cpu().tolist() for t in parts]
     counts = [r[0] | (r[1] << 32) for r in rows]
     sums = [[_lib.limbs_to_int(r[2 + j * _lib.PSS_LIMBS: 2 + (j + 1) * _lib.PSS_LIMBS]) for j in range(np_)] for r in rows]
     if sum(counts) < n_max:

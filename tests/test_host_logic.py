@@ -1,0 +1,285 @@
+"""Host-side logic of the drop-in layer, no GPU: API mirror semantics and errors, slice partitioning, carry
+composition, outcome merging / enumeration order, checkpoint format, and the N>1 path over gloo (world_size 2)
+with a handle stand-in backed by the oracle."""
+import math
+import os
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+# --------------------------------------------------------------------------- API mirror (no device needed)
+def test_sieve_facade_semantics_without_device():
+    from pss_b200 import sieve
+    # edge cases never reach the device (utils/sieve.py:473-474, 558-559, 605-606)
+    for limit in (-5, 0, 1):
+        p = sieve.generate_primes(limit)
+        assert p.dtype == np.int64 and len(p) == 0
+    assert len(sieve.generate_n_primes(0)) == 0 and len(sieve.generate_n_primes(-3)) == 0
+    assert len(sieve.generate_primes_range(10, 10)) == 0 and len(sieve.generate_primes_range(0, 1)) == 0
+    assert sieve.prime_count(1) == 0
+    with pytest.raises(ValueError, match=r"n must be positive \(1-indexed\)"):
+        sieve.nth_prime(0)
+    with pytest.raises(ValueError, match="Invalid algorithm: nope"):
+        sieve.configure(algorithm="nope")
+    with pytest.raises(ValueError, match="Unknown algorithm"):
+        sieve.generate_primes(100, algorithm="nope")
+    with pytest.raises(ValueError, match="not provided"):
+        sieve.generate_primes(100, algorithm="primesieve")
+    sieve.configure(algorithm="b200", max_memory_mb=123, prefer="gpu")
+    assert sieve.get_config() == {"algorithm": "b200", "max_memory_mb": 123, "prefer": "gpu"}
+    sieve.configure(algorithm="auto")
+    info = sieve.get_algorithm_info()
+    assert info["b200"]["available"] and info["auto"]["available"] and not info["basic"]["available"]
+    assert sieve.get_available_algorithms() == ["auto", "b200"]
+
+
+def test_primesum_argument_errors_without_device():
+    from pss_b200 import primesum
+    assert primesum(0, 2) == 0 and primesum(0, 5) == 0 and primesum(9, 0) == 9 and primesum(9.0, 0) == 9
+    with pytest.raises(ValueError, match=r"primesum\(\) requires non-negative n, got -1"):
+        primesum(-1, 2)
+    with pytest.raises(ValueError, match=r"primesum\(\) requires integral value, got 7.5"):
+        primesum(7.5, 2)
+    with pytest.raises(TypeError, match=r"primesum\(\) requires int, got str"):
+        primesum("7", 2)
+    with pytest.raises(ValueError, match="power"):
+        primesum(5, 9)
+    import inspect
+    sig = inspect.signature(primesum)
+    required = [p for p in sig.parameters.values() if p.default is inspect.Parameter.empty and p.kind == p.POSITIONAL_OR_KEYWORD]
+    assert len(required) == 1            # registry arg_count == 1 (tests/test_sequences.py:279-283)
+
+
+def test_plugin_file_exposes_user_functions():
+    import importlib.util
+    path = os.path.join(ROOT, "prime-square-sum_b200", "pss_b200", "plugin.py")
+    spec = importlib.util.spec_from_file_location("pss_plugin_under_test", path)
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    public = [n for n in dir(mod) if not n.startswith("_") and callable(getattr(mod, n)) and not isinstance(getattr(mod, n), type)]
+    assert sorted(public) == ["nth_prime", "prime_count", "primesum"]
+    assert mod.primesum(0, 2) == 0
+
+
+@pytest.mark.skipif(not os.path.exists("/root/reference/utils/function_registry.py"), reason="reference tree not present")
+def test_plugin_loads_into_the_reference_registry():
+    """the reference's own loader accepts the plugin and `user.primesum` wins unqualified lookup
+    (utils/function_registry.py:134,499-551)"""
+    sys.path.insert(0, "/root/reference")
+    try:
+        from utils.function_registry import FunctionRegistry
+        reg = FunctionRegistry()
+        n = reg.load_from_file(os.path.join(ROOT, "prime-square-sum_b200", "pss_b200", "plugin.py"))
+        assert n >= 3
+        f = reg.get("primesum")
+        assert f(0, 2) == 0
+        assert "pss_b200" in sys.modules[f.__module__].__file__ or f.__module__ != "utils.sequences"
+    finally:
+        sys.path.remove("/root/reference")
+
+
+def test_limb_conversion_roundtrip():
+    from pss_b200 import _lib
+    T = 37005443752611483714216385166550857181329086284892731078593232926279977894581784762614450464857290
+    limbs = _lib.int_to_limbs(T)
+    assert len(limbs) == 11 and _lib.limbs_to_int(limbs) == T         # 325 bits = 11 limbs
+    assert _lib.limbs_to_int(_lib.int_to_limbs(0)) == 0
+    assert len(_lib.int_to_limbs(5, 12)) == 12
+    with pytest.raises(OverflowError):
+        _lib.int_to_limbs(1 << 400, 12)
+    with pytest.raises(ValueError):
+        _lib.int_to_limbs(-1)
+
+
+# --------------------------------------------------------------------------- partitioning / composition
+def test_partition_range_is_contiguous_aligned_and_balanced(orc):
+    from pss_b200 import search
+    hi = 22801763490
+    for parts in (1, 2, 4, 8):
+        sl = search.partition_range(hi, parts)
+        assert len(sl) == parts and sl[0][0] == 0 and sl[-1][1] == hi
+        for (a, b), (c, d) in zip(sl, sl[1:]):
+            assert b == c and b % 480 == 0
+    # balance: li(x) estimate vs the true pi(x) at 5e8 primes (p_{5e8} = 11 037 271 757)
+    two = search.partition_range(hi, 2)
+    assert abs(two[0][1] - 11037271757) / 11037271757 < 0.002
+    # small ranges collapse to one slice
+    assert search.partition_range(1000, 4) == [(0, 1000)] + [(1000, 1000)] * 3
+    # exact balance check on a range the oracle can count
+    sl = search.partition_range(2 * 10 ** 7, 4)
+    counts = [orc.c_count_range(a, b) for a, b in sl]
+    assert max(counts) / min(counts) < 1.02
+
+
+def test_combine_slices_is_an_exclusive_prefix():
+    from pss_b200 import search
+    counts = [5, 0, 7, 3]
+    sums = [[10, 100], [0, 0], [20, 200], [5, 50]]
+    assert search.combine_slices(counts, sums, 0) == (0, [0, 0])
+    assert search.combine_slices(counts, sums, 2) == (5, [10, 100])
+    assert search.combine_slices(counts, sums, 3) == (12, [30, 300])
+
+
+def _po(power, cnt=0, first=0, last=0, cross=0, prime=0, at=0, before=0, final=0):
+    from pss_b200.search import PowerOutcome
+    return PowerOutcome(power, cnt, first, last, cross, prime, at, before, final)
+
+
+def test_merge_and_enumeration_order():
+    from pss_b200.search import SearchOutcome, merge_outcomes
+    a = SearchOutcome(1, 20, "==", 8944, 29, [_po(1, final=129), _po(2, final=3000), _po(3, 1, 7, 7, 7, 17, 8944, 4031, 9000)], {"ms_sieve": 1.0, "primes": 10})
+    b = SearchOutcome(1, 20, "==", 8944, 71, [_po(1, final=639), _po(2, final=30000), _po(3, final=90000)], {"ms_sieve": 2.0, "primes": 10})
+    m = merge_outcomes([a, None, b], 1, 20, "==", 8944)
+    assert m.first() == (7, 3) and m.last_prime == 71 and m.powers[2].final_sum == 90000
+    assert m.stats["ms_sieve"] == 2.0 and m.stats["primes"] == 20
+    assert m.bracket(3) == (6, 7) and m.bracket(1) == (20, 21)
+    # n outer / p inner (utils/grammar.py:939,977): ranges for "<" enumerate (n, p) in that order
+    c = SearchOutcome(1, 5, "<", 40, 11, [_po(1, 5, 1, 5, 0, 0, 0, 0, 28), _po(2, 3, 1, 3, 4, 7, 87, 38, 208)], {})
+    assert list(c.matches()) == [(1, 1), (1, 2), (2, 1), (2, 2), (3, 1), (3, 2), (4, 1), (5, 1)]
+    assert list(c.matches(limit=3)) == [(1, 1), (1, 2), (2, 1)]
+    # "!=" with the single equal index carved out
+    d = SearchOutcome(1, 6, "!=", 10, 13, [_po(1, 5, 1, 6, 3, 5, 10, 5, 41)], {})
+    assert [n for n, _ in d.matches()] == [1, 2, 4, 5, 6]
+
+
+def test_li_estimate():
+    from pss_b200.search import li
+    assert abs(li(1e9) - 50847534) / 50847534 < 2e-4
+    assert abs(li(2.28e10) - 1e9) / 1e9 < 2e-4
+    assert li(2) == 0.0
+
+
+# --------------------------------------------------------------------------- checkpoint format
+def test_sum_cache_checkpoint_matches_reference_format(tmp_path, orc):
+    from pss_b200.sum_cache import IncrementalSumCache
+    c = IncrementalSumCache(powers=[2, 3])
+    for p in orc.first_n_primes(15):
+        c.add_prime(np.int64(p))        # np.int64 input must not wrap
+    assert c.get_sum(2) == 10466        # tests/test_sum_cache.py:235-248
+    c.add_prime(1_000_000_007)
+    assert c.get_sum(3) == orc.power_sum(list(orc.first_n_primes(15)) + [1_000_000_007], 3)
+    with pytest.raises(ValueError, match="Power 5 not tracked"):
+        c.get_sum(5)
+    path = tmp_path / "sub" / "sums.npz"
+    c.save_checkpoint(path)
+    data = np.load(path, allow_pickle=True)
+    assert set(data.files) == {"metadata", "initial_values", "recent_values", "sum_p2", "sum_p3"}
+    import json
+    md = json.loads(str(data["metadata"]))
+    assert md["version"] == "1.0" and md["powers"] == [2, 3] and md["prime_count"] == 16 and md["last_prime"] == 1_000_000_007
+    d = IncrementalSumCache.load_checkpoint(path)
+    assert d.sums == c.sums and d.get_prime_count() == 16 and d.get_last_prime() == 1_000_000_007
+    # adaptive cadence (utils/sum_cache.py:143-167)
+    assert not d.should_checkpoint()
+    with pytest.raises(FileNotFoundError):
+        IncrementalSumCache.load_checkpoint(tmp_path / "missing.npz")
+    if os.path.exists("/root/reference/utils/sum_cache.py"):
+        sys.path.insert(0, "/root/reference")
+        try:
+            from utils.sum_cache import IncrementalSumCache as Ref
+            r = Ref.load_checkpoint(path)       # the reference reads our file
+            assert r.sums == c.sums and r.get_prime_count() == 16
+            r.save_checkpoint(tmp_path / "ref.npz")
+            back = IncrementalSumCache.load_checkpoint(tmp_path / "ref.npz")   # and we read the reference's
+            assert back.sums == c.sums
+        finally:
+            sys.path.remove("/root/reference")
+
+
+# --------------------------------------------------------------------------- N > 1 over gloo
+class OracleHandle:
+    """Stand-in for _lib.Handle implementing the fused slice API with the oracle (host logic tests only)."""
+
+    def __init__(self):
+        from oracle import oracle
+        self.orc = oracle
+        self.primes = None
+        self.cfg = None
+
+    def nth_prime_upper(self, n):
+        if n < 6:
+            return 15
+        b = n * (math.log(n) + math.log(math.log(n)) - (0.9484 if n >= 39017 else 0.0))
+        return int(b) + 3
+
+    def slice_sieve_sums(self, lo, hi, power_max, all_powers=False):
+        self.primes = self.orc.c_primes_range(lo, hi)
+        powers = list(range(1, power_max + 1)) if (all_powers and power_max > 1) else [power_max]
+        self.cfg = powers
+        return len(self.primes), self.orc.c_power_sums(self.primes, powers)
+
+    def slice_scan_bitmap(self, n_first, carry, n_min, n_max, power_max, target, op="==", all_powers=False):
+        from pss_b200 import _lib
+        take = min(len(self.primes), n_max - n_first + 1)
+        res = _lib.SearchResult()
+        res.n_powers = len(self.cfg)
+        res.primes_scanned = take
+        res.last_prime = int(self.primes[take - 1]) if n_first + take - 1 == n_max else 0
+        for j, k in enumerate(self.cfg):
+            r = self.orc.c_scan_compare(self.primes[:take], n_first, k, carry[j], target, op, n_min, n_max)
+            pr = res.powers[j]
+            pr.power = k
+            pr.match_count, pr.first_match_n, pr.last_match_n = r["match_count"], r["first_match_n"], r["last_match_n"]
+            pr.cross_n, pr.cross_prime = r["cross_n"], r["cross_prime"]
+            for name in ("sum_at_cross", "sum_before_cross", "final_sum"):
+                limbs = _lib.int_to_limbs(r[name], _lib.PSS_LIMBS)
+                for i in range(_lib.PSS_LIMBS):
+                    getattr(pr, name)[i] = int(limbs[i])
+        return res
+
+
+def _gloo_worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    sys.path.insert(0, os.path.join(ROOT, "prime-square-sum_b200"))
+    sys.path.insert(0, ROOT)
+    import torch.distributed as dist
+    from pss_b200 import search
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        h = OracleHandle()
+        from oracle import oracle as orc
+        n_max = 60000
+        primes = orc.c_first_n_primes(n_max)
+        out = {}
+        # a hit in rank 1's slice, one in rank 0's, a miss, and an all-powers query
+        for name, (k, multi, hit) in {"hi": (2, False, 45000), "lo": (3, False, 7), "multi": (4, True, 31000)}.items():
+            target = orc.c_prefix_sums(primes[:hit], k)[-1]
+            o = search.distributed_search(target, n_max, power=k, all_powers=multi, handle=h)
+            out[name] = (o.first(), [p.final_sum for p in o.powers], o.last_prime, o.powers[-1].sum_before_cross)
+        T = orc.trisum(666)
+        o = search.distributed_search(T, n_max, power=2, handle=h)
+        out["miss"] = (o.first(), o.bracket(), o.powers[0].final_sum, o.last_prime)
+        o = search.distributed_search(10 ** 12, n_max, power=2, n_min=50, op="<", handle=h)
+        out["lt"] = (o.powers[0].match_count, o.powers[0].first_match_n, o.powers[0].last_match_n)
+        q.put((rank, out))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_distributed_search_world_size_2_gloo(orc):
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + os.getpid() % 2000
+    procs = [ctx.Process(target=_gloo_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    results = dict(q.get(timeout=300) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    n_max = 60000
+    primes = orc.c_first_n_primes(n_max)
+    S = {k: orc.c_prefix_sums(primes, k) for k in (1, 2, 3, 4)}
+    for rank in (0, 1):
+        out = results[rank]                      # every rank returns the merged outcome
+        assert out["hi"] == ((45000, 2), [S[2][-1]], int(primes[-1]), S[2][44998])
+        assert out["lo"] == ((7, 3), [S[3][-1]], int(primes[-1]), S[3][5])
+        assert out["multi"][0] == (31000, 4) and out["multi"][1] == [S[k][-1] for k in (1, 2, 3, 4)]
+        assert out["miss"] == (None, (n_max, n_max + 1), S[2][-1], int(primes[-1]))
+        below = sum(1 for n in range(50, n_max + 1) if S[2][n - 1] < 10 ** 12)
+        assert out["lt"] == (below, 50, 49 + below)
