@@ -66,52 +66,66 @@ def load_peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    """SM clock and throttle reasons DURING the timed region.  The timed region of this workload is tens of
+    milliseconds, far shorter than `nvidia-smi -lms` can resolve, so NVML is polled from a thread every ~2 ms
+    (the main thread sits in ctypes calls with the GIL released); nvidia-smi is the fallback."""
+
+    REASONS = {0x4: "sw_power_cap", 0x8: "hw_slowdown", 0x20: "sw_thermal_slowdown", 0x40: "hw_thermal_slowdown",
+               0x80: "hw_power_brake_slowdown"}
 
     def __init__(self, gpu_index=0):
-        self.proc = None
         self.gpu_index = gpu_index
-        self.path = os.path.join(ROOT, "gpurun_out", f"clocks_bench_{os.getpid()}.csv")
+        self.samples, self.reason_bits, self.max_mhz = [], 0, None
+        self._stop = threading.Event()
+        self._thread = None
+        self._nvml = None
+
+    def _run(self):
+        nv, hdl = self._nvml
+        while not self._stop.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(hdl, nv.NVML_CLOCK_SM))
+                try:
+                    self.reason_bits |= nv.nvmlDeviceGetCurrentClocksEventReasons(hdl)
+                except Exception:
+                    self.reason_bits |= nv.nvmlDeviceGetCurrentClocksThrottleReasons(hdl)
+            except Exception:
+                break
+            time.sleep(0.002)
 
     def start(self):
         try:
-            os.makedirs(os.path.dirname(self.path), exist_ok=True)
-            self.f = open(self.path, "w")
-            self.proc = subprocess.Popen(
-                ["nvidia-smi", "-i", str(self.gpu_index),
-                 "--query-gpu=clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
-                 "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-                 "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap",
-                 "--format=csv,noheader,nounits", "-lms", "100"], stdout=self.f, stderr=subprocess.DEVNULL)
+            import pynvml as nv
+            nv.nvmlInit()
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            idx = int(vis.split(",")[self.gpu_index]) if vis and vis.split(",")[self.gpu_index].isdigit() else self.gpu_index
+            hdl = nv.nvmlDeviceGetHandleByIndex(idx)
+            self.max_mhz = nv.nvmlDeviceGetMaxClockInfo(hdl, nv.NVML_CLOCK_SM)
+            self._nvml = (nv, hdl)
+            self._thread = threading.Thread(target=self._run, daemon=True)
+            self._thread.start()
         except Exception:
-            self.proc = None
+            self._nvml = None
 
     def stop(self):
-        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
-        if self.proc is None:
-            return out
+        out = {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": [], "samples": 0, "source": "nvml"}
+        if self._thread is None:
+            return self._smi_once()
+        self._stop.set()
+        self._thread.join(timeout=2)
+        if self.samples:
+            sm = sorted(self.samples)
+            out.update(sm_mhz=float(sm[len(sm) // 2]), sm_mhz_min=float(sm[0]), sm_mhz_max_seen=float(sm[-1]), samples=len(sm),
+                       reasons=sorted(name for bit, name in self.REASONS.items() if self.reason_bits & bit))
+        return out
+
+    def _smi_once(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0, "source": "nvidia-smi (single sample after the timed region)"}
         try:
-            self.proc.terminate()
-            self.proc.wait(timeout=5)
-            self.f.close()
-            sm, reasons, mx = [], set(), None
-            for line in open(self.path):
-                parts = [x.strip() for x in line.split(",")]
-                if len(parts) < 8:
-                    continue
-                try:
-                    sm.append(float(parts[0]))
-                    mx = float(parts[1])
-                except ValueError:
-                    continue
-                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), parts[4:8]):
-                    if v.lower().startswith("active"):
-                        reasons.add(name)
-            if sm:
-                sm.sort()
-                # median of the upper half = clocks under load (idle samples between steps pull the plain median down)
-                out = {"sm_mhz": sm[len(sm) // 2], "sm_mhz_max_seen": sm[-1], "sm_max_mhz": mx, "reasons": sorted(reasons),
-                       "samples": len(sm)}
+            txt = subprocess.run(["nvidia-smi", "-i", str(self.gpu_index), "--query-gpu=clocks.sm,clocks.max.sm",
+                                  "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=10).stdout
+            a, b = [float(x) for x in txt.strip().split(",")[:2]]
+            out.update(sm_mhz=a, sm_max_mhz=b, samples=1)
         except Exception:
             pass
         return out
@@ -223,6 +237,8 @@ def main():
     torch.cuda.set_device(local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"      # keep NCCL's version banner off stdout: one JSON line only
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     os.environ["PSS_DEVICE"] = str(local_rank)
     h = _lib.default_handle()
