@@ -59,10 +59,10 @@ struct pss_handle {
     char name[256] = {0};
 
     // tuning
-    u32 tile_bytes = 96 * 1024;
+    u32 tile_bytes = 112 * 1024;   // 2 CTAs x 512 threads per SM (tools/tune_sieve.py, profiles/r01/tune_sieve_*.json)
     u32 sieve_threads = 512;
     u32 n_pat = 4;
-    u32 warp_wide_div = 32;    // p < tile_bytes / div -> one warp per prime, else 8 lanes per prime
+    u32 warp_wide_div = 512;    // p < tile_bytes / div -> one warp per prime, else 8 lanes per prime
     int search_path = 0;       // 0: fused (scan straight from the bitmap), 1: materialised u64 primes
 
     // patterns
@@ -88,7 +88,7 @@ struct pss_handle {
     u64 resident_last = 0;
 
     // fused path: column-major tile records of the last bitmap reduce and their prefixes
-    DevBuf cols, col_prefix, thread_rec;
+    DevBuf cols, col_prefix, thread_rec, warp_rec;
     bool bs_valid = false;
     u32 bs_K = 0, bs_n_tiles = 0, bs_total_cols = 0;
     bool bs_multi = false;
@@ -600,6 +600,8 @@ void fill_bscan_common(pss_handle* h, BScanParams& bp) {
     bp.col_stride = (u64)bp.n_tiles + 1;
     bp.thread_stride = (u64)bp.n_tiles * kBsThreads;
     bp.thread_rec = static_cast<u32*>(h->thread_rec.p);
+    bp.warp_stride = (u64)bp.n_tiles * (kBsThreads / 32);
+    bp.warp_rec = static_cast<u32*>(h->warp_rec.p);
 }
 
 // phase A of the fused path: per-tile (count, sums) records, column prefixes, slice totals
@@ -621,11 +623,14 @@ int bitmap_reduce(pss_handle* h, u32 K, bool multi) {
     fill_bscan_common(h, bp);
     PSS_TRY(ensure(h, h->thread_rec, (size_t)ncols * bp.thread_stride * sizeof(u32)));
     bp.thread_rec = static_cast<u32*>(h->thread_rec.p);
-    PSS_TRY(ensure(h, h->cols, (size_t)ncols * bp.col_stride * sizeof(u32)));
+    PSS_TRY(ensure(h, h->warp_rec, (size_t)ncols * bp.warp_stride * sizeof(u32)));
+    bp.warp_rec = static_cast<u32*>(h->warp_rec.p);
+    PSS_TRY(ensure(h, h->cols, (size_t)ncols * bp.col_stride * sizeof(u64)));
     PSS_TRY(ensure(h, h->col_prefix, (size_t)ncols * bp.col_stride * sizeof(u64)));
-    bp.cols = static_cast<u32*>(h->cols.p);
+    bp.cols = static_cast<u64*>(h->cols.p);
     bp.col_prefix = static_cast<const u64*>(h->col_prefix.p);
     CU_TRY(h, cudaEventRecord(h->ev[4], h->stream));
+    CU_TRY(h, cudaMemsetAsync(bp.cols, 0, (size_t)ncols * bp.col_stride * sizeof(u64), h->stream));
     PSS_TRY(launch_bscan<kBsReduce>(h, bp, K, multi));
     k_scan_columns<<<ncols, 1024, 0, h->stream>>>(bp.cols, static_cast<u64*>(h->col_prefix.p), bp.n_tiles, bp.col_stride);
     CU_TRY(h, cudaGetLastError());
@@ -693,7 +698,7 @@ int bitmap_compare(pss_handle* h, u64 n_first, const u32* carry_in, const pss_se
     if (scanned > 0) {
         BScanParams bp;
         fill_bscan_common(h, bp);
-        bp.cols = static_cast<u32*>(h->cols.p);
+        bp.cols = static_cast<u64*>(h->cols.p);
         bp.col_prefix = static_cast<const u64*>(h->col_prefix.p);
         bp.n_first = n_first;
         bp.n_min = a->n_min;
@@ -819,7 +824,7 @@ int pss_close(pss_handle* h) {
     if (!h) return PSS_OK;
     cudaSetDevice(h->device);
     if (h->stream) cudaStreamSynchronize(h->stream);
-    for (DevBuf* b : {&h->d_base, &h->d_base_inv, &h->d_base_strand, &h->cols, &h->col_prefix, &h->thread_rec, &h->tile_nact, &h->bitmap, &h->chunk_counts, &h->tile_counts, &h->tile_prefix, &h->primes, &h->status, &h->agg,
+    for (DevBuf* b : {&h->d_base, &h->d_base_inv, &h->d_base_strand, &h->cols, &h->col_prefix, &h->thread_rec, &h->warp_rec, &h->tile_nact, &h->bitmap, &h->chunk_counts, &h->tile_counts, &h->tile_prefix, &h->primes, &h->status, &h->agg,
                       &h->incl, &h->misc, &h->prefix_out, &h->user_vals})
         if (b->p) cudaFree(b->p);
     for (auto& p : h->d_pat)

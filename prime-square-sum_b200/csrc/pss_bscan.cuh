@@ -4,12 +4,13 @@
 // query path never materialises u64 primes: each thread owns kWordsPerThread consecutive bitmap words
 // (blocked order, staged through padded shared memory from coalesced uint4 loads), decodes its primes with
 // ffs, raises them to the k-th power with the same IMAD carry chains as pss_scan.cuh and
-//   kBsReduce   block-reduces (count, S_k limbs) per tile  -> column-major u32 tile records
+//   kBsReduce   per-thread and per-warp (count, S_k limbs) records + per-tile deferred-carry columns (u64 atomics)
 //   k_scan_columns  exclusive u64 prefix of every column (count, each 32-bit limb as a deferred-carry
 //                   64-bit lane) across tiles — the grid level of the warp -> block -> grid scan
 //   kBsCompare  re-walks the tile from its exact prefix (carry-in + normalised column prefixes + block
 //               scan), forms EVERY partial sum S_k(n) and compares it with the target limbs.
-// No CTA ever waits for another CTA (three launches instead of a look-back chain), so the multi-GPU
+// Both passes are warp-autonomous (warp-local staging, no __syncthreads) and no CTA ever waits for another
+// CTA (three launches instead of a look-back chain), so the multi-GPU
 // "phase A" (slice count + slice sums) is simply the column totals of the first two launches.
 //
 // Replaces the same reference code as pss_scan.cuh (utils/sequences.py:75, utils/gpu.py:169-247,
@@ -33,9 +34,11 @@ struct BScanParams {
     u32 n_small;             // 2, 3, 5 inside [lo, hi): handled by thread 0 of tile 0 (not representable)
     u64 small_primes[3];
     // tile records, column major: col c of tile t at cols[c * col_stride + t]; col 0 = count, 1.. = limbs
-    u32* cols;
+    u64* cols;               // deferred-carry 64-bit lanes, accumulated with atomics (zeroed before the reduce pass)
     const u64* col_prefix;   // exclusive prefixes, same layout, (n_tiles + 1) entries per column
     u64 col_stride;
+    u32* warp_rec;           // exact per-warp (count, limbs), col c of global warp g at warp_rec[c * warp_stride + g]
+    u64 warp_stride;
     // per-thread records of the reduce pass (count, sums), column major over global thread ids, so that
     // the compare pass needs no second power pass to rebuild its block scan
     u32* thread_rec;         // col c of global thread g at thread_rec[c * thread_stride + g]
@@ -67,33 +70,39 @@ __device__ __forceinline__ u32 msb_value_offset(u32 m) {
 
 // Decode loop: one prime per iteration for every lane that still has one (lanes own equal word counts, so
 // the trip counts differ only by the local density fluctuation).  The refill of an exhausted word is
-// branch-free (unconditional shared-memory load + selects) so the warp never splits around the power chain.
+// branch-free (unconditional shared-memory load + selects) and the body is a plain if-region, so the warp
+// reconverges every iteration and never splits around the power chain.
+// f(plo, phi) -> false stops this lane (past n_max).
 template <class F>
-__device__ __forceinline__ void walk_words(const u32* my_words, u64 value_base, F& f) {
+__device__ __forceinline__ void walk_words(const u32* my_words, u32 base_lo, u32 base_hi, F& f) {
     u32 wi = 0, w = 0, woff = 0;
-    for (;;) {
+    bool alive = true;
+    while (alive) {
         const bool need = (w == 0);
         const u32 idx = min(wi, (u32)(kWordsPerThread - 1));
         const u32 nw = my_words[idx];
         w = need ? ((wi < (u32)kWordsPerThread) ? nw : 0u) : w;
         woff = need ? idx * 120u : woff;
         wi += need ? 1u : 0u;
-        if (w == 0) {                       // empty word (rare) or end of this thread's range
-            if (wi > (u32)kWordsPerThread) return;
-            continue;
+        if (w != 0) {
+            const u32 m = 31u - (u32)__clz(w);
+            w ^= (1u << m);
+            const u32 off = woff + msb_value_offset(m);
+            const u32 plo = base_lo + off;
+            const u32 phi = base_hi + (plo < off ? 1u : 0u);
+            alive = f(plo, phi);
+        } else {
+            alive = (wi <= (u32)kWordsPerThread);   // empty word (rare): try the next one; else done
         }
-        const u32 m = 31u - (u32)__clz(w);
-        w ^= (1u << m);
-        if (!f(value_base + (woff + msb_value_offset(m)))) return;
     }
 }
 
 template <int K, bool MULTI>
 struct BsAccFn {
     u32* acc;
-    __device__ __forceinline__ bool operator()(u64 p) {
+    __device__ __forceinline__ bool operator()(u32 plo, u32 phi) {
         AccFn<K, MULTI> fn{acc};
-        power_chain<K, MULTI>(p, fn);
+        power_chain2<K, MULTI>(plo, phi, fn);
         return true;
     }
 };
@@ -106,14 +115,14 @@ struct BsCmpFn {
     u64 tile_n0;     // global index of the tile's first prime
     u32 li;          // tile-local index of the next prime
     u32 lmin, lmax;  // window [n_min, n_max] in tile-local indices (saturated)
-    __device__ __forceinline__ bool operator()(u64 p) {
+    __device__ __forceinline__ bool operator()(u32 plo, u32 phi) {
         if (li > lmax) return false;
-        inner.p = p;
+        inner.p = ((u64)phi << 32) | plo;
         inner.local_idx = li;
         inner.in_window = (li >= lmin);
-        power_chain<K, MULTI>(p, inner);
+        power_chain2<K, MULTI>(plo, phi, inner);
         if (li == lmax && tile_n0 + li == P->n_max) {   // exactly one thread in the grid: S(n_max), p_{n_max}
-            *P->last_prime_out = p;
+            *P->last_prime_out = inner.p;
 #pragma unroll
             for (int jj = 0; jj < Lay::NP; ++jj)
 #pragma unroll
@@ -125,71 +134,67 @@ struct BsCmpFn {
     }
 };
 
+// Warp-autonomous kernel: a warp owns one "warp tile" = 32 threads x 24 words (768 words, 92 160 integers);
+// 8 consecutive warp tiles form a scan tile (the granularity of the column prefix).  No __syncthreads.
 template <int K, bool MULTI, int MODE>
 __global__ void __launch_bounds__(kBsThreads) k_bitmap_scan(const __grid_constant__ BScanParams P) {
     using Lay = Layout<K, MULTI>;
     constexpr int TOTAL = Lay::TOTAL, NP = Lay::NP, T = kBsThreads, NWARP = T / 32;
-    constexpr int WPT = kWordsPerThread, PAD = WPT + 1;
+    constexpr int WPT = kWordsPerThread, PAD = WPT + 1, WARP_WORDS = 32 * WPT;
 
     __shared__ u32 s_words[T * PAD];
-    __shared__ u32 s_warp[NWARP][TOTAL + 1];   // [..][TOTAL] = count
-    __shared__ u32 s_excl[TOTAL];
-    __shared__ u64 s_tile_n0;
 
     const u32 tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+    u32* my_warp_words = s_words + warp * 32 * PAD;
+    const u32* my_words = my_warp_words + lane * PAD;
+    const u64 n_warp_tiles = (u64)P.n_tiles * NWARP;
+    const u64 warp_stride = (u64)gridDim.x * NWARP;
 
-    for (u32 tile = blockIdx.x; tile < P.n_tiles; tile += gridDim.x) {
+    for (u64 wt = (u64)blockIdx.x * NWARP + warp; wt < n_warp_tiles; wt += warp_stride) {
+        const u32 tile = (u32)(wt / NWARP);
+        const u32 wit = (u32)(wt % NWARP);          // warp index inside the scan tile
         if constexpr (MODE == kBsCompare) {
-            // tiles that start beyond n_max have nothing to compare
             if (P.n_first + P.col_prefix[tile] > P.n_max) break;   // prefixes are monotone in tile
         }
-        const u64 word0 = (u64)tile * kBsTileWords;
-        // ---- coalesced uint4 loads -> padded blocked layout (word w of thread t at t*PAD + w)
+        const u64 word0 = wt * WARP_WORDS;
+        // ---- warp-local staging: coalesced uint4 loads -> padded blocked layout, bit-reversed
         const uint4* g4 = reinterpret_cast<const uint4*>(P.bitmap + word0);
+        __syncwarp();
 #pragma unroll
         for (int r = 0; r < WPT / 4; ++r) {
-            const u32 q = r * T + tid;            // uint4 index inside the tile
-            const u64 wq = word0 + 4ull * q;
+            const u32 q = r * 32 + lane;          // uint4 index inside the warp tile
             uint4 v = make_uint4(0, 0, 0, 0);
-            if (wq + 4 <= P.n_words) v = __ldg(g4 + q);
-            const u32 wl = 4u * q;                // first word (tile local); 4 | WPT so one owner thread
+            if (word0 + 4ull * q + 4 <= P.n_words) v = __ldg(g4 + q);
+            const u32 wl = 4u * q;                // first word (warp-tile local); 4 | WPT so one owner thread
             const u32 dst = (wl / WPT) * PAD + (wl % WPT);
-            s_words[dst] = __brev(v.x); s_words[dst + 1] = __brev(v.y);
-            s_words[dst + 2] = __brev(v.z); s_words[dst + 3] = __brev(v.w);
+            my_warp_words[dst] = __brev(v.x); my_warp_words[dst + 1] = __brev(v.y);
+            my_warp_words[dst + 2] = __brev(v.z); my_warp_words[dst + 3] = __brev(v.w);
         }
-        __syncthreads();
+        __syncwarp();
 
-        const u32* my_words = s_words + tid * PAD;
-        const u64 value_base = (P.B_start + 4ull * (word0 + (u64)tid * WPT)) * 30ull;
-        const bool has_small = (tile == 0 && tid == 0 && P.n_small > 0);
+        const u64 value_base = (P.B_start + 4ull * (word0 + (u64)lane * WPT)) * 30ull;
+        const u32 base_lo = (u32)value_base, base_hi = (u32)(value_base >> 32);
+        const bool has_small = (wt == 0 && lane == 0 && P.n_small > 0);
+        const u64 gthread = wt * 32 + lane;
 
-        // ---- pass 1: thread-local count and sums (reduce pass: decode + powers; compare pass: reload the
-        //      reduce pass's per-thread record)
         u32 acc[TOTAL];
         u32 cnt = 0;
-        const u64 gthread = (u64)tile * T + tid;
         if constexpr (MODE == kBsReduce) {
+            // ---- thread-local count and sums
 #pragma unroll
             for (int i = 0; i < TOTAL; ++i) acc[i] = 0;
 #pragma unroll
             for (int i = 0; i < WPT; ++i) cnt += __popc(my_words[i]);
             BsAccFn<K, MULTI> fn{acc};
             if (has_small) {
-                for (u32 i = 0; i < P.n_small; ++i) fn(P.small_primes[i]);
+                for (u32 i = 0; i < P.n_small; ++i) fn((u32)P.small_primes[i], 0u);
                 cnt += P.n_small;
             }
-            walk_words(my_words, value_base, fn);
+            walk_words(my_words, base_lo, base_hi, fn);
             P.thread_rec[gthread] = cnt;
 #pragma unroll
             for (int i = 0; i < TOTAL; ++i) P.thread_rec[(u64)(1 + i) * P.thread_stride + gthread] = acc[i];
-        } else {
-            cnt = __ldg(P.thread_rec + gthread);
-#pragma unroll
-            for (int i = 0; i < TOTAL; ++i) acc[i] = __ldg(P.thread_rec + (u64)(1 + i) * P.thread_stride + gthread);
-        }
-
-        if constexpr (MODE == kBsReduce) {
-            // ---- block reduce -> one column-major record per tile
+            // ---- warp totals (exact limbs) -> warp record; deferred-carry u64 atomics -> tile record
 #pragma unroll
             for (int d = 16; d >= 1; d >>= 1) {
                 OpShflXorAdd op{acc, d};
@@ -197,31 +202,20 @@ __global__ void __launch_bounds__(kBsThreads) k_bitmap_scan(const __grid_constan
             }
             cnt = __reduce_add_sync(0xFFFFFFFFu, cnt);
             if (lane == 0) {
+                P.warp_rec[wt] = cnt;
+                atomicAdd(reinterpret_cast<unsigned long long*>(P.cols + tile), (unsigned long long)cnt);
 #pragma unroll
-                for (int i = 0; i < TOTAL; ++i) s_warp[warp][i] = acc[i];
-                s_warp[warp][TOTAL] = cnt;
-            }
-            __syncthreads();
-            if (warp == 0) {
-                u32 v[TOTAL];
-#pragma unroll
-                for (int i = 0; i < TOTAL; ++i) v[i] = (lane < NWARP) ? s_warp[lane][i] : 0u;
-                u32 c = (lane < NWARP) ? s_warp[lane][TOTAL] : 0u;
-#pragma unroll
-                for (int d = 16; d >= 1; d >>= 1) {
-                    OpShflXorAdd op{v, d};
-                    for_each_power<0, Lay>(op);
-                }
-                c = __reduce_add_sync(0xFFFFFFFFu, c);
-                if (lane == 0) {
-                    P.cols[tile] = c;
-#pragma unroll
-                    for (int i = 0; i < TOTAL; ++i) P.cols[(u64)(1 + i) * P.col_stride + tile] = v[i];
+                for (int i = 0; i < TOTAL; ++i) {
+                    P.warp_rec[(u64)(1 + i) * P.warp_stride + wt] = acc[i];
+                    atomicAdd(reinterpret_cast<unsigned long long*>(P.cols + (u64)(1 + i) * P.col_stride + tile),
+                              (unsigned long long)acc[i]);
                 }
             }
-            __syncthreads();
         } else {
-            // ---- warp inclusive scan of (count, sums); exclusive values for this lane
+            // ---- exclusive prefix of this thread = carry-in + tile prefix + earlier warps + earlier lanes
+            cnt = __ldg(P.thread_rec + gthread);
+#pragma unroll
+            for (int i = 0; i < TOTAL; ++i) acc[i] = __ldg(P.thread_rec + (u64)(1 + i) * P.thread_stride + gthread);
             u32 cinc = cnt;
 #pragma unroll
             for (int d = 1; d < 32; d <<= 1) {
@@ -230,70 +224,58 @@ __global__ void __launch_bounds__(kBsThreads) k_bitmap_scan(const __grid_constan
                 const u32 o = __shfl_up_sync(0xFFFFFFFFu, cinc, d);
                 if (lane >= (u32)d) cinc += o;
             }
-            if (lane == 31) {
-#pragma unroll
-                for (int i = 0; i < TOTAL; ++i) s_warp[warp][i] = acc[i];
-                s_warp[warp][TOTAL] = cinc;
-            }
             u32 run[TOTAL];
 #pragma unroll
             for (int i = 0; i < TOTAL; ++i) {
                 const u32 up = __shfl_up_sync(0xFFFFFFFFu, acc[i], 1);
                 run[i] = lane ? up : 0u;
             }
-            u32 cexc = cinc - cnt;
-            __syncthreads();
-            if (warp == 0) {
-                // exclusive scan of the warp totals
-                u32 wi_[TOTAL];
+            u32 li0 = cinc - cnt;
+            // earlier warps of this scan tile: lane l < wit fetches warp record l, butterfly sum
+            {
+                u32 v[TOTAL];
+                u32 c = 0;
+                const u64 wrec = (u64)tile * NWARP + lane;
 #pragma unroll
-                for (int i = 0; i < TOTAL; ++i) wi_[i] = (lane < NWARP) ? s_warp[lane][i] : 0u;
-                u32 wc = (lane < NWARP) ? s_warp[lane][TOTAL] : 0u;
-                const u32 wc0 = wc;
+                for (int i = 0; i < TOTAL; ++i) v[i] = (lane < wit) ? __ldg(P.warp_rec + (u64)(1 + i) * P.warp_stride + wrec) : 0u;
+                if (lane < wit) c = __ldg(P.warp_rec + wrec);
 #pragma unroll
-                for (int d = 1; d < NWARP; d <<= 1) {
-                    OpShflUpAdd op{wi_, d, lane >= (u32)d};
+                for (int d = 4; d >= 1; d >>= 1) {   // records live in lanes 0..7
+                    OpShflXorAdd op{v, d};
                     for_each_power<0, Lay>(op);
-                    const u32 o = __shfl_up_sync(0xFFFFFFFFu, wc, d);
-                    if (lane >= (u32)d) wc += o;
                 }
+                c += __shfl_xor_sync(0xFFFFFFFFu, c, 4);
+                c += __shfl_xor_sync(0xFFFFFFFFu, c, 2);
+                c += __shfl_xor_sync(0xFFFFFFFFu, c, 1);
 #pragma unroll
-                for (int i = 0; i < TOTAL; ++i) {
-                    const u32 up = __shfl_up_sync(0xFFFFFFFFu, wi_[i], 1);
-                    if (lane < NWARP) s_warp[lane][i] = lane ? up : 0u;
-                }
-                if (lane < NWARP) s_warp[lane][TOTAL] = wc - wc0;
-                // tile prefix = carry-in + normalised deferred-carry column prefixes
-                if (lane == 0) {
-                    u32 ex[TOTAL];
+                for (int i = 0; i < TOTAL; ++i) v[i] = __shfl_sync(0xFFFFFFFFu, v[i], 0);
+                c = __shfl_sync(0xFFFFFFFFu, c, 0);
+                OpAdd op{run, v};
+                for_each_power<0, Lay>(op);
+                li0 += c;
+            }
+            // tile prefix = carry-in + normalised deferred-carry column prefixes (uniform across the warp)
+            {
+                u32 ex[TOTAL];
 #pragma unroll
-                    for (int jj = 0; jj < NP; ++jj) {
-                        u64 c = 0;
+                for (int jj = 0; jj < NP; ++jj) {
+                    u64 c = 0;
 #pragma unroll
-                        for (int i = 0; i < PSS_LIMBS; ++i) {
-                            if (i < Lay::width(jj)) {
-                                const int col = 1 + Lay::offset(jj) + i;
-                                const u64 v = P.col_prefix[(u64)col * P.col_stride + tile];
-                                // v < 2^63, carry < 2^32: split the add to stay inside 64 bits
-                                const u64 lo = (v & 0xFFFFFFFFull) + (c & 0xFFFFFFFFull) + P.carry_in[jj * PSS_LIMBS + i];
-                                ex[Lay::offset(jj) + i] = (u32)lo;
-                                c = (v >> 32) + (c >> 32) + (lo >> 32);
-                            }
+                    for (int i = 0; i < PSS_LIMBS; ++i) {
+                        if (i < Lay::width(jj)) {
+                            const int col = 1 + Lay::offset(jj) + i;
+                            const u64 v = P.col_prefix[(u64)col * P.col_stride + tile];
+                            const u64 lo = (v & 0xFFFFFFFFull) + (c & 0xFFFFFFFFull) + P.carry_in[jj * PSS_LIMBS + i];
+                            ex[Lay::offset(jj) + i] = (u32)lo;
+                            c = (v >> 32) + (c >> 32) + (lo >> 32);
                         }
                     }
-#pragma unroll
-                    for (int i = 0; i < TOTAL; ++i) s_excl[i] = ex[i];
-                    s_tile_n0 = P.n_first + P.col_prefix[tile];
                 }
+                OpAdd op{run, ex};
+                for_each_power<0, Lay>(op);
             }
-            __syncthreads();
-            // ---- pass 2: exact exclusive prefix of this thread, every S_k(n) formed and compared
-            {
-                OpAdd op1{run, s_excl};
-                for_each_power<0, Lay>(op1);
-                OpAdd op2{run, s_warp[warp]};
-                for_each_power<0, Lay>(op2);
-            }
+            const u64 tile_n0 = P.n_first + P.col_prefix[tile];
+            // ---- every S_k(n) formed and compared
             int prevc[NP];
             u32 mcount[NP], mfirst[NP], mlast[NP];
 #pragma unroll
@@ -307,16 +289,15 @@ __global__ void __launch_bounds__(kBsThreads) k_bitmap_scan(const __grid_constan
                 OpCmpInit op{run, P.target, P.target_over_mask, prevc};
                 for_each_power<0, Lay>(op);
             }
-            const u64 tile_n0 = s_tile_n0;
             // window in tile-local indices: a tile holds < 2^20 primes, so saturating to u32 is exact
             const u32 lmin = (P.n_min > tile_n0) ? (u32)min(P.n_min - tile_n0, (u64)0xFFFFFFFFull) : 0u;
             const u32 lmax = (u32)min(P.n_max - tile_n0, (u64)0xFFFFFFFEull);   // n_max >= tile_n0 (checked above)
-            BsCmpFn<K, MULTI> fn{{run, &P, prevc, mcount, mfirst, mlast, tile_n0, 0, 0, 0, false}, &P, tile_n0,
-                                 s_warp[warp][TOTAL] + cexc, lmin, lmax};
+            BsCmpFn<K, MULTI> fn{{run, &P, prevc, mcount, mfirst, mlast, tile_n0, 0, 0, 0, false}, &P, tile_n0, li0, lmin, lmax};
             bool go = true;
             if (has_small)
-                for (u32 i = 0; i < P.n_small && go; ++i) go = fn(P.small_primes[i]);
-            if (go) walk_words(my_words, value_base, fn);
+                for (u32 i = 0; i < P.n_small && go; ++i) go = fn((u32)P.small_primes[i], 0u);
+            if (go) walk_words(my_words, base_lo, base_hi, fn);
+            __syncwarp();
 #pragma unroll
             for (int jj = 0; jj < NP; ++jj) {
                 if (__any_sync(0xFFFFFFFFu, mcount[jj] != 0)) {
@@ -331,18 +312,17 @@ __global__ void __launch_bounds__(kBsThreads) k_bitmap_scan(const __grid_constan
                     }
                 }
             }
-            __syncthreads();
         }
     }
 }
 
-// ---- grid level of the scan: exclusive u64 prefix of every u32 column, one CTA per column --------------
+// ---- grid level of the scan: exclusive u64 prefix of every (deferred-carry) column, one CTA per column --------------
 // out[c * stride + t] = sum_{i<t} in[c * stride + i]  for t = 0..n  (entry n = column total)
-__global__ void __launch_bounds__(1024) k_scan_columns(const u32* in, u64* out, u32 n, u64 stride) {
+__global__ void __launch_bounds__(1024) k_scan_columns(const u64* in, u64* out, u32 n, u64 stride) {
     __shared__ u64 s_warp[32];
     __shared__ u64 s_running;
     const u32 tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
-    const u32* col = in + (u64)blockIdx.x * stride;
+    const u64* col = in + (u64)blockIdx.x * stride;
     u64* o = out + (u64)blockIdx.x * stride;
     if (tid == 0) s_running = 0;
     __syncthreads();

@@ -178,6 +178,19 @@ __device__ __forceinline__ void power_chain(u64 p, F& f) {
     }
 }
 
+// same chain from a pre-split prime (plo, phi)
+template <int K, bool MULTI, class F>
+__device__ __forceinline__ void power_chain2(u32 plo, u32 phi, F& f) {
+    if constexpr (K == 2 && !MULTI) {
+        f.apply_square(plo, phi);
+    } else {
+        Big<2> p1;
+        p1.v[0] = plo;
+        p1.v[1] = phi;
+        ChainStep<1, K, MULTI, F>::run(p1, plo, phi, f);
+    }
+}
+
 template <int K, bool MULTI>
 struct AccFn {
     using Lay = Layout<K, MULTI>;
