@@ -134,6 +134,13 @@ int pss_primesum(pss_handle* h, uint64_t n, uint32_t power, uint32_t* limbs_out 
 /* ---- K1+K2+K3 fused search (single GPU) ---------------------------------------------------- */
 int pss_search(pss_handle* h, const pss_search_args* args, pss_search_result* res);
 
+/* `for_any primesum(n,power) == tri(m)` (config: n <= 1e8, m <= 1e7): every partial sum S(n), n in
+ * [n_min,n_max], is tested for triangularity on the device (8S+1 perfect square, utils/number_theory.py:292-354)
+ * with m restricted to [m_min,m_max].  pairs_out receives up to cap (n, m) pairs (unordered); *count is the
+ * total number found.  Replaces the m x n double loop of utils/grammar.py:937-999 for this RHS. */
+int pss_search_tri(pss_handle* h, uint64_t n_min, uint64_t n_max, uint32_t power, uint64_t m_min, uint64_t m_max,
+                   uint64_t* pairs_out, uint32_t cap, uint32_t* count, pss_stats* stats);
+
 /* search path selection: 0 (default) = fused, K2/K3 read the sieve's bit-packed output directly;
  * 1 = materialised, K1c compacts u64 primes first (the layout generate_primes / slice_* serve). */
 int pss_set_search_path(pss_handle* h, int materialised);

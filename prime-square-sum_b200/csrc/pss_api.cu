@@ -96,7 +96,7 @@ struct pss_handle {
     u32 bs_sums[PSS_MAX_POWER * PSS_LIMBS] = {0};   // slice sums per power record (normalised limbs)
 
     // scan workspace
-    DevBuf status, agg, incl, misc, prefix_out, user_vals;
+    DevBuf status, agg, incl, misc, prefix_out, user_vals, tri_buf;
     MiscDev* h_misc = nullptr;   // pinned
 
     cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
@@ -582,6 +582,20 @@ int launch_bscan(pss_handle* h, const BScanParams& bp, u32 K, bool multi) {
     return fail(h, PSS_EINVAL, "unsupported power configuration k=%u all_powers=%d", K, (int)multi);
 }
 
+int launch_bscan_tri(pss_handle* h, const BScanParams& bp, u32 K) {
+    switch (K) {
+        case 1: return launch_bscan_t<1, false, kBsTri>(h, bp);
+        case 2: return launch_bscan_t<2, false, kBsTri>(h, bp);
+        case 3: return launch_bscan_t<3, false, kBsTri>(h, bp);
+        case 4: return launch_bscan_t<4, false, kBsTri>(h, bp);
+        case 5: return launch_bscan_t<5, false, kBsTri>(h, bp);
+        case 6: return launch_bscan_t<6, false, kBsTri>(h, bp);
+        case 7: return launch_bscan_t<7, false, kBsTri>(h, bp);
+        case 8: return launch_bscan_t<8, false, kBsTri>(h, bp);
+    }
+    return fail(h, PSS_EINVAL, "unsupported power %u", K);
+}
+
 u32 total_limbs_of(u32 K, bool multi) {
     u32 t = 0;
     for (u32 j = 0; j < n_powers_of(K, multi); ++j) t += (u32)sum_limbs((int)expo_of(K, multi, j));
@@ -824,7 +838,7 @@ int pss_close(pss_handle* h) {
     if (!h) return PSS_OK;
     cudaSetDevice(h->device);
     if (h->stream) cudaStreamSynchronize(h->stream);
-    for (DevBuf* b : {&h->d_base, &h->d_base_inv, &h->d_base_strand, &h->cols, &h->col_prefix, &h->thread_rec, &h->warp_rec, &h->tile_nact, &h->bitmap, &h->chunk_counts, &h->tile_counts, &h->tile_prefix, &h->primes, &h->status, &h->agg,
+    for (DevBuf* b : {&h->d_base, &h->d_base_inv, &h->d_base_strand, &h->cols, &h->col_prefix, &h->thread_rec, &h->warp_rec, &h->tile_nact, &h->tri_buf, &h->bitmap, &h->chunk_counts, &h->tile_counts, &h->tile_prefix, &h->primes, &h->status, &h->agg,
                       &h->incl, &h->misc, &h->prefix_out, &h->user_vals})
         if (b->p) cudaFree(b->p);
     for (auto& p : h->d_pat)
@@ -1021,6 +1035,60 @@ int pss_search(pss_handle* h, const pss_search_args* a, pss_search_result* res) 
         PSS_TRY(bitmap_compare(h, 1, nullptr, a, res));
     }
     fill_stats(h, &res->stats, before);
+    return PSS_OK;
+}
+
+int pss_search_tri(pss_handle* h, uint64_t n_min, uint64_t n_max, uint32_t power, uint64_t m_min, uint64_t m_max,
+                   uint64_t* pairs_out, uint32_t cap, uint32_t* count, pss_stats* stats) {
+    PSS_TRY(check_handle(h));
+    if (!count || (cap && !pairs_out)) return fail(h, PSS_EINVAL, "null output");
+    if (n_min < 1 || n_max < n_min) return fail(h, PSS_EINVAL, "need 1 <= n_min <= n_max");
+    if (power < 1 || power > PSS_MAX_POWER) return fail(h, PSS_EINVAL, "power %u out of range 1..%d", power, PSS_MAX_POWER);
+    if (m_max >= (1ull << 29)) return fail(h, PSS_EINVAL, "m_max must be below 2^29 (tri(m) is tested in 64-bit arithmetic)");
+    *count = 0;
+    const pss_stats before = stats_snapshot(h);
+    const u64 bound = pss_nth_prime_upper(n_max) + 1;
+    if (bound > kMaxValue) return fail(h, PSS_EINVAL, "n = %llu needs primes beyond 2^%d", (unsigned long long)n_max, PSS_MAX_PRIME_BITS);
+    PSS_TRY(sieve_range(h, 0, bound));
+    if (h->sv_total < n_max) return fail(h, PSS_EINTERNAL, "prime count bound failed");
+    PSS_TRY(bitmap_reduce(h, power, false));
+    if (m_max >= m_min && m_max >= 1) {
+        const u32 dev_cap = std::max<u32>(cap, 1);
+        PSS_TRY(ensure(h, h->tri_buf, (size_t)dev_cap * 2 * sizeof(u64) + 16));
+        MiscDev* hm = h->h_misc;
+        memset(hm, 0, sizeof(MiscDev));
+        MiscDev* dm = static_cast<MiscDev*>(h->misc.p);
+        BScanParams bp;
+        fill_bscan_common(h, bp);
+        bp.cols = static_cast<u64*>(h->cols.p);
+        bp.col_prefix = static_cast<const u64*>(h->col_prefix.p);
+        bp.n_first = 1;
+        bp.n_min = n_min;
+        bp.n_max = n_max;
+        bp.carry_in = dm->carry;
+        bp.results = dm->results;
+        bp.last_prime_out = &dm->last_prime;
+        bp.error_flag = &dm->error_flag;
+        bp.tri_m_min = std::max<u64>(m_min, 1);
+        bp.tri_m_max = m_max;
+        bp.tri_max_value = m_max * (m_max + 1) / 2;
+        bp.tri_out = static_cast<u64*>(h->tri_buf.p);
+        bp.tri_count = &dm->ticket;   // reused as the match counter
+        bp.tri_cap = cap;
+        CU_TRY(h, cudaEventRecord(h->ev[4], h->stream));
+        CU_TRY(h, cudaMemcpyAsync(dm, hm, sizeof(MiscDev), cudaMemcpyHostToDevice, h->stream));
+        PSS_TRY(launch_bscan_tri(h, bp, power));
+        CU_TRY(h, cudaEventRecord(h->ev[5], h->stream));
+        CU_TRY(h, cudaMemcpyAsync(hm, dm, sizeof(MiscDev), cudaMemcpyDeviceToHost, h->stream));
+        CU_TRY(h, cudaStreamSynchronize(h->stream));
+        h->acc.ms_power_scan += ev_ms(h, 4, 5);
+        h->acc.ms_bitmap_compare += ev_ms(h, 4, 5);
+        h->acc.primes += n_max;
+        *count = hm->ticket;
+        const u32 n_copy = std::min<u32>(hm->ticket, cap);
+        if (n_copy) CU_TRY(h, cudaMemcpy(pairs_out, h->tri_buf.p, (size_t)n_copy * 2 * sizeof(u64), cudaMemcpyDeviceToHost));
+    }
+    if (stats) fill_stats(h, stats, before);
     return PSS_OK;
 }
 

@@ -24,7 +24,7 @@ namespace pss {
 constexpr int kBsThreads = 256;
 constexpr int kWordsPerThread = 24;                          // 96 B of bitmap = 2880 integers per thread
 constexpr int kBsTileWords = kBsThreads * kWordsPerThread;   // 6144 words = 24 KiB = 737 280 integers
-enum BsMode { kBsReduce = 0, kBsCompare = 1 };
+enum BsMode { kBsReduce = 0, kBsCompare = 1, kBsTri = 2 };
 
 struct BScanParams {
     const u32* bitmap;       // word 0 = absolute byte index B_start
@@ -53,6 +53,11 @@ struct BScanParams {
     u64* last_prime_out;     // written by the thread that owns n_max
     u32* prefix_out;         // unused here (Pass2Fn interface)
     u32* error_flag;
+    // triangular-number predicate (kBsTri): S_k(n) == tri(m), m in [tri_m_min, tri_m_max]
+    u64 tri_m_min, tri_m_max, tri_max_value;
+    u64* tri_out;            // (n, m) pairs
+    u32* tri_count;
+    u32 tri_cap;
 };
 
 // Words are staged BIT-REVERSED: the lowest prime of a word is its most significant set bit m (one FLO).
@@ -107,10 +112,10 @@ struct BsAccFn {
     }
 };
 
-template <int K, bool MULTI>
+template <int K, bool MULTI, int PMODE>
 struct BsCmpFn {
     using Lay = Layout<K, MULTI>;
-    Pass2Fn<K, MULTI, kModeCompare, BScanParams> inner;
+    Pass2Fn<K, MULTI, PMODE, BScanParams> inner;
     const BScanParams* P;
     u64 tile_n0;     // global index of the tile's first prime
     u32 li;          // tile-local index of the next prime
@@ -153,7 +158,7 @@ __global__ void __launch_bounds__(kBsThreads) k_bitmap_scan(const __grid_constan
     for (u64 wt = (u64)blockIdx.x * NWARP + warp; wt < n_warp_tiles; wt += warp_stride) {
         const u32 tile = (u32)(wt / NWARP);
         const u32 wit = (u32)(wt % NWARP);          // warp index inside the scan tile
-        if constexpr (MODE == kBsCompare) {
+        if constexpr (MODE != kBsReduce) {
             if (P.n_first + P.col_prefix[tile] > P.n_max) break;   // prefixes are monotone in tile
         }
         const u64 word0 = wt * WARP_WORDS;
@@ -285,14 +290,15 @@ __global__ void __launch_bounds__(kBsThreads) k_bitmap_scan(const __grid_constan
                 mlast[jj] = 0;
                 prevc[jj] = 0;
             }
-            {
+            if constexpr (MODE == kBsCompare) {
                 OpCmpInit op{run, P.target, P.target_over_mask, prevc};
                 for_each_power<0, Lay>(op);
             }
             // window in tile-local indices: a tile holds < 2^20 primes, so saturating to u32 is exact
             const u32 lmin = (P.n_min > tile_n0) ? (u32)min(P.n_min - tile_n0, (u64)0xFFFFFFFFull) : 0u;
             const u32 lmax = (u32)min(P.n_max - tile_n0, (u64)0xFFFFFFFEull);   // n_max >= tile_n0 (checked above)
-            BsCmpFn<K, MULTI> fn{{run, &P, prevc, mcount, mfirst, mlast, tile_n0, 0, 0, 0, false}, &P, tile_n0, li0, lmin, lmax};
+            constexpr int PMODE = (MODE == kBsTri) ? kModeTri : kModeCompare;
+            BsCmpFn<K, MULTI, PMODE> fn{{run, &P, prevc, mcount, mfirst, mlast, tile_n0, 0, 0, 0, false}, &P, tile_n0, li0, lmin, lmax};
             bool go = true;
             if (has_small)
                 for (u32 i = 0; i < P.n_small && go; ++i) go = fn((u32)P.small_primes[i], 0u);

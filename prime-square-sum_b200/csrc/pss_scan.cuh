@@ -26,7 +26,7 @@ namespace pss {
 constexpr int kScanThreads = 256;
 constexpr u32 kSpinLimit = 1u << 22;   // look-back watchdog (polls); sets error_flag instead of hanging
 
-enum ScanMode { kModeReduce = 0, kModeCompare = 1, kModePrefix = 2 };
+enum ScanMode { kModeReduce = 0, kModeCompare = 1, kModePrefix = 2, kModeTri = 3 };
 
 template <int K, bool MULTI>
 PSS_HD constexpr int lay_width(int j) { return sum_limbs(MULTI ? j + 1 : K); }
@@ -239,6 +239,30 @@ struct Pass2Fn {
             u32* o = P->prefix_out + elem * PSS_LIMBS;
 #pragma unroll
             for (int i = 0; i < PSS_LIMBS; ++i) o[i] = (i < W) ? run[OFF + i] : 0u;
+        } else if constexpr (MODE == kModeTri) {
+            // S == tri(m) for some m in [tri_m_min, tri_m_max]  <=>  8S+1 is a perfect square s^2 and
+            // m = (s-1)/2 is in range (reference: utils/number_theory.py:292-354 qtri).  tri(m_max) < 2^59,
+            // so only sums that fit 64 bits can match; the square root is taken in double and corrected.
+            bool small = true;
+#pragma unroll
+            for (int i = 2; i < W; ++i) small = small && (run[OFF + i] == 0u);
+            const u64 S = ((u64)run[OFF + 1] << 32) | run[OFF];
+            if (in_window && small && S <= P->tri_max_value) {
+                const u64 d = 8ull * S + 1ull;
+                u64 r = (u64)sqrt((double)d);
+                while (r * r > d) --r;
+                while ((r + 1) * (r + 1) <= d) ++r;
+                if (r * r == d) {
+                    const u64 m = (r - 1) >> 1;
+                    if (m >= P->tri_m_min && m <= P->tri_m_max) {
+                        const u32 slot = atomicAdd(P->tri_count, 1u);
+                        if (slot < P->tri_cap) {
+                            P->tri_out[2 * slot] = n_base + local_idx;
+                            P->tri_out[2 * slot + 1] = m;
+                        }
+                    }
+                }
+            }
         } else {
             const int c = ((P->target_over_mask >> J) & 1u) ? -1 : limbs_cmp<W>(run + OFF, P->target);
             if (in_window && ((P->cmp_mask >> (c + 1)) & 1u)) {

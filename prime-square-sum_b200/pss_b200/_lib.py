@@ -65,7 +65,7 @@ EXPORTS = [
     "pss_power_sum", "pss_primesum", "pss_search",
     "pss_slice_sieve", "pss_slice_reduce", "pss_slice_scan", "pss_slice_prefix_sums", "pss_slice_primes",
     "pss_slice_device_buffer", "pss_nth_prime_upper", "pss_stats_reset", "pss_stats_get",
-    "pss_set_search_path", "pss_slice_sieve_sums", "pss_slice_scan_bitmap",
+    "pss_set_search_path", "pss_slice_sieve_sums", "pss_slice_scan_bitmap", "pss_search_tri",
 ]
 
 _cdll = None
@@ -104,6 +104,7 @@ def load_library() -> ctypes.CDLL:
     L.pss_slice_prefix_sums.argtypes = [H, u64, u64, u32, pu32, pu32]
     L.pss_slice_primes.argtypes = [H, u64, u64, pu64]
     L.pss_slice_device_buffer.argtypes = [H, ctypes.POINTER(ctypes.c_void_p), pu64]
+    L.pss_search_tri.argtypes = [H, u64, u64, u32, u64, u64, pu64, u32, pu32, ctypes.POINTER(Stats)]
     L.pss_set_search_path.argtypes = [H, ctypes.c_int]
     L.pss_slice_sieve_sums.argtypes = [H, u64, u64, u32, u32, pu64, pu32]
     L.pss_slice_scan_bitmap.argtypes = [H, u64, pu32, ctypes.POINTER(SearchArgs), ctypes.POINTER(SearchResult)]
@@ -302,6 +303,18 @@ class Handle:
         s = Stats()
         self._check(self._L.pss_stats_get(self._h, ctypes.byref(s)))
         return stats_to_dict(s)
+
+    def search_tri(self, n_min: int, n_max: int, power: int, m_min: int, m_max: int, cap: int = 4096):
+        """[(n, m)] with primesum(n, power) == tri(m), sorted by n; plus the per-kernel stats"""
+        out = np.zeros(2 * max(cap, 1), dtype=np.uint64)
+        cnt = u32(0)
+        st = Stats()
+        self._check(self._L.pss_search_tri(self._h, n_min, n_max, power, m_min, m_max, _pu64(out), cap, ctypes.byref(cnt),
+                                           ctypes.byref(st)))
+        if cnt.value > cap:
+            raise MemoryError(f"{cnt.value} matches exceed the buffer of {cap}")
+        pairs = sorted((int(out[2 * i]), int(out[2 * i + 1])) for i in range(cnt.value))
+        return pairs, stats_to_dict(st)
 
     def set_search_path(self, materialised: bool):
         self._check(self._L.pss_set_search_path(self._h, 1 if materialised else 0))

@@ -165,6 +165,16 @@ def for_any(target: int, n_max: int, power: int = 2, n_min: int = 1, op: str = "
         yield {"n": n, "p": p} if all_powers else {"n": n}
 
 
+def for_any_tri(n_max: int, m_max: int, power: int = 2, n_min: int = 1, m_min: int = 1,
+                handle: Optional["_lib.Handle"] = None) -> List[Dict[str, int]]:
+    """`for_any primesum(n,power) == tri(m)`: the reference iterates m outer / n inner (alphabetical,
+    utils/grammar.py:939,977) and prints `Found: m=36, n=7`; S(n) is strictly increasing, so ordering by m is
+    ordering by n.  Every partial sum is tested for triangularity on the device."""
+    h = handle or _lib.default_handle()
+    pairs, _ = h.search_tri(n_min, n_max, power, m_min, m_max)
+    return [{"m": m, "n": n} for n, m in sorted(pairs, key=lambda t: (t[1], t[0]))]
+
+
 # ------------------------------------------------------------------------------- multi-GPU
 def li(x: float) -> float:
     """Offset logarithmic integral estimate of pi(x) (asymptotic series; only used to balance slices)."""

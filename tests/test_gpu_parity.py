@@ -168,6 +168,45 @@ def test_find_matches_golden(handle, golden, search_path):
         assert res == case["matches"], expr
 
 
+def test_fastpath_reproduces_reference_cli_output(handle, golden):
+    """exact stdout lines / rc of the reference CLI for the hot-path query shapes
+    (tests/test_cli_integration.py:156-182,257-267; golden find_matches cases)"""
+    from pss_b200.fastpath import try_fast_query
+    assert try_fast_query("does_exist primesum(n,2) == 666") == (["Found: n=7"], 0)
+    assert try_fast_query("primesum(n,2) == 666") == (["Found: n=7"], 0)                  # default quantifier
+    assert try_fast_query("does_exist primesum(n,2) == 667", {"n": 1000}) == (["No match found within bounds."], 1)
+    assert try_fast_query("for_any primesum(n,2) == tri(m)", {"n": 100, "m": 3200}) == (["Found: m=36, n=7", "Found: m=3169, n=86"], 0)
+    assert try_fast_query("does_exist primesum(n,2) == 666", fmt="json") == (['{"found": true, "variables": {"n": 7}}'], 0)
+    assert try_fast_query("does_exist primesum(n,2) == 667", {"n": 50}, fmt="json") == (['{"found": false, "variables": null}'], 1)
+    assert try_fast_query("does_exist primesum(n,2) == 667", {"n": 50}, fmt="csv") == (["not_found"], 1)
+    assert try_fast_query("does_exist primesum(n,2) == trisum(10)") == (["Found: n=7"], 0)
+    assert try_fast_query("does_exist primesum(n,2) == trisum(666)", {"n": 200000}) == (["No match found within bounds."], 1)
+    assert try_fast_query("does_exist primesum(n,2) == 666", {"n": 100}, {"n": 8}) == (["No match found within bounds."], 1)
+    assert try_fast_query("primesum(n,2) + 1 == 667") is None and try_fast_query("fibonacci(n) == 8") is None
+    for case in golden["find_matches"]:
+        res = try_fast_query(case["expr"], case["bounds"])
+        exp = ["Found: " + ", ".join(f"{k}={v}" for k, v in sorted(mm.items())) for mm in case["matches"]]
+        assert res == ((exp, 0) if exp else (["No match found within bounds."], 1)), case["expr"]
+
+
+def test_tri_predicate(handle, orc, golden):
+    """config C2's RHS: for_any primesum(n,2) == tri(m) (reference answer from find_matches: m=36,n=7; m=3169,n=86)"""
+    from pss_b200 import search
+    case = next(c for c in golden["find_matches"] if "tri(m)" in c["expr"])
+    assert search.for_any_tri(case["bounds"]["n"], case["bounds"]["m"]) == case["matches"]
+    assert search.for_any_tri(100, 3168) == [{"m": 36, "n": 7}]            # m bound is inclusive
+    assert search.for_any_tri(100, 3200, n_min=8) == [{"m": 3169, "n": 86}]
+    assert search.for_any_tri(85, 10 ** 7) == [{"m": 36, "n": 7}]
+    # every power against the oracle's qtri on every partial sum
+    primes = orc.c_first_n_primes(200000)
+    for k in (1, 2, 3):
+        sums = orc.c_prefix_sums(primes, k)
+        exp = [{"m": orc.qtri(s), "n": i + 1} for i, s in enumerate(sums) if orc.qtri(s) is not None and 1 <= orc.qtri(s) <= 2 ** 28]
+        assert search.for_any_tri(200000, 2 ** 28, power=k) == sorted(exp, key=lambda d: (d["m"], d["n"])), k
+    # SURVEY §8c: within tri(1e7) the only hits of primesum(n,2) are (7,36) and (86,3169)
+    assert search.for_any_tri(10 ** 6, 10 ** 7) == [{"m": 36, "n": 7}, {"m": 3169, "n": 86}]
+
+
 @pytest.mark.parametrize("k,multi", [(1, False), (2, False), (3, False), (4, False), (5, False), (6, False), (7, False),
                                      (8, False), (2, True), (3, True), (5, True), (6, True)])
 def test_synthetic_hits_and_brackets(handle, orc, k, multi, search_path):
@@ -355,6 +394,12 @@ def test_at_scale_1e8(handle, golden):
     ptr, cnt = handle.slice_device_buffer()
     assert cnt == 10 ** 8
     assert sha_u64(got) == row["sha256_primes_le_u64"]
+
+
+def test_at_scale_c2(handle, golden):
+    """config C2 at full size: for_any primesum(n,2) == tri(m), n <= 1e8, m <= 1e7"""
+    from pss_b200 import search
+    assert search.for_any_tri(10 ** 8, 10 ** 7) == [{"m": 36, "n": 7}, {"m": 3169, "n": 86}]
 
 
 def test_at_scale_1e9_c3(handle, golden, search_path):

@@ -283,3 +283,24 @@ def test_distributed_search_world_size_2_gloo(orc):
         assert out["miss"] == (None, (n_max, n_max + 1), S[2][-1], int(primes[-1]))
         below = sum(1 for n in range(50, n_max + 1) if S[2][n - 1] < 10 ** 12)
         assert out["lt"] == (below, 50, 49 + below)
+
+
+# --------------------------------------------------------------------------- fast-path recogniser (host part)
+def test_fastpath_recogniser_host_side(orc):
+    from pss_b200 import fastpath
+    for b in (1, 2, 3, 6, 10, 15, 28, 100, 666):
+        assert fastpath._trisum(b) == orc.trisum(b)
+    assert fastpath._trisum(666).bit_length() == 325
+    # shapes that are NOT the hot path stay with the generic evaluator
+    for expr in ("fibonacci(n) == 8", "primesum(n,2) + 1 == 667", "does_exist primesum(n,2) == fibonacci(m)",
+                 "for_any primesum(n,2) < tri(m)", "verify primesum(7,2) == 666", "primesum(n, n) == 4"):
+        assert fastpath.try_fast_query(expr, {"n": 10, "m": 10}) is None, expr
+    m = fastpath._EXPR.match("for_any primesum(n,p) >= 8944")
+    assert m.groupdict() == {"quant": "for_any", "nvar": "n", "parg": "p", "op": ">=", "rhs": "8944"}
+    assert fastpath.format_match({"n": 7, "m": 36}) == "Found: m=36, n=7"                      # utils/cli.py:1253,1271
+    assert fastpath.format_match({"n": 7}, "json") == '{"found": true, "variables": {"n": 7}}'  # tests/test_cli_integration.py:257-267
+    assert fastpath.format_match({"n": 7}, "csv") == "n=7"
+    assert fastpath.format_no_match() == "No match found within bounds."
+    assert fastpath.format_no_match("json") == '{"found": false, "variables": null}'
+    with pytest.raises(ValueError, match="Missing bound"):
+        fastpath.try_fast_query("primesum(q,2) == 4")
