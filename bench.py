@@ -299,6 +299,8 @@ def main():
         launches = int(tsum[6])
     else:
         wall_ms = wall * 1e3
+    if os.environ.get("PSS_TRACE") and world > 1:
+        print(f"[trace rank {rank}] host phases of the last step (ms): {out.stats.get('host_ms')}", file=sys.stderr)
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()

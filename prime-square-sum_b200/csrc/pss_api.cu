@@ -310,16 +310,12 @@ int sieve_range(pss_handle* h, u64 lo, u64 hi) {
         sp.n_base = (e > b) ? (u32)(e - b) : 0;
         const u32 warp_lim = tile_bytes / std::max<u32>(h->warp_wide_div, 1);
         sp.n_warp_wide = (e > b) ? (u32)(std::lower_bound(b, e, warp_lim) - b) : 0;
-        // per tile: how many base primes satisfy p*p < tile end (ascending in t)
-        std::vector<u32> nact(n_tiles);
-        for (u32 t = 0; t < n_tiles; ++t) {
-            const u64 tile_end = std::min<u64>((B_start + (u64)(t + 1) * tile_bytes) * 30ull, hi);
-            const u64 pl = isqrt_u64(tile_end - 1);
-            nact[t] = (e > b) ? (u32)(std::upper_bound(b, e, (u32)std::min<u64>(pl, 0xFFFFFFFFull)) - b) : 0;
-        }
+        // per tile: how many base primes satisfy p*p < tile end (tiny device kernel, no host work)
         PSS_TRY(ensure(h, h->tile_nact, (size_t)n_tiles * sizeof(u32)));
-        CU_TRY(h, cudaMemcpyAsync(h->tile_nact.p, nact.data(), (size_t)n_tiles * sizeof(u32), cudaMemcpyHostToDevice, h->stream));
-        CU_TRY(h, cudaStreamSynchronize(h->stream));   // nact is a stack-lifetime staging buffer
+        k_tile_nact<<<(n_tiles + 255) / 256, 256, 0, h->stream>>>(sp.base_p, sp.n_base, B_start, tile_bytes, hi, n_tiles,
+                                                                  static_cast<u32*>(h->tile_nact.p));
+        CU_TRY(h, cudaGetLastError());
+        h->launches++;
         sp.tile_nact = static_cast<const u32*>(h->tile_nact.p);
     }
     sp.n_pat = h->n_pat;

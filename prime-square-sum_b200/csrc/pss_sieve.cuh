@@ -70,6 +70,21 @@ __global__ void k_build_pattern(uint8_t* out, u64 n_bytes, u32 q0, u32 q1, u32 q
     }
 }
 
+// per tile: number of base primes with p*p < tile end (exact 64-bit compare, binary search; ascending table)
+__global__ void k_tile_nact(const u32* base_p, u32 n_base, u64 B_start, u32 tile_bytes, u64 hi, u32 n_tiles, u32* out) {
+    const u32 t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n_tiles) return;
+    u64 tile_end = (B_start + (u64)(t + 1) * tile_bytes) * 30ull;
+    if (tile_end > hi) tile_end = hi;
+    u32 lo = 0, hiI = n_base;            // first index with p*p >= tile_end
+    while (lo < hiI) {
+        const u32 mid = (lo + hiI) >> 1;
+        const u64 p = base_p[mid];
+        if (p * p < tile_end) lo = mid + 1; else hiI = mid;
+    }
+    out[t] = lo;
+}
+
 // r = B0 mod p.  32-bit byte indices (hi < 1.28e11): one mul-hi with the staged reciprocal.
 __device__ __forceinline__ u32 tile_mod(u64 B0, u32 p, u32 inv, bool wide) {
     if (wide) return (u32)(B0 % p);

@@ -190,19 +190,33 @@ def li(x: float) -> float:
     return x / lx * (1.0 + s)
 
 
-def partition_range(hi_excl: int, parts: int, lo: int = 0) -> List[Tuple[int, int]]:
-    """Cut [lo, hi_excl) into `parts` contiguous slices of ~equal prime count; interior cuts are multiples
-    of 480 (16 bitmap bytes) so every slice starts on a 16-byte aligned bitmap byte."""
+# Cost model behind the slice cuts (measured on B200, profiles/r01): the scan passes cost is proportional to
+# the slice's prime count, the sieve's to its width times a slowly growing per-integer factor (more base
+# primes are active in higher tiles: ~ (x/N)^0.12); for the whole C3 range sieve : scans = 0.635 : 1.
+SIEVE_WEIGHT = 0.635
+SIEVE_EXPONENT = 0.12
+
+
+def partition_range(hi_excl: int, parts: int, lo: int = 0, sieve_weight: float = SIEVE_WEIGHT,
+                    sieve_exponent: float = SIEVE_EXPONENT) -> List[Tuple[int, int]]:
+    """Cut [lo, hi_excl) into `parts` contiguous slices of ~equal estimated device time
+    (sieve_weight = 0: equal prime counts); interior cuts are multiples of 480 (16 bitmap bytes) so every
+    slice starts on a 16-byte aligned bitmap byte."""
     if parts <= 1 or hi_excl - lo < 480 * parts * 4:
         return [(lo, hi_excl)] + [(hi_excl, hi_excl)] * (parts - 1)
-    total = li(hi_excl) - li(lo)
+    pi_est = li(hi_excl)
+
+    def cost(x: float) -> float:
+        return li(x) + sieve_weight * pi_est * (max(x, 0.0) / hi_excl) ** (1.0 + sieve_exponent)
+
+    total = cost(hi_excl) - cost(lo)
     cuts = [lo]
     for g in range(1, parts):
-        want = li(lo) + total * g / parts
+        want = cost(lo) + total * g / parts
         a, b = cuts[-1], hi_excl
         for _ in range(64):
             mid = (a + b) / 2
-            if li(mid) < want:
+            if cost(mid) < want:
                 a = mid
             else:
                 b = mid
@@ -257,9 +271,11 @@ def distributed_search(target: int, n_max: int, power: int = 2, n_min: int = 1, 
     exchanges go through torch.distributed: the (count, sums) allgather as a uint32 CUDA tensor over NCCL,
     the final merge as an object gather.
     """
+    import time
     import torch
     import torch.distributed as dist
 
+    t0 = time.perf_counter()
     world = dist.get_world_size(group) if dist.is_initialized() else 1
     rank = dist.get_rank(group) if dist.is_initialized() else 0
     h = handle or _lib.default_handle()
@@ -271,15 +287,18 @@ def distributed_search(target: int, n_max: int, power: int = 2, n_min: int = 1, 
     np_ = _np(power, all_powers)
     # fused phase A: sieve + per-tile sums (no u64 prime buffer); leaves the slice's bitmap resident
     count_g, sums_g = h.slice_sieve_sums(lo_g, hi_g, power, all_powers)
+    t1 = time.perf_counter()
 
     # ---- the one exchange: 8 B count + np_ * 48 B of limbs per rank
     payload = [count_g & 0xFFFFFFFF, count_g >> 32]
     for s in sums_g:
         payload.extend(int(x) for x in _lib.int_to_limbs(s, _lib.PSS_LIMBS))
+    dev = None
+    if gather is None:
+        dev = torch.device("cuda", torch.cuda.current_device()) if dist.get_backend(group) == "nccl" else torch.device("cpu")
     if gather is not None:
         rows = gather(payload)
     else:
-        dev = torch.device("cuda", torch.cuda.current_device()) if dist.get_backend(group) == "nccl" else torch.device("cpu")
         mine = torch.tensor(payload, dtype=torch.int64, device=dev)
         parts = [torch.empty_like(mine) for _ in range(world)]
         dist.all_gather(parts, mine, group=group)       # NCCL over NVLink on the GPU box, gloo in CPU tests
@@ -289,6 +308,7 @@ def distributed_search(target: int, n_max: int, power: int = 2, n_min: int = 1, 
     if sum(counts) < n_max:
         raise RuntimeError("prime count bound violated")
     n_before, carry = combine_slices(counts, sums, rank)
+    t2 = time.perf_counter()
 
     # ---- local scan with the carry; the rank holding n_max truncates, later ranks skip
     local = None
@@ -296,9 +316,62 @@ def distributed_search(target: int, n_max: int, power: int = 2, n_min: int = 1, 
     if take > 0:
         res = h.slice_scan_bitmap(n_before + 1, carry, n_min, n_max, power, target, op, all_powers)
         local = _outcome_from_result(res, n_min, n_max, op, target)
+    t3 = time.perf_counter()
+    # ---- merge: one more fixed-size exchange (per power: 5 u64 + 3 x 12 limbs, + last_prime / stats)
+    rec = _pack_outcome(local, np_)
     if gather is not None:
-        outs = gather(local)
+        rows = gather(rec)
     else:
-        outs = [None] * world
-        dist.all_gather_object(outs, local, group=group)
-    return merge_outcomes(outs, n_min, n_max, op, target)
+        mine = torch.tensor(rec, dtype=torch.int64, device=dev)
+        parts = [torch.empty_like(mine) for _ in range(world)]
+        dist.all_gather(parts, mine, group=group)
+        rows = [t.cpu().tolist() for t in parts]
+    outs = [_unpack_outcome(r, np_, power, all_powers, n_min, n_max, op, target) for r in rows]
+    merged = merge_outcomes(outs, n_min, n_max, op, target)
+    t4 = time.perf_counter()
+    merged.stats["host_ms"] = {"sieve_sums": (t1 - t0) * 1e3, "exchange": (t2 - t1) * 1e3, "scan": (t3 - t2) * 1e3,
+                               "merge": (t4 - t3) * 1e3}
+    return merged
+
+
+_STAT_KEYS = ("ms_sieve", "ms_count_scan", "ms_compact", "ms_power_scan", "ms_bitmap_reduce", "ms_bitmap_compare",
+              "ms_total_device", "primes", "sieve_lo", "sieve_hi", "launches")
+
+
+def _pack_outcome(o: Optional[SearchOutcome], np_: int) -> List[int]:
+    """fixed-size int64 record of a rank's outcome (big integers as 32-bit limbs; times in nanoseconds)"""
+    L = _lib.PSS_LIMBS
+    if o is None:
+        return [0] * (2 + len(_STAT_KEYS) + np_ * (5 + 3 * L))
+    rec = [1, o.last_prime]
+    for k in _STAT_KEYS:
+        v = o.stats.get(k, 0)
+        rec.append(int(round(v * 1e6)) if k.startswith("ms_") else int(v))
+    for p in o.powers:
+        rec += [p.match_count, p.first_match_n, p.last_match_n, p.cross_n, p.cross_prime]
+        for big in (p.sum_at_cross, p.sum_before_cross, p.final_sum):
+            rec += [int(x) for x in _lib.int_to_limbs(big, L)]
+    return rec
+
+
+def _unpack_outcome(r: Sequence[int], np_: int, power: int, all_powers: bool, n_min, n_max, op, target) -> Optional[SearchOutcome]:
+    L = _lib.PSS_LIMBS
+    if not r[0]:
+        return None
+    stats = {}
+    for i, k in enumerate(_STAT_KEYS):
+        v = r[2 + i]
+        stats[k] = v / 1e6 if k.startswith("ms_") else v
+    pos = 2 + len(_STAT_KEYS)
+    powers = []
+    for j in range(np_):
+        mc, fm, lm, cn, cp = r[pos:pos + 5]
+        pos += 5
+        bigs = []
+        for _ in range(3):
+            bigs.append(_lib.limbs_to_int(r[pos:pos + L]))
+            pos += L
+        powers.append(PowerOutcome(power=(j + 1) if (all_powers and power > 1) else power, match_count=mc, first_match_n=fm,
+                                   last_match_n=lm, cross_n=cn, cross_prime=cp, sum_at_cross=bigs[0],
+                                   sum_before_cross=bigs[1], final_sum=bigs[2]))
+    return SearchOutcome(n_min, n_max, op, target, r[1], powers, stats)

@@ -104,13 +104,16 @@ def test_partition_range_is_contiguous_aligned_and_balanced(orc):
         assert len(sl) == parts and sl[0][0] == 0 and sl[-1][1] == hi
         for (a, b), (c, d) in zip(sl, sl[1:]):
             assert b == c and b % 480 == 0
-    # balance: li(x) estimate vs the true pi(x) at 5e8 primes (p_{5e8} = 11 037 271 757)
-    two = search.partition_range(hi, 2)
+    # prime-count balance (sieve_weight = 0): li(x) estimate vs the true pi(x) at 5e8 primes (p_{5e8} = 11 037 271 757)
+    two = search.partition_range(hi, 2, sieve_weight=0.0)
     assert abs(two[0][1] - 11037271757) / 11037271757 < 0.002
+    # default = estimated device time: the upper slice costs more per integer, so it is narrower than that
+    two_t = search.partition_range(hi, 2)
+    assert 11037271757 < two_t[0][1] < 0.53 * hi
     # small ranges collapse to one slice
     assert search.partition_range(1000, 4) == [(0, 1000)] + [(1000, 1000)] * 3
     # exact balance check on a range the oracle can count
-    sl = search.partition_range(2 * 10 ** 7, 4)
+    sl = search.partition_range(2 * 10 ** 7, 4, sieve_weight=0.0)
     counts = [orc.c_count_range(a, b) for a, b in sl]
     assert max(counts) / min(counts) < 1.02
 
