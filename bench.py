@@ -270,7 +270,8 @@ def main():
     if rank == 0:
         sampler.start()
     per_step_dev = []
-    kern = {"ms_sieve": 0.0, "ms_count_scan": 0.0, "ms_compact": 0.0, "ms_power_scan": 0.0}
+    kern = {"ms_sieve": 0.0, "ms_count_scan": 0.0, "ms_compact": 0.0, "ms_power_scan": 0.0, "ms_bitmap_reduce": 0.0,
+            "ms_bitmap_compare": 0.0}
     launches = 0
     barrier()
     t0 = time.perf_counter()
@@ -288,15 +289,15 @@ def main():
 
     dev_ms = sum(per_step_dev)
     if world > 1:
-        t = torch.tensor([dev_ms, wall * 1e3, kern["ms_sieve"], kern["ms_count_scan"], kern["ms_compact"], kern["ms_power_scan"],
-                          float(launches)], dtype=torch.float64, device="cuda")
+        kkeys = ["ms_sieve", "ms_count_scan", "ms_compact", "ms_power_scan", "ms_bitmap_reduce", "ms_bitmap_compare"]
+        t = torch.tensor([dev_ms, wall * 1e3] + [kern[k] for k in kkeys] + [float(launches)], dtype=torch.float64, device="cuda")
         tmax = t.clone()
         dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
         tsum = t.clone()
         dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
         dev_ms, wall_ms = float(tmax[0]), float(tmax[1])
-        kern = {k: float(tmax[2 + i]) for i, k in enumerate(["ms_sieve", "ms_count_scan", "ms_compact", "ms_power_scan"])}
-        launches = int(tsum[6])
+        kern = {k: float(tmax[2 + i]) for i, k in enumerate(kkeys)}
+        launches = int(tsum[2 + len(kkeys)])
     else:
         wall_ms = wall * 1e3
     if os.environ.get("PSS_TRACE") and world > 1:
@@ -316,17 +317,25 @@ def main():
     primes_per_launch = n_primes / world
     np_ = w["power"] if w["all_powers"] else 1
     imad = sum(IMAD_PER_PRIME.get(k, 0) for k in ([w["power"]] if not w["all_powers"] else [w["power"]]))
+    def rate(x, ms):
+        return x / (ms * 1e-3) if ms else None
+
+    ms_reduce = per.get("ms_bitmap_reduce", 0.0)
+    ms_compare = per.get("ms_bitmap_compare", 0.0)
     kernels = {
-        "k_sieve": {"ms": per["ms_sieve"], "hbm_GBps_algorithmic": 8 * primes_per_launch / (per["ms_sieve"] * 1e-3) / 1e9 if per["ms_sieve"] else None,
-                    "smem_crossoffs_per_s": CROSSOFFS_PER_PRIME[args.workload] * primes_per_launch / (per["ms_sieve"] * 1e-3) if per["ms_sieve"] else None,
-                    "smem_peak_accesses_per_s": 148 * 32 * 1.965e9, "integers_per_s": (w["p_n"] + 1) / world / (per["ms_sieve"] * 1e-3) if per["ms_sieve"] else None},
+        "k_sieve": {"ms": per["ms_sieve"], "hbm_GBps_algorithmic": rate(8 * primes_per_launch, per["ms_sieve"]) and rate(8 * primes_per_launch, per["ms_sieve"]) / 1e9,
+                    "smem_crossoffs_per_s": rate(CROSSOFFS_PER_PRIME[args.workload] * primes_per_launch, per["ms_sieve"]),
+                    "smem_peak_accesses_per_s": 148 * 32 * 1.965e9,
+                    "integers_per_s": rate((w["p_n"] + 1) / world, per["ms_sieve"])},
         "k_scan_tile_counts": {"ms": per["ms_count_scan"]},
-        "k_compact": {"ms": per["ms_compact"], "hbm_GBps_algorithmic": 8 * primes_per_launch / (per["ms_compact"] * 1e-3) / 1e9 if per["ms_compact"] else None},
-        "k_power_scan": {"ms": per["ms_power_scan"], "hbm_GBps_algorithmic": 8 * primes_per_launch / (per["ms_power_scan"] * 1e-3) / 1e9 if per["ms_power_scan"] else None,
-                         "imad_per_s": imad * primes_per_launch * (2 if world > 1 else 1) / (per["ms_power_scan"] * 1e-3) if per["ms_power_scan"] else None,
-                         "imad_peak_per_s": 148 * 64 * 1.965e9},
+        "k_compact": {"ms": per["ms_compact"], "hbm_GBps_algorithmic": rate(8 * primes_per_launch, per["ms_compact"]) and rate(8 * primes_per_launch, per["ms_compact"]) / 1e9},
+        "k_bitmap_scan<reduce>+k_scan_columns": {"ms": ms_reduce, "hbm_GBps_algorithmic": rate(8 * primes_per_launch, ms_reduce) and rate(8 * primes_per_launch, ms_reduce) / 1e9,
+                                                 "imad_per_s": rate(imad * primes_per_launch, ms_reduce), "imad_peak_per_s": 148 * 64 * 1.965e9},
+        "k_bitmap_scan<compare>": {"ms": ms_compare, "hbm_GBps_algorithmic": rate(8 * primes_per_launch, ms_compare) and rate(8 * primes_per_launch, ms_compare) / 1e9,
+                                   "imad_per_s": rate(imad * primes_per_launch, ms_compare), "imad_peak_per_s": 148 * 64 * 1.965e9},
+        "k_power_scan (materialised path)": {"ms": max(per["ms_power_scan"] - ms_reduce - ms_compare, 0.0)},
     }
-    dominant = max(("k_sieve", "k_compact", "k_power_scan"), key=lambda k: kernels[k]["ms"])
+    dominant = max(("k_sieve", "k_compact", "k_bitmap_scan<reduce>+k_scan_columns", "k_bitmap_scan<compare>"), key=lambda k: kernels[k]["ms"])
     traffic = None
     tp = os.path.join(ROOT, "profiles", "ncu_traffic.json")
     if os.path.exists(tp):
@@ -338,7 +347,8 @@ def main():
     roofline = {
         "bound": "hbm", "kernel": dominant, "achieved": achieved, "peak": peak, "unit": "GB/s",
         "frac": achieved / peak if achieved else None, "traffic": traffic, "peak_source": peak_src,
-        "algorithmic_bytes_per_unit": "8 B per prime per kernel (u64 written once by K1, read once by K3); 16 B per prime for the path",
+        "algorithmic_bytes_per_unit": "SURVEY 8(d): 8 B per prime per kernel (u64 written once by K1, read once by K3), 16 B per prime for "
+                                      "the path; the fused path actually moves 0.76 B/prime (bit-packed wheel-30), see traffic",
         "path_achieved_GBps": 16 * n_primes / (dev_ms / K * 1e-3) / 1e9,
         "path_frac": 16 * n_primes / (dev_ms / K * 1e-3) / 1e9 / peak,
         "kernels": kernels,

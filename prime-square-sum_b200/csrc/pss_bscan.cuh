@@ -73,33 +73,40 @@ __device__ __forceinline__ u32 msb_value_offset(u32 m) {
     return r - 30u * (m >> 3);
 }
 
+__device__ __forceinline__ u32 msb_index(u32 w) {   // FLO: index of the most significant set bit (w != 0)
+    u32 r;
+    asm("bfind.u32 %0, %1;" : "=r"(r) : "r"(w));
+    return r;
+}
+
 // Decode loop: one prime per iteration for every lane that still has one (lanes own equal word counts, so
-// the trip counts differ only by the local density fluctuation).  The refill of an exhausted word is
-// branch-free (unconditional shared-memory load + selects) and the body is a plain if-region, so the warp
-// reconverges every iteration and never splits around the power chain.
-// f(plo, phi) -> false stops this lane (past n_max).
+// the trip counts differ only by the local density fluctuation).  Refill of an exhausted word is branch-free:
+// an unconditional shared-memory load + select; the thread's padded row ends with a zero sentinel word, so no
+// bounds select is needed.  The body is a plain if-region: the warp reconverges every iteration.
+// f(plo, phi) -> false stops this lane.  Returns the last prime handed to f.
 template <class F>
-__device__ __forceinline__ void walk_words(const u32* my_words, u32 base_lo, u32 base_hi, F& f) {
-    u32 wi = 0, w = 0, woff = 0;
+__device__ __forceinline__ u64 walk_words(const u32* my_words, u64 value_base, F& f) {
+    const u32* ptr = my_words;
+    const u32* const end = my_words + kWordsPerThread;   // sentinel slot (always 0)
+    u32 w = 0, woff = 0u - 120u;
+    u64 p = 0;
     bool alive = true;
     while (alive) {
         const bool need = (w == 0);
-        const u32 idx = min(wi, (u32)(kWordsPerThread - 1));
-        const u32 nw = my_words[idx];
-        w = need ? ((wi < (u32)kWordsPerThread) ? nw : 0u) : w;
-        woff = need ? idx * 120u : woff;
-        wi += need ? 1u : 0u;
+        const u32 nw = *ptr;             // ptr <= end: inside this thread's padded row
+        w = need ? nw : w;
+        ptr += need ? 1 : 0;
+        woff += need ? 120u : 0u;
         if (w != 0) {
-            const u32 m = 31u - (u32)__clz(w);
+            const u32 m = msb_index(w);
             w ^= (1u << m);
-            const u32 off = woff + msb_value_offset(m);
-            const u32 plo = base_lo + off;
-            const u32 phi = base_hi + (plo < off ? 1u : 0u);
-            alive = f(plo, phi);
+            p = value_base + (u64)(woff + msb_value_offset(m));
+            alive = f((u32)p, (u32)(p >> 32));
         } else {
-            alive = (wi <= (u32)kWordsPerThread);   // empty word (rare): try the next one; else done
+            alive = (ptr <= end);        // empty word (rare): try the next one; sentinel: done
         }
     }
+    return p;
 }
 
 template <int K, bool MULTI>
@@ -112,37 +119,127 @@ struct BsAccFn {
     }
 };
 
-template <int K, bool MULTI, int PMODE>
+// most-significant-limb-first three-way compare (the outcome is almost always decided by the top limb)
+template <int W>
+__device__ __forceinline__ int limbs_cmp_top(const u32* a, const u32* t) {
+#pragma unroll
+    for (int i = W - 1; i >= 0; --i)
+        if (a[i] != t[i]) return (a[i] < t[i]) ? -1 : 1;
+    return 0;
+}
+
+// Compare-pass functor.  Every partial sum S_k(n) is formed in `run` and compared with the target; the
+// per-thread bookkeeping uses that S is strictly increasing: inside one thread the outcomes are
+// "<" ... "<" ["=="] ">" ... ">", so (number below, index of the equal one, number processed) describe every
+// operator's matches exactly.  quota = primes left up to n_max, skip = primes still below n_min.
+template <int K, bool MULTI, int PMODE, bool HAS_SKIP>
 struct BsCmpFn {
     using Lay = Layout<K, MULTI>;
-    Pass2Fn<K, MULTI, PMODE, BScanParams> inner;
+    static constexpr int NP = Lay::NP;
+    u32* run;
     const BScanParams* P;
-    u64 tile_n0;     // global index of the tile's first prime
-    u32 li;          // tile-local index of the next prime
-    u32 lmin, lmax;  // window [n_min, n_max] in tile-local indices (saturated)
+    u64 tile_n0;       // global index of the tile's first prime
+    u32 li;            // tile-local index of the next prime
+    u32 quota, skip;
+    u32 n_in;          // in-window primes processed
+    u32 n_lt[NP];      // ... of which S < target
+    u32 eq_li[NP];     // tile-local index with S == target (in window), 0xFFFFFFFF if none
+    bool below[NP];    // previous partial sum < target
+    u32 cur_lo, cur_hi;
+
+    template <int E>
+    __device__ __forceinline__ void apply(const Big<pow_limbs(E)>& pe) {
+        constexpr int J = MULTI ? E - 1 : 0;
+        acc_add<Lay::offset(J), Lay::width(J), pow_limbs(E)>(run, pe.v);
+        post<E>(&pe);
+    }
+    __device__ __forceinline__ void apply_square(u32 plo, u32 phi) {
+        square_acc4(run, plo, phi);
+        post<2>(nullptr);
+    }
+    template <int E>
+    __device__ __forceinline__ void post(const Big<pow_limbs(E)>* pe) {
+        constexpr int J = MULTI ? E - 1 : 0;
+        constexpr int OFF = Lay::offset(J), W = Lay::width(J);
+        const bool inw = HAS_SKIP ? (skip == 0) : true;
+        if constexpr (PMODE == kModeTri) {
+            // S == tri(m), m in [tri_m_min, tri_m_max]  <=>  8S+1 = s^2 and m = (s-1)/2 in range
+            // (utils/number_theory.py:292-354 qtri).  tri(m_max) < 2^59: only sums that fit 64 bits can match.
+            bool small = true;
+#pragma unroll
+            for (int i = 2; i < W; ++i) small = small && (run[OFF + i] == 0u);
+            const u64 S = ((u64)run[OFF + 1] << 32) | run[OFF];
+            if (inw && small && S <= P->tri_max_value) {
+                const u64 d = 8ull * S + 1ull;
+                u64 r = (u64)sqrt((double)d);
+                while (r * r > d) --r;
+                while ((r + 1) * (r + 1) <= d) ++r;
+                if (r * r == d) {
+                    const u64 m = (r - 1) >> 1;
+                    if (m >= P->tri_m_min && m <= P->tri_m_max) {
+                        const u32 slot = atomicAdd(P->tri_count, 1u);
+                        if (slot < P->tri_cap) {
+                            P->tri_out[2 * slot] = tile_n0 + li;
+                            P->tri_out[2 * slot + 1] = m;
+                        }
+                    }
+                }
+            }
+        } else {
+            const int c = ((P->target_over_mask >> J) & 1u) ? -1 : limbs_cmp_top<W>(run + OFF, P->target);
+            if (inw) {
+                n_lt[J] += (c < 0) ? 1u : 0u;
+                if (c == 0) eq_li[J] = li;
+            }
+            if (below[J] && c >= 0) {   // the unique crossing of this power: S(n-1) < T <= S(n)
+                pss_power_result* r = P->results + J;
+                r->cross_n = tile_n0 + li;
+                r->cross_prime = ((u64)cur_hi << 32) | cur_lo;
+                Big<pow_limbs(E)> pw;
+                if (pe) {
+                    pw = *pe;
+                } else {   // fused-square path: rebuild p^2 for the (once per query) bracket record
+                    Big<2> p1;
+                    p1.v[0] = cur_lo;
+                    p1.v[1] = cur_hi;
+                    big_mul_p<pow_limbs(2), 2>(reinterpret_cast<Big<pow_limbs(2)>&>(pw), p1, cur_lo, cur_hi);
+                }
+                u32 before[W];
+                limbs_sub<W, pow_limbs(E)>(before, run + OFF, pw.v);
+#pragma unroll
+                for (int i = 0; i < PSS_LIMBS; ++i) {
+                    r->sum_at_cross[i] = (i < W) ? run[OFF + i] : 0u;
+                    r->sum_before_cross[i] = (i < W) ? before[i] : 0u;
+                }
+            }
+            below[J] = (c < 0);
+        }
+    }
     __device__ __forceinline__ bool operator()(u32 plo, u32 phi) {
-        if (li > lmax) return false;
-        inner.p = ((u64)phi << 32) | plo;
-        inner.local_idx = li;
-        inner.in_window = (li >= lmin);
-        power_chain2<K, MULTI>(plo, phi, inner);
-        if (li == lmax && tile_n0 + li == P->n_max) {   // exactly one thread in the grid: S(n_max), p_{n_max}
-            *P->last_prime_out = inner.p;
-#pragma unroll
-            for (int jj = 0; jj < Lay::NP; ++jj)
-#pragma unroll
-                for (int i = 0; i < PSS_LIMBS; ++i)
-                    P->results[jj].final_sum[i] = (i < Lay::width(jj)) ? inner.run[Lay::offset(jj) + i] : 0u;
+        cur_lo = plo;
+        cur_hi = phi;
+        power_chain2<K, MULTI>(plo, phi, *this);
+        if (HAS_SKIP) {
+            if (skip == 0) ++n_in; else --skip;
+        } else {
+            ++n_in;
         }
         ++li;
-        return true;
+        return --quota != 0;
     }
 };
 
 // Warp-autonomous kernel: a warp owns one "warp tile" = 32 threads x 24 words (768 words, 92 160 integers);
 // 8 consecutive warp tiles form a scan tile (the granularity of the column prefix).  No __syncthreads.
+// resident CTAs per SM the register allocation is bounded for (issue-bound kernel: occupancy hides the
+// dependent IMAD/carry chains)
+template <int K, bool MULTI>
+constexpr int bs_min_blocks() {
+    return MULTI ? (K >= 4 ? 2 : 3) : (K >= 6 ? 3 : 1);
+}
+
 template <int K, bool MULTI, int MODE>
-__global__ void __launch_bounds__(kBsThreads) k_bitmap_scan(const __grid_constant__ BScanParams P) {
+__global__ void __launch_bounds__(kBsThreads, bs_min_blocks<K, MULTI>()) k_bitmap_scan(const __grid_constant__ BScanParams P) {
     using Lay = Layout<K, MULTI>;
     constexpr int TOTAL = Lay::TOTAL, NP = Lay::NP, T = kBsThreads, NWARP = T / 32;
     constexpr int WPT = kWordsPerThread, PAD = WPT + 1, WARP_WORDS = 32 * WPT;
@@ -152,6 +249,7 @@ __global__ void __launch_bounds__(kBsThreads) k_bitmap_scan(const __grid_constan
     const u32 tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
     u32* my_warp_words = s_words + warp * 32 * PAD;
     const u32* my_words = my_warp_words + lane * PAD;
+    my_warp_words[lane * PAD + WPT] = 0u;        // sentinel word of this thread's row (never overwritten)
     const u64 n_warp_tiles = (u64)P.n_tiles * NWARP;
     const u64 warp_stride = (u64)gridDim.x * NWARP;
 
@@ -178,7 +276,6 @@ __global__ void __launch_bounds__(kBsThreads) k_bitmap_scan(const __grid_constan
         __syncwarp();
 
         const u64 value_base = (P.B_start + 4ull * (word0 + (u64)lane * WPT)) * 30ull;
-        const u32 base_lo = (u32)value_base, base_hi = (u32)(value_base >> 32);
         const bool has_small = (wt == 0 && lane == 0 && P.n_small > 0);
         const u64 gthread = wt * 32 + lane;
 
@@ -195,7 +292,7 @@ __global__ void __launch_bounds__(kBsThreads) k_bitmap_scan(const __grid_constan
                 for (u32 i = 0; i < P.n_small; ++i) fn((u32)P.small_primes[i], 0u);
                 cnt += P.n_small;
             }
-            walk_words(my_words, base_lo, base_hi, fn);
+            walk_words(my_words, value_base, fn);
             P.thread_rec[gthread] = cnt;
 #pragma unroll
             for (int i = 0; i < TOTAL; ++i) P.thread_rec[(u64)(1 + i) * P.thread_stride + gthread] = acc[i];
@@ -280,41 +377,90 @@ __global__ void __launch_bounds__(kBsThreads) k_bitmap_scan(const __grid_constan
                 for_each_power<0, Lay>(op);
             }
             const u64 tile_n0 = P.n_first + P.col_prefix[tile];
-            // ---- every S_k(n) formed and compared
-            int prevc[NP];
-            u32 mcount[NP], mfirst[NP], mlast[NP];
-#pragma unroll
-            for (int jj = 0; jj < NP; ++jj) {
-                mcount[jj] = 0;
-                mfirst[jj] = 0xFFFFFFFFu;
-                mlast[jj] = 0;
-                prevc[jj] = 0;
-            }
-            if constexpr (MODE == kBsCompare) {
-                OpCmpInit op{run, P.target, P.target_over_mask, prevc};
-                for_each_power<0, Lay>(op);
-            }
-            // window in tile-local indices: a tile holds < 2^20 primes, so saturating to u32 is exact
+            // ---- every S_k(n) formed and compared.  Window bounds in tile-local indices (a tile holds < 2^20
+            //      primes, so saturating to u32 is exact): quota = primes this thread may process (<= n_max),
+            //      skip = primes of this thread still below n_min.
             const u32 lmin = (P.n_min > tile_n0) ? (u32)min(P.n_min - tile_n0, (u64)0xFFFFFFFFull) : 0u;
             const u32 lmax = (u32)min(P.n_max - tile_n0, (u64)0xFFFFFFFEull);   // n_max >= tile_n0 (checked above)
+            const u32 have = cnt;                                               // primes owned by this thread
+            const u32 quota = (li0 > lmax) ? 0u : min(have, lmax - li0 + 1u);
+            const u32 skip0 = (lmin > li0) ? min(lmin - li0, quota) : 0u;
+            const bool owns_nmax = quota > 0 && (tile_n0 + li0 + quota - 1 == P.n_max);
             constexpr int PMODE = (MODE == kBsTri) ? kModeTri : kModeCompare;
-            BsCmpFn<K, MULTI, PMODE> fn{{run, &P, prevc, mcount, mfirst, mlast, tile_n0, 0, 0, 0, false}, &P, tile_n0, li0, lmin, lmax};
-            bool go = true;
-            if (has_small)
-                for (u32 i = 0; i < P.n_small && go; ++i) go = fn((u32)P.small_primes[i], 0u);
-            if (go) walk_words(my_words, base_lo, base_hi, fn);
-            __syncwarp();
+            u32 n_in = 0, n_lt[NP], eq_li[NP];
+            u64 last_p = 0;
+            const bool any_skip = __any_sync(0xFFFFFFFFu, skip0 != 0);
+            auto run_walk = [&](auto& fn) {
 #pragma unroll
-            for (int jj = 0; jj < NP; ++jj) {
-                if (__any_sync(0xFFFFFFFFu, mcount[jj] != 0)) {
-                    const u32 c = __reduce_add_sync(0xFFFFFFFFu, mcount[jj]);
-                    const u32 f = __reduce_min_sync(0xFFFFFFFFu, mfirst[jj]);
-                    const u32 l = __reduce_max_sync(0xFFFFFFFFu, mlast[jj]);
-                    if (lane == 0) {
-                        pss_power_result* r = P.results + jj;
-                        atomicAdd(reinterpret_cast<unsigned long long*>(&r->match_count), (unsigned long long)c);
-                        atomicMin(reinterpret_cast<unsigned long long*>(&r->first_match_n), (unsigned long long)(tile_n0 + f));
-                        atomicMax(reinterpret_cast<unsigned long long*>(&r->last_match_n), (unsigned long long)(tile_n0 + l - 1));
+                for (int jj = 0; jj < NP; ++jj) {
+                    fn.n_lt[jj] = 0;
+                    fn.eq_li[jj] = 0xFFFFFFFFu;
+                    fn.below[jj] = false;
+                }
+                if constexpr (MODE == kBsCompare) {
+                    int c0[NP];
+                    OpCmpInit op{run, P.target, P.target_over_mask, c0};
+                    for_each_power<0, Lay>(op);
+#pragma unroll
+                    for (int jj = 0; jj < NP; ++jj) fn.below[jj] = (c0[jj] < 0);
+                }
+                if (quota > 0) {
+                    bool go = true;
+                    if (has_small)
+                        for (u32 i = 0; i < P.n_small && go; ++i) {
+                            last_p = P.small_primes[i];
+                            go = fn((u32)last_p, 0u);
+                        }
+                    if (go) last_p = walk_words(my_words, value_base, fn);
+                }
+                n_in = fn.n_in;
+#pragma unroll
+                for (int jj = 0; jj < NP; ++jj) {
+                    n_lt[jj] = fn.n_lt[jj];
+                    eq_li[jj] = fn.eq_li[jj];
+                }
+            };
+            if (any_skip) {
+                BsCmpFn<K, MULTI, PMODE, true> fn{run, &P, tile_n0, li0, quota, skip0, 0, {}, {}, {}, 0, 0};
+                run_walk(fn);
+            } else {
+                BsCmpFn<K, MULTI, PMODE, false> fn{run, &P, tile_n0, li0, quota, 0, 0, {}, {}, {}, 0, 0};
+                run_walk(fn);
+            }
+            if (owns_nmax) {   // exactly one thread in the grid: S(n_max) and p_{n_max}
+                *P.last_prime_out = last_p;
+#pragma unroll
+                for (int jj = 0; jj < NP; ++jj)
+#pragma unroll
+                    for (int i = 0; i < PSS_LIMBS; ++i)
+                        P.results[jj].final_sum[i] = (i < Lay::width(jj)) ? run[Lay::offset(jj) + i] : 0u;
+            }
+            __syncwarp();
+            if constexpr (MODE == kBsCompare) {
+                // matches of this thread: in-window indices [a, a + n_in); outcomes  < ... < [==] > ... >
+                const u32 a = li0 + skip0;
+#pragma unroll
+                for (int jj = 0; jj < NP; ++jj) {
+                    const u32 eq = (eq_li[jj] != 0xFFFFFFFFu) ? 1u : 0u;
+                    const u32 lt = n_lt[jj], gt = n_in - lt - eq;
+                    u32 mc = 0, mf = 0xFFFFFFFFu, ml = 0;   // count, first (tile-local), last + 1
+                    if (n_in) {
+                        const u32 m = P.cmp_mask;
+                        // contiguous runs: [a, a+lt) below, [a+lt, a+lt+eq) equal, [a+lt+eq, a+n_in) above
+                        if ((m & 1u) && lt) { mc += lt; mf = min(mf, a); ml = max(ml, a + lt); }
+                        if ((m & 2u) && eq) { mc += 1; mf = min(mf, a + lt); ml = max(ml, a + lt + 1); }
+                        if ((m & 4u) && gt) { mc += gt; mf = min(mf, a + lt + eq); ml = max(ml, a + n_in); }
+                    }
+                    if (__any_sync(0xFFFFFFFFu, mc != 0)) {
+                        const u32 c = __reduce_add_sync(0xFFFFFFFFu, mc);
+                        const u32 f = __reduce_min_sync(0xFFFFFFFFu, mf);
+                        const u32 l = __reduce_max_sync(0xFFFFFFFFu, ml);
+                        if (lane == 0) {
+                            pss_power_result* r = P.results + jj;
+                            atomicAdd(reinterpret_cast<unsigned long long*>(&r->match_count), (unsigned long long)c);
+                            atomicMin(reinterpret_cast<unsigned long long*>(&r->first_match_n), (unsigned long long)(tile_n0 + f));
+                            atomicMax(reinterpret_cast<unsigned long long*>(&r->last_match_n), (unsigned long long)(tile_n0 + l - 1));
+                        }
                     }
                 }
             }
