@@ -86,27 +86,30 @@ __device__ __forceinline__ u32 msb_index(u32 w) {   // FLO: index of the most si
 // f(plo, phi) -> false stops this lane.  Returns the last prime handed to f.
 template <class F>
 __device__ __forceinline__ u64 walk_words(const u32* my_words, u64 value_base, F& f) {
-    const u32* ptr = my_words;
-    const u32* const end = my_words + kWordsPerThread;   // sentinel slot (always 0)
-    u32 w = 0, woff = 0u - 120u;
-    u64 p = 0;
+    // 32-bit bookkeeping throughout: word index instead of a generic pointer, and the 64-bit value base split
+    // into two opaque registers (otherwise ptxas rematerialises "byte index * 30" inside the loop)
+    u32 base_lo = (u32)value_base, base_hi = (u32)(value_base >> 32);
+    asm volatile("" : "+r"(base_lo), "+r"(base_hi));
+    u32 wi = 0, w = 0, woff = 0u - 120u;
+    u32 plo = 0, phi = 0;
     bool alive = true;
     while (alive) {
         const bool need = (w == 0);
-        const u32 nw = *ptr;             // ptr <= end: inside this thread's padded row
+        const u32 nw = my_words[wi];     // wi <= kWordsPerThread: the sentinel slot of this thread's padded row
         w = need ? nw : w;
-        ptr += need ? 1 : 0;
+        wi += need ? 1u : 0u;
         woff += need ? 120u : 0u;
         if (w != 0) {
             const u32 m = msb_index(w);
             w ^= (1u << m);
-            p = value_base + (u64)(woff + msb_value_offset(m));
-            alive = f((u32)p, (u32)(p >> 32));
+            const u32 off = woff + msb_value_offset(m);
+            asm("add.cc.u32 %0, %2, %3;\n\taddc.u32 %1, %4, 0;" : "=r"(plo), "=r"(phi) : "r"(base_lo), "r"(off), "r"(base_hi));
+            alive = f(plo, phi);
         } else {
-            alive = (ptr <= end);        // empty word (rare): try the next one; sentinel: done
+            alive = (wi <= (u32)kWordsPerThread);   // empty word (rare): try the next one; sentinel: done
         }
     }
-    return p;
+    return ((u64)phi << 32) | plo;
 }
 
 template <int K, bool MULTI>
