@@ -62,7 +62,7 @@ struct pss_handle {
     u32 tile_bytes = 112 * 1024;   // 2 CTAs x 512 threads per SM (tools/tune_sieve.py, profiles/r01/tune_sieve_*.json)
     u32 sieve_threads = 512;
     u32 n_pat = 4;
-    u32 warp_wide_div = 512;    // p < tile_bytes / div -> one warp per prime, else 8 lanes per prime
+    u32 warp_wide_div = 128;    // p < tile_bytes / div -> dense (one warp per prime, skewed conflict-free lanes), else one lane per prime
     int search_path = 0;       // 0: fused (scan straight from the bitmap), 1: materialised u64 primes
 
     // patterns
@@ -250,10 +250,11 @@ int launch_sieve(pss_handle* h, const SieveParams& sp) {
         attr_set = true;
     }
     int occ = 1;
-    CU_TRY(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_sieve<THREADS>, THREADS, sp.tile_bytes));
+    const size_t smem = (size_t)sp.tile_bytes + kSieveScratchBytes;
+    CU_TRY(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_sieve<THREADS>, THREADS, smem));
     if (occ < 1) return fail(h, PSS_EINTERNAL, "sieve tile of %u bytes does not fit shared memory", sp.tile_bytes);
     const u32 grid = std::min<u32>(sp.n_tiles, (u32)(h->sm_count * occ));
-    k_sieve<THREADS><<<grid, THREADS, sp.tile_bytes, h->stream>>>(sp);
+    k_sieve<THREADS><<<grid, THREADS, smem, h->stream>>>(sp);
     CU_TRY(h, cudaGetLastError());
     h->launches++;
     return PSS_OK;

@@ -101,12 +101,19 @@ __device__ __forceinline__ u32 first_hit(u32 p, u32 c, u32 r, bool is_strand0, u
     return x;
 }
 
+// inverse of an odd p modulo 64 (one Newton step from x0 = p, which is already correct modulo 8)
+__device__ __forceinline__ u32 inv_mod64(u32 p) { return p * (2u - p * p); }
+
+// the sieve kernel's dynamic shared memory: the tile followed by a 128-byte scratch line (one word per bank) that
+// absorbs the cross-offs of lanes that are outside the tile in a given iteration (see the dense phase)
+constexpr u32 kSieveScratchBytes = 128;
+
 template <int THREADS>
 __global__ void __launch_bounds__(THREADS) k_sieve(const SieveParams P) {
     extern __shared__ uint4 smem4[];
-    u32* tile = reinterpret_cast<u32*>(smem4);
     __shared__ u64 s_off16[kMaxPatterns];
     __shared__ u32 s_cnt[THREADS / 32];
+    __shared__ u32 s_next;       // work queue of phase B (dense primes first, then batches of 32 sparse primes)
 
     const u32 tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
     constexpr u32 NW = THREADS / 32;
@@ -114,11 +121,15 @@ __global__ void __launch_bounds__(THREADS) k_sieve(const SieveParams P) {
     const u32 tile_vec = tile_bytes >> 4;
     const u32 chunks_per_tile = tile_bytes / kChunkBytes;
     const bool wide = P.wide_index != 0;
-    char* tile_b = reinterpret_cast<char*>(tile);
+    char* const tile_b = reinterpret_cast<char*>(smem4);
+    // AND-reduction on the tile byte offset `off` (multiple of 4).  Plain atomicAnd with the result unused compiles
+    // to ATOMS.AND RZ; unlike an asm volatile statement it leaves the enclosing regions reconvergent.
+    auto cross = [&](u32 off, u32 mask) { atomicAnd(reinterpret_cast<u32*>(tile_b + off), mask); };
 
     for (u32 t = blockIdx.x; t < P.n_tiles; t += gridDim.x) {
         const u64 B0 = P.B_start + (u64)t * tile_bytes;
         if (tid < P.n_pat) s_off16[tid] = (B0 % P.pat_period16[tid]) >> 4;
+        if (tid == 32) s_next = 0;
         __syncthreads();
 
         // ---- phase A: tile init from the pre-sieved patterns (L2-resident, aligned uint4 loads)
@@ -132,61 +143,97 @@ __global__ void __launch_bounds__(THREADS) k_sieve(const SieveParams P) {
         }
         __syncthreads();
 
+        // ---- phase B: cross-offs.  Warps pull work items from a shared-memory queue (largest items first):
+        //        items [0, n_dense)   one dense prime each (p < tile/128), whole warp, bank-conflict free
+        //        items [n_dense, ..)  batches of 32 consecutive sparse primes, one prime per lane
         const u32 nact = __ldg(P.tile_nact + t);
-        // ---- phase B2: dense primes, one warp per prime: lane -> (strand j, sub-sequence), stride 4p.
-        //      The stride is a multiple of 4 bytes, so the word-aligned address advances by a constant and
-        //      the bit mask is loop invariant.  The next prime's table entries are prefetched (L2 latency).
-        {
-            const u32 j = lane & 7u, sub = lane >> 3;
-            const u32 nw = min(P.n_warp_wide, nact);
-            u32 i = warp, p_n = 0, inv_n = 0, cb_n = 0;
-            if (i < nw) {
-                p_n = __ldg(P.base_p + i);
-                inv_n = __ldg(P.base_inv + i);
-                cb_n = __ldg(P.base_strand + i * 8u + j);
-            }
-            while (i < nw) {
-                const u32 p = p_n, inv = inv_n, cb = cb_n;
-                i += NW;
-                if (i < nw) {
-                    p_n = __ldg(P.base_p + i);
-                    inv_n = __ldg(P.base_inv + i);
-                    cb_n = __ldg(P.base_strand + i * 8u + j);
-                }
+        const u32 n_dense = min(P.n_warp_wide, nact);
+        const u32 n_items = n_dense + ((nact - n_dense + 31u) >> 5);
+        for (;;) {
+            u32 item = 0;
+            if (lane == 0) item = atomicAdd(&s_next, 1u);
+            item = __shfl_sync(0xFFFFFFFFu, item, 0);
+            if (item >= n_items) break;
+            if (item < n_dense) {
+                // dense prime: lane -> (strand j, sub-sequence s), word stride p (byte stride 4p), constant mask.
+                // Lane l delays its start by e_l iterations with (w_l - e_l p) = l (mod 32): at every iteration the
+                // 32 lanes then address the 32 different banks (l + it*p) mod 32 -- one wavefront per warp instruction.
+                const u32 j = lane & 7u, s = lane >> 3;
+                const u32 p = __ldg(P.base_p + item), inv = __ldg(P.base_inv + item);
+                const u32 cb = __ldg(P.base_strand + item * 8u + j);
                 const u32 r = tile_mod(B0, p, inv, wide);
-                u32 x = first_hit(p, cb & 0xFFFFFFu, r, j == 0, B0) + sub * p;
+                const u32 c = cb & 0xFFFFFFu;
+                const bool special = (j == 0) && (B0 <= (u64)c);      // q = 0 would be p itself: first hit is one period later
+                const u32 x = first_hit(p, c, r, j == 0, B0) + s * p;  // x < 4p unless special
                 const u32 mask = ~(1u << (((x & 3u) << 3) + (cb >> 24)));
-                const u32 stride = 4u * p;
-                for (u32 xa = x & ~3u; xa < tile_bytes; xa += stride)
-                    atomicAnd(reinterpret_cast<u32*>(tile_b + xa), mask);
-            }
-        }
-        // ---- phase B3: sparse primes, 8 lanes (one per strand) per prime, stride p (odd): the byte
-        //      position inside the word advances by p & 3, i.e. the mask rotates by a per-prime constant.
-        {
-            const u32 j = tid & 7u;
-            constexpr u32 NG = THREADS / 8;
-            u32 i = P.n_warp_wide + (tid >> 3), p_n = 0, inv_n = 0, cb_n = 0;
-            if (i < nact) {
-                p_n = __ldg(P.base_p + i);
-                inv_n = __ldg(P.base_inv + i);
-                cb_n = __ldg(P.base_strand + i * 8u + j);
-            }
-            while (i < nact) {
-                const u32 p = p_n, inv = inv_n, cb = cb_n;
-                i += NG;
-                if (i < nact) {
-                    p_n = __ldg(P.base_p + i);
-                    inv_n = __ldg(P.base_inv + i);
-                    cb_n = __ldg(P.base_strand + i * 8u + j);
+                const u32 w = x >> 2;
+                const u32 e = special ? 0u : (((w - lane) * inv_mod64(p)) & 31u);
+                // byte offset of the lane's word; "negative" while the lane is still waiting (w < p there, so it
+                // wraps far above tile_bytes)
+                u32 a = (w - e * p) << 2;
+                const u32 step = p << 2;
+                const u32 H = tile_bytes / step;          // every lane has at least H - 2 hits
+                const u32 n_it = 32u + H;                 // ... and at most H + 1, after a delay of at most 31
+                // a lane outside the tile ANDs into the scratch word of the bank it would have used: no branch, and the
+                // instruction stays one wavefront
+                auto guarded = [&]() {
+                    cross((a < tile_bytes) ? a : ((a & 127u) | tile_bytes), mask);
+                    a += step;
+                };
+                u32 it = 0;
+                for (; it < 31u; ++it) guarded();                       // staggered start
+                if (H > 33u) {                                          // steady state: all 32 lanes inside the tile
+#pragma unroll 4
+                    for (; it + 2u < H; ++it) {
+                        cross(a, mask);
+                        a += step;
+                    }
                 }
-                const u32 r = tile_mod(B0, p, inv, wide);
-                u32 x = first_hit(p, cb & 0xFFFFFFu, r, j == 0, B0);
-                u32 mask = ~(1u << (((x & 3u) << 3) + (cb >> 24)));
+                for (; it < n_it; ++it) guarded();                      // staggered end
+            } else {
+                // sparse primes: one prime per lane, its 8 strands one after the other; byte stride p (odd), so the
+                // byte position inside the word advances by p & 3: the mask rotates by a per-prime constant.
+                // Trip counts are warp-uniform (no votes, no divergence): every lane of the batch has at least
+                // n_uni = T / p_hi - 1 hits per strand and at most h_max = (T - 1) / p_lo + 1; the iterations in
+                // between are guarded by redirecting lanes that have left the tile to their scratch word.
+                const u32 first = n_dense + ((item - n_dense) << 5);
+                const u32 n_on = min(32u, nact - first);
+                const bool on = lane < n_on;
+                const u32 park = tile_bytes + 4u * lane;     // this lane's scratch word
+                u32 p = 0, inv = 0;
+                uint4 s0 = make_uint4(park, park, park, park), s1 = s0;   // idle lane: c = park, bit 0, p = 0: stays parked
+                if (on) {
+                    const u32 i = first + lane;
+                    p = __ldg(P.base_p + i);
+                    inv = __ldg(P.base_inv + i);
+                    s0 = __ldg(reinterpret_cast<const uint4*>(P.base_strand) + 2u * i);
+                    s1 = __ldg(reinterpret_cast<const uint4*>(P.base_strand) + 2u * i + 1u);
+                }
+                const u32 p_lo = __shfl_sync(0xFFFFFFFFu, p, 0);
+                const u32 p_hi = __shfl_sync(0xFFFFFFFFu, p, n_on - 1u);
+                const u32 U = tile_bytes / p_hi;
+                const u32 n_uni = (U > 1u) ? U - 1u : 0u;
+                const u32 n_rag = (tile_bytes - 1u) / p_lo + 1u - n_uni;
+                const u32 cbs[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
+                const u32 r = on ? tile_mod(B0, p, inv, wide) : 0u;
                 const u32 rot = (p & 3u) << 3;
-                for (; x < tile_bytes; x += p) {
-                    atomicAnd(reinterpret_cast<u32*>(tile_b + (x & ~3u)), mask);
-                    mask = __funnelshift_l(mask, mask, rot);
+#pragma unroll
+                for (u32 j = 0; j < 8; ++j) {
+                    const u32 cb = cbs[j];
+                    u32 x = first_hit(p, cb & 0xFFFFFFu, r, j == 0, B0);
+                    u32 mask = ~(1u << (((x & 3u) << 3) + (cb >> 24)));
+#pragma unroll 4
+                    for (u32 k = 0; k < n_uni; ++k) {
+                        cross(x & ~3u, mask);
+                        x += p;
+                        mask = __funnelshift_l(mask, mask, rot);
+                    }
+#pragma unroll 1
+                    for (u32 k = 0; k < n_rag; ++k) {
+                        cross((x < tile_bytes) ? (x & ~3u) : park, mask);
+                        x += p;
+                        mask = __funnelshift_l(mask, mask, rot);
+                    }
                 }
             }
         }
