@@ -64,6 +64,7 @@ struct pss_handle {
     u32 n_pat = 4;
     u32 warp_wide_div = 128;    // p < tile_bytes / div -> dense (one warp per prime, skewed conflict-free lanes), else one lane per prime
     int search_path = 0;       // 0: fused (scan straight from the bitmap), 1: materialised u64 primes
+    int reduce_moments = 1;    // k = 2 reduce pass from per-byte moment tables (0: walk every prime; PSS_REDUCE_MOMENTS)
 
     // patterns
     uint4* d_pat[kMaxPatterns] = {nullptr, nullptr, nullptr, nullptr};
@@ -642,7 +643,14 @@ int bitmap_reduce(pss_handle* h, u32 K, bool multi) {
     bp.col_prefix = static_cast<const u64*>(h->col_prefix.p);
     CU_TRY(h, cudaEventRecord(h->ev[4], h->stream));
     CU_TRY(h, cudaMemsetAsync(bp.cols, 0, (size_t)ncols * bp.col_stride * sizeof(u64), h->stream));
-    PSS_TRY(launch_bscan<kBsReduce>(h, bp, K, multi));
+    if (K == 2 && !multi && h->reduce_moments) {
+        const u32 grid = std::min<u32>(bp.n_tiles, (u32)(h->sm_count * 8));
+        k_bitmap_moments2<<<grid, kBsThreads, 0, h->stream>>>(bp);
+        CU_TRY(h, cudaGetLastError());
+        h->launches++;
+    } else {
+        PSS_TRY(launch_bscan<kBsReduce>(h, bp, K, multi));
+    }
     k_scan_columns<<<ncols, 1024, 0, h->stream>>>(bp.cols, static_cast<u64*>(h->col_prefix.p), bp.n_tiles, bp.col_stride);
     CU_TRY(h, cudaGetLastError());
     h->launches++;
@@ -811,6 +819,7 @@ int pss_open(int device, pss_handle** out) {
     h->n_pat = std::min<u32>(env_u32("PSS_NPAT", h->n_pat), kMaxPatterns);
     if (const char* sp_ = getenv("PSS_SEARCH_PATH")) h->search_path = (strcmp(sp_, "materialised") == 0 || strcmp(sp_, "materialized") == 0) ? 1 : 0;
     h->warp_wide_div = env_u32("PSS_WARP_WIDE_DIV", h->warp_wide_div);
+    h->reduce_moments = (int)env_u32("PSS_REDUCE_MOMENTS", (u32)h->reduce_moments);
     h->tile_bytes = std::max<u32>(8192, std::min<u32>((h->tile_bytes / kChunkBytes) * kChunkBytes, 216 * 1024));
     auto cleanup = [&](int rc) {
         pss_close(h);

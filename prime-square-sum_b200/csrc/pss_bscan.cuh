@@ -232,6 +232,33 @@ struct BsCmpFn {
     }
 };
 
+// Tail of the reduce pass, shared by the walking kernel and the moment kernel: per-thread record, exact warp totals
+// (butterfly of carry-propagating adds) -> warp record, deferred-carry u64 atomics -> scan-tile columns.
+template <int K, bool MULTI>
+__device__ __forceinline__ void bs_reduce_tail(const BScanParams& P, u32* acc, u32 cnt, u64 wt, u32 tile, u32 lane) {
+    using Lay = Layout<K, MULTI>;
+    constexpr int TOTAL = Lay::TOTAL;
+    const u64 gthread = wt * 32 + lane;
+    P.thread_rec[gthread] = cnt;
+#pragma unroll
+    for (int i = 0; i < TOTAL; ++i) P.thread_rec[(u64)(1 + i) * P.thread_stride + gthread] = acc[i];
+#pragma unroll
+    for (int d = 16; d >= 1; d >>= 1) {
+        OpShflXorAdd op{acc, d};
+        for_each_power<0, Lay>(op);
+    }
+    cnt = __reduce_add_sync(0xFFFFFFFFu, cnt);
+    if (lane == 0) {
+        P.warp_rec[wt] = cnt;
+        atomicAdd(reinterpret_cast<unsigned long long*>(P.cols + tile), (unsigned long long)cnt);
+#pragma unroll
+        for (int i = 0; i < TOTAL; ++i) {
+            P.warp_rec[(u64)(1 + i) * P.warp_stride + wt] = acc[i];
+            atomicAdd(reinterpret_cast<unsigned long long*>(P.cols + (u64)(1 + i) * P.col_stride + tile), (unsigned long long)acc[i]);
+        }
+    }
+}
+
 // Warp-autonomous kernel: a warp owns one "warp tile" = 32 threads x 24 words (768 words, 92 160 integers);
 // 8 consecutive warp tiles form a scan tile (the granularity of the column prefix).  No __syncthreads.
 // resident CTAs per SM the register allocation is bounded for (issue-bound kernel: occupancy hides the
@@ -296,26 +323,7 @@ __global__ void __launch_bounds__(kBsThreads, bs_min_blocks<K, MULTI>()) k_bitma
                 cnt += P.n_small;
             }
             walk_words(my_words, value_base, fn);
-            P.thread_rec[gthread] = cnt;
-#pragma unroll
-            for (int i = 0; i < TOTAL; ++i) P.thread_rec[(u64)(1 + i) * P.thread_stride + gthread] = acc[i];
-            // ---- warp totals (exact limbs) -> warp record; deferred-carry u64 atomics -> tile record
-#pragma unroll
-            for (int d = 16; d >= 1; d >>= 1) {
-                OpShflXorAdd op{acc, d};
-                for_each_power<0, Lay>(op);
-            }
-            cnt = __reduce_add_sync(0xFFFFFFFFu, cnt);
-            if (lane == 0) {
-                P.warp_rec[wt] = cnt;
-                atomicAdd(reinterpret_cast<unsigned long long*>(P.cols + tile), (unsigned long long)cnt);
-#pragma unroll
-                for (int i = 0; i < TOTAL; ++i) {
-                    P.warp_rec[(u64)(1 + i) * P.warp_stride + wt] = acc[i];
-                    atomicAdd(reinterpret_cast<unsigned long long*>(P.cols + (u64)(1 + i) * P.col_stride + tile),
-                              (unsigned long long)acc[i]);
-                }
-            }
+            bs_reduce_tail<K, MULTI>(P, acc, cnt, wt, tile, lane);
         } else {
             // ---- exclusive prefix of this thread = carry-in + tile prefix + earlier warps + earlier lanes
             cnt = __ldg(P.thread_rec + gthread);
@@ -468,6 +476,83 @@ __global__ void __launch_bounds__(kBsThreads, bs_min_blocks<K, MULTI>()) k_bitma
                 }
             }
         }
+    }
+}
+
+// ---- reduce pass for the sum of SQUARES without touching individual primes ---------------------------------------
+// A thread's 24 words cover the 2880 integers [B, B + 2880).  With o = p - B:
+//     sum p^2 = M0 * B^2 + 2 B * M1 + M2,      M0 = #primes, M1 = sum o, M2 = sum o^2        (exact)
+// and the moments come from a 256-entry byte table (count, sum r, sum r^2 of the wheel residues r of the set bits,
+// packed 6 + 10 + 14 bits so that four entries add without overflow) plus constant byte / word position weights.
+// ~32 instructions per 32-bit word (~5 primes) instead of ~48 per prime for decode + square + accumulate.  The output
+// (thread / warp records, scan-tile columns) is bit-identical to k_bitmap_scan<2, false, kBsReduce>.
+__global__ void __launch_bounds__(kBsThreads) k_bitmap_moments2(const __grid_constant__ BScanParams P) {
+    constexpr int NWARP = kBsThreads / 32, WPT = kWordsPerThread, WARP_WORDS = 32 * WPT;
+    __shared__ u32 s_lut[256];
+    {
+        const u32 v = threadIdx.x;     // kBsThreads == 256: one entry per thread
+        u32 n = 0, r1 = 0, r2 = 0;
+#pragma unroll
+        for (u32 j = 0; j < 8; ++j)
+            if ((v >> j) & 1u) {
+                const u32 r = wheel_residue(j);
+                n += 1u; r1 += r; r2 += r * r;
+            }
+        s_lut[v] = n | (r1 << 6) | (r2 << 16);
+    }
+    __syncthreads();
+    const u32 lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    const u64 n_warp_tiles = (u64)P.n_tiles * NWARP;
+    const u64 warp_stride = (u64)gridDim.x * NWARP;
+    for (u64 wt = (u64)blockIdx.x * NWARP + warp; wt < n_warp_tiles; wt += warp_stride) {
+        const u32 tile = (u32)(wt / NWARP);
+        const u64 word0 = wt * WARP_WORDS + (u64)lane * WPT;      // this thread's first word
+        const uint4* g4 = reinterpret_cast<const uint4*>(P.bitmap + word0);
+        uint4 v[WPT / 4];
+#pragma unroll
+        for (int q = 0; q < WPT / 4; ++q) {
+            v[q] = make_uint4(0, 0, 0, 0);
+            if (word0 + 4ull * q + 4 <= P.n_words) v[q] = __ldg(g4 + q);
+        }
+        u32 M0 = 0, M1 = 0;
+        u64 M2 = 0;
+#pragma unroll
+        for (int i = 0; i < WPT; ++i) {
+            const uint4 vv = v[i >> 2];
+            const u32 w = (i & 3) == 0 ? vv.x : (i & 3) == 1 ? vv.y : (i & 3) == 2 ? vv.z : vv.w;
+            const u32 e0 = s_lut[w & 255u], e1 = s_lut[(w >> 8) & 255u], e2 = s_lut[(w >> 16) & 255u], e3 = s_lut[w >> 24];
+            const u32 W = e0 + e1 + e2 + e3;                       // moments about each byte's own origin
+            const u32 V = e1 + 2u * e2 + 3u * e3;                  // byte-index weighted (count and sum r fields)
+            const u32 Q = (e1 & 63u) + 4u * (e2 & 63u) + 9u * (e3 & 63u);
+            const u32 m0 = W & 63u;
+            const u32 m1 = ((W >> 6) & 1023u) + 30u * (V & 63u);                     // about the word origin
+            const u32 m2 = (W >> 16) + 60u * ((V >> 6) & 1023u) + 900u * Q;
+            const u32 c = 120u * i;                                                  // word origin inside the thread's range
+            M0 += m0;
+            M1 += m1 + c * m0;
+            M2 += (u64)(m2 + 2u * c * m1 + c * c * m0);
+        }
+        // thread sum = M0 * B^2 + 2 B M1 + M2
+        const u64 B = (P.B_start + 4ull * word0) * 30ull;
+        const u32 blo = (u32)B, bhi = (u32)(B >> 32);
+        u32 acc[4] = {0, 0, 0, 0};
+        {
+            Big<2> b1;  b1.v[0] = blo;  b1.v[1] = bhi;
+            Big<3> b2;  big_mul_p<3, 2>(b2, b1, blo, bhi);
+            Big<4> t;   big_mul_p<4, 3>(t, b2, M0, 0u);
+            acc_add<0, 4, 4>(acc, t.v);
+            Big<2> m;   m.v[0] = 2u * M1;  m.v[1] = 0u;
+            Big<3> x;   big_mul_p<3, 2>(x, m, blo, bhi);
+            acc_add<0, 4, 3>(acc, x.v);
+            const u32 m2v[2] = {(u32)M2, (u32)(M2 >> 32)};
+            acc_add<0, 4, 2>(acc, m2v);
+        }
+        u32 cnt = M0;
+        if (wt == 0 && lane == 0 && P.n_small > 0) {
+            for (u32 i = 0; i < P.n_small; ++i) square_acc4(acc, (u32)P.small_primes[i], 0u);
+            cnt += P.n_small;
+        }
+        bs_reduce_tail<2, false>(P, acc, cnt, wt, tile, lane);
     }
 }
 

@@ -293,6 +293,27 @@ def test_fused_tile_boundaries(handle, orc):
         assert po.final_sum == sums[-1] and out.last_prime == int(primes[-1])
 
 
+def test_moment_reduce_matches_walk_and_oracle(orc):
+    """k = 2 reduce pass from the per-byte moment tables (default) against the per-prime walking reduce and the
+    oracle: slice counts and slice sums on ragged ranges (range edges inside a byte, below 7, around 2^32)"""
+    from pss_b200 import _lib
+    os.environ["PSS_REDUCE_MOMENTS"] = "0"
+    try:
+        h_walk = _lib.Handle(-1)
+    finally:
+        del os.environ["PSS_REDUCE_MOMENTS"]
+    h_mom = _lib.Handle(-1)
+    for lo, hi in [(0, 2), (0, 8), (0, 100), (3, 2881), (0, 3_000_000), (2879, 2 * 737280 + 17), (10 ** 9 + 7, 10 ** 9 + 4_000_001),
+                   (2 ** 32 - 10 ** 6, 2 ** 32 + 10 ** 6), (22_800_000_000, 22_801_763_490), (2 ** 39, 2 ** 39 + 3_000_000)]:
+        exp_p = orc.c_primes_range(lo, hi)
+        exp = orc.c_power_sums(exp_p, [2])
+        a = h_mom.slice_sieve_sums(lo, hi, 2, False)
+        b = h_walk.slice_sieve_sums(lo, hi, 2, False)
+        assert a == b == (len(exp_p), exp), (lo, hi)
+    h_walk.close()
+    h_mom.close()
+
+
 def test_fused_slices_compose(handle, orc):
     """fused multi-GPU decomposition on one device: slice_sieve_sums / slice_scan_bitmap with carries"""
     from pss_b200 import search
