@@ -145,6 +145,13 @@ int pss_search_tri(pss_handle* h, uint64_t n_min, uint64_t n_max, uint32_t power
  * 1 = materialised, K1c compacts u64 primes first (the layout generate_primes / slice_* serve). */
 int pss_set_search_path(pss_handle* h, int materialised);
 
+/* compare-pass strategy of the fused path.  0 (default) = interval pruning: S_k(n) is strictly increasing in n, so a
+ * block of consecutive primes whose exact sum interval (S_before, S_after] does not contain the target compares
+ * like its prefix; only the block that brackets the target (and the one holding n_max) is walked prime by prime.
+ * 1 = exhaustive: every prime is decoded, raised to the k-th power and every S_k(n) is formed and compared, as the
+ * reference's per-n loop does (utils/grammar.py:977-988).  Results are identical in both modes. */
+int pss_set_compare_mode(pss_handle* h, int exhaustive);
+
 /* fused slice API (multi-GPU phase A / B without a u64 prime buffer):
  * sieve [lo,hi) + per-tile sums; returns the slice's prime count and sum p^k per power record */
 int pss_slice_sieve_sums(pss_handle* h, uint64_t lo, uint64_t hi_excl, uint32_t power_max, uint32_t all_powers,

@@ -64,6 +64,7 @@ struct pss_handle {
     u32 n_pat = 4;
     u32 warp_wide_div = 128;    // p < tile_bytes / div -> dense (one warp per prime, skewed conflict-free lanes), else one lane per prime
     int search_path = 0;       // 0: fused (scan straight from the bitmap), 1: materialised u64 primes
+    int compare_exhaustive = 0;  // 1: the compare pass walks every prime; 0: interval pruning (PSS_COMPARE_EXHAUSTIVE / pss_set_compare_mode)
     int reduce_moments = 1;    // k = 2 reduce pass from per-byte moment tables (0: walk every prime; PSS_REDUCE_MOMENTS)
 
     // patterns
@@ -723,6 +724,7 @@ int bitmap_compare(pss_handle* h, u64 n_first, const u32* carry_in, const pss_se
         bp.n_min = a->n_min;
         bp.n_max = a->n_max;
         bp.cmp_mask = kMasks[a->cmp];
+        bp.exhaustive = h->compare_exhaustive ? 1u : 0u;
         for (u32 i = 0; i < a->target_nlimbs && i < PSS_LIMBS; ++i) bp.target[i] = a->target[i];
         for (u32 j = 0; j < np; ++j) {
             const u32 w = (u32)sum_limbs((int)expo_of(K, multi, j));
@@ -820,6 +822,7 @@ int pss_open(int device, pss_handle** out) {
     if (const char* sp_ = getenv("PSS_SEARCH_PATH")) h->search_path = (strcmp(sp_, "materialised") == 0 || strcmp(sp_, "materialized") == 0) ? 1 : 0;
     h->warp_wide_div = env_u32("PSS_WARP_WIDE_DIV", h->warp_wide_div);
     h->reduce_moments = (int)env_u32("PSS_REDUCE_MOMENTS", (u32)h->reduce_moments);
+    h->compare_exhaustive = (int)env_u32("PSS_COMPARE_EXHAUSTIVE", (u32)h->compare_exhaustive);
     h->tile_bytes = std::max<u32>(8192, std::min<u32>((h->tile_bytes / kChunkBytes) * kChunkBytes, 216 * 1024));
     auto cleanup = [&](int rc) {
         pss_close(h);
@@ -1075,6 +1078,7 @@ int pss_search_tri(pss_handle* h, uint64_t n_min, uint64_t n_max, uint32_t power
         bp.results = dm->results;
         bp.last_prime_out = &dm->last_prime;
         bp.error_flag = &dm->error_flag;
+        bp.exhaustive = h->compare_exhaustive ? 1u : 0u;
         bp.tri_m_min = std::max<u64>(m_min, 1);
         bp.tri_m_max = m_max;
         bp.tri_max_value = m_max * (m_max + 1) / 2;
@@ -1095,6 +1099,12 @@ int pss_search_tri(pss_handle* h, uint64_t n_min, uint64_t n_max, uint32_t power
         if (n_copy) CU_TRY(h, cudaMemcpy(pairs_out, h->tri_buf.p, (size_t)n_copy * 2 * sizeof(u64), cudaMemcpyDeviceToHost));
     }
     if (stats) fill_stats(h, stats, before);
+    return PSS_OK;
+}
+
+int pss_set_compare_mode(pss_handle* h, int exhaustive) {
+    PSS_TRY(check_handle(h));
+    h->compare_exhaustive = exhaustive ? 1 : 0;
     return PSS_OK;
 }
 

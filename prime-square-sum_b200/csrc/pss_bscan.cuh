@@ -47,6 +47,8 @@ struct BScanParams {
     u64 n_first;             // global 1-based index of the slice's first prime
     u64 n_min, n_max;
     u32 cmp_mask, target_over_mask;
+    u32 exhaustive;          // 1: walk every prime and form every S_k(n); 0: prune warp tiles / threads whose sum interval
+                             // (S_before, S_after] cannot contain the target (identical results: S is strictly increasing)
     u32 target[PSS_LIMBS];
     const u32* carry_in;     // NP * PSS_LIMBS limbs (device)
     pss_power_result* results;
@@ -291,19 +293,21 @@ __global__ void __launch_bounds__(kBsThreads, bs_min_blocks<K, MULTI>()) k_bitma
         }
         const u64 word0 = wt * WARP_WORDS;
         // ---- warp-local staging: coalesced uint4 loads -> padded blocked layout, bit-reversed
-        const uint4* g4 = reinterpret_cast<const uint4*>(P.bitmap + word0);
-        __syncwarp();
+        auto stage = [&]() {
+            const uint4* g4 = reinterpret_cast<const uint4*>(P.bitmap + word0);
+            __syncwarp();
 #pragma unroll
-        for (int r = 0; r < WPT / 4; ++r) {
-            const u32 q = r * 32 + lane;          // uint4 index inside the warp tile
-            uint4 v = make_uint4(0, 0, 0, 0);
-            if (word0 + 4ull * q + 4 <= P.n_words) v = __ldg(g4 + q);
-            const u32 wl = 4u * q;                // first word (warp-tile local); 4 | WPT so one owner thread
-            const u32 dst = (wl / WPT) * PAD + (wl % WPT);
-            my_warp_words[dst] = __brev(v.x); my_warp_words[dst + 1] = __brev(v.y);
-            my_warp_words[dst + 2] = __brev(v.z); my_warp_words[dst + 3] = __brev(v.w);
-        }
-        __syncwarp();
+            for (int r = 0; r < WPT / 4; ++r) {
+                const u32 q = r * 32 + lane;          // uint4 index inside the warp tile
+                uint4 v = make_uint4(0, 0, 0, 0);
+                if (word0 + 4ull * q + 4 <= P.n_words) v = __ldg(g4 + q);
+                const u32 wl = 4u * q;                // first word (warp-tile local); 4 | WPT so one owner thread
+                const u32 dst = (wl / WPT) * PAD + (wl % WPT);
+                my_warp_words[dst] = __brev(v.x); my_warp_words[dst + 1] = __brev(v.y);
+                my_warp_words[dst + 2] = __brev(v.z); my_warp_words[dst + 3] = __brev(v.w);
+            }
+            __syncwarp();
+        };
 
         const u64 value_base = (P.B_start + 4ull * (word0 + (u64)lane * WPT)) * 30ull;
         const bool has_small = (wt == 0 && lane == 0 && P.n_small > 0);
@@ -312,6 +316,7 @@ __global__ void __launch_bounds__(kBsThreads, bs_min_blocks<K, MULTI>()) k_bitma
         u32 acc[TOTAL];
         u32 cnt = 0;
         if constexpr (MODE == kBsReduce) {
+            stage();
             // ---- thread-local count and sums
 #pragma unroll
             for (int i = 0; i < TOTAL; ++i) acc[i] = 0;
@@ -325,27 +330,25 @@ __global__ void __launch_bounds__(kBsThreads, bs_min_blocks<K, MULTI>()) k_bitma
             walk_words(my_words, value_base, fn);
             bs_reduce_tail<K, MULTI>(P, acc, cnt, wt, tile, lane);
         } else {
-            // ---- exclusive prefix of this thread = carry-in + tile prefix + earlier warps + earlier lanes
-            cnt = __ldg(P.thread_rec + gthread);
-#pragma unroll
-            for (int i = 0; i < TOTAL; ++i) acc[i] = __ldg(P.thread_rec + (u64)(1 + i) * P.thread_stride + gthread);
-            u32 cinc = cnt;
-#pragma unroll
-            for (int d = 1; d < 32; d <<= 1) {
-                OpShflUpAdd op{acc, d, lane >= (u32)d};
-                for_each_power<0, Lay>(op);
-                const u32 o = __shfl_up_sync(0xFFFFFFFFu, cinc, d);
-                if (lane >= (u32)d) cinc += o;
-            }
-            u32 run[TOTAL];
-#pragma unroll
-            for (int i = 0; i < TOTAL; ++i) {
-                const u32 up = __shfl_up_sync(0xFFFFFFFFu, acc[i], 1);
-                run[i] = lane ? up : 0u;
-            }
-            u32 li0 = cinc - cnt;
-            // earlier warps of this scan tile: lane l < wit fetches warp record l, butterfly sum
+            // ---- warp prefix (uniform) = carry-in + normalised deferred-carry tile prefix + earlier warps of the scan tile
+            u32 wpre[TOTAL];
+            u32 wli0 = 0;                // tile-local index of the warp's first prime
             {
+#pragma unroll
+                for (int jj = 0; jj < NP; ++jj) {
+                    u64 c = 0;
+#pragma unroll
+                    for (int i = 0; i < PSS_LIMBS; ++i) {
+                        if (i < Lay::width(jj)) {
+                            const int col = 1 + Lay::offset(jj) + i;
+                            const u64 v = P.col_prefix[(u64)col * P.col_stride + tile];
+                            const u64 lo = (v & 0xFFFFFFFFull) + (c & 0xFFFFFFFFull) + P.carry_in[jj * PSS_LIMBS + i];
+                            wpre[Lay::offset(jj) + i] = (u32)lo;
+                            c = (v >> 32) + (c >> 32) + (lo >> 32);
+                        }
+                    }
+                }
+                // earlier warps of this scan tile: lane l < wit fetches warp record l, butterfly sum
                 u32 v[TOTAL];
                 u32 c = 0;
                 const u64 wrec = (u64)tile * NWARP + lane;
@@ -362,94 +365,184 @@ __global__ void __launch_bounds__(kBsThreads, bs_min_blocks<K, MULTI>()) k_bitma
                 c += __shfl_xor_sync(0xFFFFFFFFu, c, 1);
 #pragma unroll
                 for (int i = 0; i < TOTAL; ++i) v[i] = __shfl_sync(0xFFFFFFFFu, v[i], 0);
-                c = __shfl_sync(0xFFFFFFFFu, c, 0);
-                OpAdd op{run, v};
-                for_each_power<0, Lay>(op);
-                li0 += c;
-            }
-            // tile prefix = carry-in + normalised deferred-carry column prefixes (uniform across the warp)
-            {
-                u32 ex[TOTAL];
-#pragma unroll
-                for (int jj = 0; jj < NP; ++jj) {
-                    u64 c = 0;
-#pragma unroll
-                    for (int i = 0; i < PSS_LIMBS; ++i) {
-                        if (i < Lay::width(jj)) {
-                            const int col = 1 + Lay::offset(jj) + i;
-                            const u64 v = P.col_prefix[(u64)col * P.col_stride + tile];
-                            const u64 lo = (v & 0xFFFFFFFFull) + (c & 0xFFFFFFFFull) + P.carry_in[jj * PSS_LIMBS + i];
-                            ex[Lay::offset(jj) + i] = (u32)lo;
-                            c = (v >> 32) + (c >> 32) + (lo >> 32);
-                        }
-                    }
-                }
-                OpAdd op{run, ex};
+                wli0 = __shfl_sync(0xFFFFFFFFu, c, 0);
+                OpAdd op{wpre, v};
                 for_each_power<0, Lay>(op);
             }
             const u64 tile_n0 = P.n_first + P.col_prefix[tile];
-            // ---- every S_k(n) formed and compared.  Window bounds in tile-local indices (a tile holds < 2^20
-            //      primes, so saturating to u32 is exact): quota = primes this thread may process (<= n_max),
-            //      skip = primes of this thread still below n_min.
+            // window bounds in tile-local indices (a tile holds < 2^20 primes, so saturating to u32 is exact)
             const u32 lmin = (P.n_min > tile_n0) ? (u32)min(P.n_min - tile_n0, (u64)0xFFFFFFFFull) : 0u;
             const u32 lmax = (u32)min(P.n_max - tile_n0, (u64)0xFFFFFFFEull);   // n_max >= tile_n0 (checked above)
-            const u32 have = cnt;                                               // primes owned by this thread
-            const u32 quota = (li0 > lmax) ? 0u : min(have, lmax - li0 + 1u);
-            const u32 skip0 = (lmin > li0) ? min(lmin - li0, quota) : 0u;
-            const bool owns_nmax = quota > 0 && (tile_n0 + li0 + quota - 1 == P.n_max);
             constexpr int PMODE = (MODE == kBsTri) ? kModeTri : kModeCompare;
-            u32 n_in = 0, n_lt[NP], eq_li[NP];
-            u64 last_p = 0;
-            const bool any_skip = __any_sync(0xFFFFFFFFu, skip0 != 0);
-            auto run_walk = [&](auto& fn) {
+
+            // per-lane outcome of this warp tile: in-window indices [a, a + n_in), of which n_lt below the target and
+            // eq_li the (tile-local) index of an exact hit.  S is strictly increasing, so inside any run of consecutive
+            // primes the outcomes are  < ... < [==] > ... >.
+            u32 a = 0, n_in = 0, n_lt[NP], eq_li[NP];
 #pragma unroll
-                for (int jj = 0; jj < NP; ++jj) {
-                    fn.n_lt[jj] = 0;
-                    fn.eq_li[jj] = 0xFFFFFFFFu;
-                    fn.below[jj] = false;
-                }
+            for (int jj = 0; jj < NP; ++jj) {
+                n_lt[jj] = 0;
+                eq_li[jj] = 0xFFFFFFFFu;
+            }
+
+            // ---- interval pruning, warp level.  If the warp tile lies entirely inside (or outside) the window, does
+            //      not hold n_max, and the target is not inside (S_before, S_after] of the warp tile for any power, every
+            //      partial sum of the tile compares like its prefix: no prime of it has to be touched.
+            bool warp_done = false;
+            if (!P.exhaustive) {
+                const u32 wcnt = __ldg(P.warp_rec + wt);
+                const u32 wquota = (wli0 > lmax) ? 0u : min(wcnt, lmax - wli0 + 1u);
+                const u32 wskip = (lmin > wli0) ? min(lmin - wli0, wquota) : 0u;
+                const bool holds_nmax = wquota > 0 && (tile_n0 + wli0 + wquota - 1 == P.n_max);
+                bool simple = !holds_nmax && (wskip == 0 || wskip == wquota);
                 if constexpr (MODE == kBsCompare) {
-                    int c0[NP];
+                    if (simple) {
+                        u32 wend[TOTAL];
+#pragma unroll
+                        for (int i = 0; i < TOTAL; ++i) wend[i] = wpre[i];
+                        u32 wsum[TOTAL];
+#pragma unroll
+                        for (int i = 0; i < TOTAL; ++i) wsum[i] = __ldg(P.warp_rec + (u64)(1 + i) * P.warp_stride + wt);
+                        OpAdd op{wend, wsum};
+                        for_each_power<0, Lay>(op);
+                        int c0[NP], c1[NP];
+                        OpCmpInit o0{wpre, P.target, P.target_over_mask, c0};
+                        for_each_power<0, Lay>(o0);
+                        OpCmpInit o1{wend, P.target, P.target_over_mask, c1};
+                        for_each_power<0, Lay>(o1);
+#pragma unroll
+                        for (int jj = 0; jj < NP; ++jj) simple = simple && !(c0[jj] < 0 && c1[jj] >= 0);
+                        if (simple) {
+                            warp_done = true;
+                            if (lane == 0) {
+                                a = wli0 + wskip;
+                                n_in = wquota - wskip;
+#pragma unroll
+                                for (int jj = 0; jj < NP; ++jj) n_lt[jj] = (c0[jj] < 0) ? n_in : 0u;
+                            }
+                        }
+                    }
+                } else {
+                    // triangular predicate: only sums <= tri(m_max) (< 2^59) can match; S grows monotonically
+                    bool beyond = false;
+#pragma unroll
+                    for (int i = 2; i < Lay::width(0); ++i) beyond = beyond || (wpre[i] != 0u);
+                    beyond = beyond || ((((u64)wpre[1] << 32) | wpre[0]) > P.tri_max_value);
+                    if (simple && beyond) warp_done = true;
+                }
+            }
+
+            if (!warp_done) {
+                // ---- thread level: exclusive prefix of this thread = warp prefix + earlier lanes
+                cnt = __ldg(P.thread_rec + gthread);
+                u32 own[TOTAL];
+#pragma unroll
+                for (int i = 0; i < TOTAL; ++i) own[i] = acc[i] = __ldg(P.thread_rec + (u64)(1 + i) * P.thread_stride + gthread);
+                u32 cinc = cnt;
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) {
+                    OpShflUpAdd op{acc, d, lane >= (u32)d};
+                    for_each_power<0, Lay>(op);
+                    const u32 o = __shfl_up_sync(0xFFFFFFFFu, cinc, d);
+                    if (lane >= (u32)d) cinc += o;
+                }
+                u32 run[TOTAL];
+#pragma unroll
+                for (int i = 0; i < TOTAL; ++i) {
+                    const u32 up = __shfl_up_sync(0xFFFFFFFFu, acc[i], 1);
+                    run[i] = lane ? up : 0u;
+                }
+                {
+                    OpAdd op{run, wpre};
+                    for_each_power<0, Lay>(op);
+                }
+                const u32 li0 = wli0 + cinc - cnt;
+                // quota = primes this thread may process (<= n_max), skip = primes of this thread still below n_min
+                const u32 have = cnt;
+                const u32 quota = (li0 > lmax) ? 0u : min(have, lmax - li0 + 1u);
+                const u32 skip0 = (lmin > li0) ? min(lmin - li0, quota) : 0u;
+                const bool owns_nmax = quota > 0 && (tile_n0 + li0 + quota - 1 == P.n_max);
+                int c0[NP];
+#pragma unroll
+                for (int jj = 0; jj < NP; ++jj) c0[jj] = 0;
+                if constexpr (MODE == kBsCompare) {
                     OpCmpInit op{run, P.target, P.target_over_mask, c0};
                     for_each_power<0, Lay>(op);
-#pragma unroll
-                    for (int jj = 0; jj < NP; ++jj) fn.below[jj] = (c0[jj] < 0);
                 }
-                if (quota > 0) {
-                    bool go = true;
-                    if (has_small)
-                        for (u32 i = 0; i < P.n_small && go; ++i) {
-                            last_p = P.small_primes[i];
-                            go = fn((u32)last_p, 0u);
+                // ---- interval pruning, thread level (same argument on the thread's 2880 integers)
+                bool walk = quota > 0;
+                if (!P.exhaustive && walk && !owns_nmax && (skip0 == 0 || skip0 == quota)) {
+                    if constexpr (MODE == kBsCompare) {
+                        u32 end[TOTAL];
+#pragma unroll
+                        for (int i = 0; i < TOTAL; ++i) end[i] = run[i];
+                        OpAdd op{end, own};
+                        for_each_power<0, Lay>(op);
+                        int c1[NP];
+                        OpCmpInit o1{end, P.target, P.target_over_mask, c1};
+                        for_each_power<0, Lay>(o1);
+                        bool bracket = false;
+#pragma unroll
+                        for (int jj = 0; jj < NP; ++jj) bracket = bracket || (c0[jj] < 0 && c1[jj] >= 0);
+                        walk = bracket;
+                    } else {
+                        bool beyond = false;
+#pragma unroll
+                        for (int i = 2; i < Lay::width(0); ++i) beyond = beyond || (run[i] != 0u);
+                        beyond = beyond || ((((u64)run[1] << 32) | run[0]) > P.tri_max_value);
+                        walk = !beyond;
+                    }
+                }
+                a = li0 + skip0;
+                u64 last_p = 0;
+                if (__any_sync(0xFFFFFFFFu, walk)) stage();   // the bitmap is only read where a walk is needed
+                if (walk) {
+                    // ---- every S_k(n) of this thread formed and compared
+                    auto run_walk = [&](auto& fn) {
+#pragma unroll
+                        for (int jj = 0; jj < NP; ++jj) {
+                            fn.n_lt[jj] = 0;
+                            fn.eq_li[jj] = 0xFFFFFFFFu;
+                            fn.below[jj] = (MODE == kBsCompare) ? (c0[jj] < 0) : false;
                         }
-                    if (go) last_p = walk_words(my_words, value_base, fn);
+                        bool go = true;
+                        if (has_small)
+                            for (u32 i = 0; i < P.n_small && go; ++i) {
+                                last_p = P.small_primes[i];
+                                go = fn((u32)last_p, 0u);
+                            }
+                        if (go) last_p = walk_words(my_words, value_base, fn);
+                        n_in = fn.n_in;
+#pragma unroll
+                        for (int jj = 0; jj < NP; ++jj) {
+                            n_lt[jj] = fn.n_lt[jj];
+                            eq_li[jj] = fn.eq_li[jj];
+                        }
+                    };
+                    if (skip0 != 0) {
+                        BsCmpFn<K, MULTI, PMODE, true> fn{run, &P, tile_n0, li0, quota, skip0, 0, {}, {}, {}, 0, 0};
+                        run_walk(fn);
+                    } else {
+                        BsCmpFn<K, MULTI, PMODE, false> fn{run, &P, tile_n0, li0, quota, 0, 0, {}, {}, {}, 0, 0};
+                        run_walk(fn);
+                    }
+                    if (owns_nmax) {   // exactly one thread in the grid: S(n_max) and p_{n_max}
+                        *P.last_prime_out = last_p;
+#pragma unroll
+                        for (int jj = 0; jj < NP; ++jj)
+#pragma unroll
+                            for (int i = 0; i < PSS_LIMBS; ++i)
+                                P.results[jj].final_sum[i] = (i < Lay::width(jj)) ? run[Lay::offset(jj) + i] : 0u;
+                    }
+                } else if (quota > 0) {
+                    n_in = quota - skip0;
+#pragma unroll
+                    for (int jj = 0; jj < NP; ++jj) n_lt[jj] = (c0[jj] < 0) ? n_in : 0u;
                 }
-                n_in = fn.n_in;
-#pragma unroll
-                for (int jj = 0; jj < NP; ++jj) {
-                    n_lt[jj] = fn.n_lt[jj];
-                    eq_li[jj] = fn.eq_li[jj];
-                }
-            };
-            if (any_skip) {
-                BsCmpFn<K, MULTI, PMODE, true> fn{run, &P, tile_n0, li0, quota, skip0, 0, {}, {}, {}, 0, 0};
-                run_walk(fn);
-            } else {
-                BsCmpFn<K, MULTI, PMODE, false> fn{run, &P, tile_n0, li0, quota, 0, 0, {}, {}, {}, 0, 0};
-                run_walk(fn);
-            }
-            if (owns_nmax) {   // exactly one thread in the grid: S(n_max) and p_{n_max}
-                *P.last_prime_out = last_p;
-#pragma unroll
-                for (int jj = 0; jj < NP; ++jj)
-#pragma unroll
-                    for (int i = 0; i < PSS_LIMBS; ++i)
-                        P.results[jj].final_sum[i] = (i < Lay::width(jj)) ? run[Lay::offset(jj) + i] : 0u;
             }
             __syncwarp();
             if constexpr (MODE == kBsCompare) {
-                // matches of this thread: in-window indices [a, a + n_in); outcomes  < ... < [==] > ... >
-                const u32 a = li0 + skip0;
+                // matches: in-window indices [a, a + n_in); outcomes  < ... < [==] > ... >
 #pragma unroll
                 for (int jj = 0; jj < NP; ++jj) {
                     const u32 eq = (eq_li[jj] != 0xFFFFFFFFu) ? 1u : 0u;

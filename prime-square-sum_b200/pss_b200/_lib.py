@@ -66,6 +66,7 @@ EXPORTS = [
     "pss_slice_sieve", "pss_slice_reduce", "pss_slice_scan", "pss_slice_prefix_sums", "pss_slice_primes",
     "pss_slice_device_buffer", "pss_nth_prime_upper", "pss_stats_reset", "pss_stats_get",
     "pss_set_search_path", "pss_slice_sieve_sums", "pss_slice_scan_bitmap", "pss_search_tri",
+    "pss_set_compare_mode",
 ]
 
 _cdll = None
@@ -106,6 +107,7 @@ def load_library() -> ctypes.CDLL:
     L.pss_slice_device_buffer.argtypes = [H, ctypes.POINTER(ctypes.c_void_p), pu64]
     L.pss_search_tri.argtypes = [H, u64, u64, u32, u64, u64, pu64, u32, pu32, ctypes.POINTER(Stats)]
     L.pss_set_search_path.argtypes = [H, ctypes.c_int]
+    L.pss_set_compare_mode.argtypes = [H, ctypes.c_int]
     L.pss_slice_sieve_sums.argtypes = [H, u64, u64, u32, u32, pu64, pu32]
     L.pss_slice_scan_bitmap.argtypes = [H, u64, pu32, ctypes.POINTER(SearchArgs), ctypes.POINTER(SearchResult)]
     L.pss_stats_reset.argtypes = [H]
@@ -318,6 +320,10 @@ class Handle:
 
     def set_search_path(self, materialised: bool):
         self._check(self._L.pss_set_search_path(self._h, 1 if materialised else 0))
+
+    def set_compare_mode(self, exhaustive: bool):
+        """fused compare pass: False (default) = interval pruning, True = walk every prime / form every S_k(n)"""
+        self._check(self._L.pss_set_compare_mode(self._h, 1 if exhaustive else 0))
 
     def slice_sieve_sums(self, lo: int, hi_excl: int, power_max: int, all_powers: bool = False):
         """fused phase A: (count, [sum p^k per power record]) of the primes in [lo, hi)"""

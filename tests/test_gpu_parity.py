@@ -139,12 +139,15 @@ def test_every_partial_sum(handle, orc, golden):
 
 
 # ------------------------------------------------------------------------------- K3 scan + compare
-@pytest.fixture(params=["fused", "materialised"])
+@pytest.fixture(params=["fused", "fused-exhaustive", "materialised"])
 def search_path(request, handle):
-    """both query paths: fused (K2/K3 read the sieve bitmap) and materialised (K1c u64 primes + look-back scan)"""
+    """every query path: fused (K2/K3 read the sieve bitmap) with interval pruning (default) and with the exhaustive
+    per-prime compare, and materialised (K1c u64 primes + look-back scan)"""
     handle.set_search_path(request.param == "materialised")
+    handle.set_compare_mode(request.param == "fused-exhaustive")
     yield request.param
     handle.set_search_path(False)
+    handle.set_compare_mode(False)
 
 
 def test_find_matches_golden(handle, golden, search_path):
