@@ -5,13 +5,19 @@ bench.py — headline benchmark of the hot path (BASELINE.json metric):
 
 A "step" is one complete pass of the hot path over the workload
     C3:  does_exist primesum(n,2) == trisum(666), n in [1, 1e9]        (BASELINE.json configs[2])
-i.e. sieve [0, 2.28e10) -> compaction of the first 1e9 primes -> exact p^2 -> decoupled look-back scan ->
-compare of every partial sum with the 325-bit target.  Inputs are only the query parameters: nothing is
-pre-computed or cached between steps (the bitmap and prime buffers are rewritten every step; both are far
-larger than L2).
+i.e. sieve [0, 2.28e10) into the wheel-30 bitmap -> exact sums of p^2 per 2880-integer block, warp tile and scan
+tile -> grid-level prefix scan -> compare against the 325-bit target (the block whose exact sum interval brackets
+the target and the block holding n_max are walked prime by prime; every other block compares like its prefix
+because S(n) is strictly increasing) -> match / bracket record.  Inputs are only the query parameters: nothing
+is pre-computed or cached between steps (bitmap and block records are rewritten every step; both are far
+larger than L2).  The same step with the EXHAUSTIVE compare (every prime decoded and squared, every S(n)
+formed and compared: pss_set_compare_mode(1)) is timed after the headline loop and reported under
+"exhaustive_compare".
 
-  value      primes / device time (CUDA events on the library's launch stream, summed over the step's
-             kernels, max over ranks), inputs resident.
+  value      primes / device time: CUDA events on the library's launch stream from the first launch to the end
+             of the last kernel of each query (gaps between kernels included) at N = 1; at N > 1 the two device
+             phases are separated by the host-side exchange, so the per-kernel event times are summed;
+             max over ranks, inputs resident.
   e2e        the same metric through the public Python API (ctypes -> C ABI with host buffers): wall clock
              around K calls, barrier + synchronize on both sides, max over ranks.
   roofline   dominant kernel vs the measured HBM copy bandwidth (MEASURED_PEAKS.json), plus the kernel-local
@@ -207,7 +213,9 @@ def workload_config(name, gpus):
                     f"n in [{w['n_min']}, {w['n_max']}] (sieve [0, {w['p_n'] + 1}), {w['n_max']} primes)",
         "n_max": w["n_max"], "power": w["power"], "all_powers": w["all_powers"],
         "partition": f"value range split into {gpus} li(x)-balanced slices" if gpus > 1 else "single slice",
-        "l2": "inputs larger than L2 (bitmap 760 MB + primes 8 GB rewritten every step; no flush needed)",
+        "l2": "working set larger than L2 (bitmap 760 MB + 170 MB of block records rewritten every step; no flush needed)",
+        "compare": "interval pruning (exact: S_k(n) strictly increasing); the exhaustive per-prime compare is timed "
+                   "separately under exhaustive_compare",
     }
 
 
@@ -220,6 +228,7 @@ def main():
     ap.add_argument("--workload", default="C3", choices=sorted(WORKLOADS))
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-exhaustive", action="store_true", help="skip the extra steps with the exhaustive compare")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "b200":
         args.warmup = 3   # timing rule: at least 3 warm-up steps (allocations, pattern build, clocks)
@@ -273,24 +282,49 @@ def main():
     kern = {"ms_sieve": 0.0, "ms_count_scan": 0.0, "ms_compact": 0.0, "ms_power_scan": 0.0, "ms_bitmap_reduce": 0.0,
             "ms_bitmap_compare": 0.0}
     launches = 0
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        h.stats_reset()
-        out = step()
-        s = h.stats()
-        per_step_dev.append(s["ms_total_device"])
-        for k in kern:
-            kern[k] += s[k]
-        launches += s["launches"]
-    barrier()
-    wall = time.perf_counter() - t0
+
+    def timed_steps(n_steps, collect):
+        dev = []
+        barrier()
+        t_start = time.perf_counter()
+        for _ in range(n_steps):
+            h.stats_reset()
+            o = step()
+            s = h.stats()
+            # N = 1: whole-query span on the launch stream (gaps included); N > 1: sum of the kernels' event times
+            dev.append(s["ms_span"] if (world == 1 and s.get("ms_span", 0.0) > 0.0) else s["ms_total_device"])
+            if collect is not None:
+                for k in kern:
+                    collect[k] += s[k]
+                collect["launches"] = collect.get("launches", 0) + s["launches"]
+        barrier()
+        return dev, time.perf_counter() - t_start, o
+
+    acc = dict(kern)
+    per_step_dev, wall, out = timed_steps(args.steps, acc)
+    launches = acc.pop("launches", 0)
+    kern = acc
     clocks = sampler.stop() if rank == 0 else None
+    # the same steps with the exhaustive per-prime compare (outside the headline timed region)
+    exhaustive = None
+    if not args.no_exhaustive:
+        h.set_compare_mode(True)
+        try:
+            step()
+            ex_acc = dict.fromkeys(kern, 0.0)
+            ex_dev, ex_wall, ex_out = timed_steps(args.steps, ex_acc)
+            assert ex_out.first() is None and ex_out.last_prime == w["p_n"]
+            for po in ex_out.powers:
+                assert po.final_sum == w["sums"][po.power], f"S_{po.power} mismatch (exhaustive)"
+            exhaustive = (sum(ex_dev), ex_wall * 1e3, ex_acc["ms_bitmap_compare"] / args.steps)
+        finally:
+            h.set_compare_mode(False)
 
     dev_ms = sum(per_step_dev)
     if world > 1:
         kkeys = ["ms_sieve", "ms_count_scan", "ms_compact", "ms_power_scan", "ms_bitmap_reduce", "ms_bitmap_compare"]
-        t = torch.tensor([dev_ms, wall * 1e3] + [kern[k] for k in kkeys] + [float(launches)], dtype=torch.float64, device="cuda")
+        exv = list(exhaustive) if exhaustive else [0.0, 0.0, 0.0]
+        t = torch.tensor([dev_ms, wall * 1e3] + [kern[k] for k in kkeys] + [float(launches)] + exv, dtype=torch.float64, device="cuda")
         tmax = t.clone()
         dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
         tsum = t.clone()
@@ -298,6 +332,8 @@ def main():
         dev_ms, wall_ms = float(tmax[0]), float(tmax[1])
         kern = {k: float(tmax[2 + i]) for i, k in enumerate(kkeys)}
         launches = int(tsum[2 + len(kkeys)])
+        if exhaustive:
+            exhaustive = tuple(float(x) for x in tmax[3 + len(kkeys): 6 + len(kkeys)])
     else:
         wall_ms = wall * 1e3
     if os.environ.get("PSS_TRACE") and world > 1:
@@ -320,6 +356,7 @@ def main():
     def rate(x, ms):
         return x / (ms * 1e-3) if ms else None
 
+    reduce_name = "k_bitmap_moments2+k_scan_columns" if (w["power"] == 2 and not w["all_powers"]) else "k_bitmap_scan<reduce>+k_scan_columns"
     ms_reduce = per.get("ms_bitmap_reduce", 0.0)
     ms_compare = per.get("ms_bitmap_compare", 0.0)
     kernels = {
@@ -329,13 +366,13 @@ def main():
                     "integers_per_s": rate((w["p_n"] + 1) / world, per["ms_sieve"])},
         "k_scan_tile_counts": {"ms": per["ms_count_scan"]},
         "k_compact": {"ms": per["ms_compact"], "hbm_GBps_algorithmic": rate(8 * primes_per_launch, per["ms_compact"]) and rate(8 * primes_per_launch, per["ms_compact"]) / 1e9},
-        "k_bitmap_scan<reduce>+k_scan_columns": {"ms": ms_reduce, "hbm_GBps_algorithmic": rate(8 * primes_per_launch, ms_reduce) and rate(8 * primes_per_launch, ms_reduce) / 1e9,
+        reduce_name: {"ms": ms_reduce, "hbm_GBps_algorithmic": rate(8 * primes_per_launch, ms_reduce) and rate(8 * primes_per_launch, ms_reduce) / 1e9,
                                                  "imad_per_s": rate(imad * primes_per_launch, ms_reduce), "imad_peak_per_s": 148 * 64 * 1.965e9},
         "k_bitmap_scan<compare>": {"ms": ms_compare, "hbm_GBps_algorithmic": rate(8 * primes_per_launch, ms_compare) and rate(8 * primes_per_launch, ms_compare) / 1e9,
                                    "imad_per_s": rate(imad * primes_per_launch, ms_compare), "imad_peak_per_s": 148 * 64 * 1.965e9},
         "k_power_scan (materialised path)": {"ms": max(per["ms_power_scan"] - ms_reduce - ms_compare, 0.0)},
     }
-    dominant = max(("k_sieve", "k_compact", "k_bitmap_scan<reduce>+k_scan_columns", "k_bitmap_scan<compare>"), key=lambda k: kernels[k]["ms"])
+    dominant = max(("k_sieve", "k_compact", reduce_name, "k_bitmap_scan<compare>"), key=lambda k: kernels[k]["ms"])
     traffic = None
     tp = os.path.join(ROOT, "profiles", "ncu_traffic.json")
     if os.path.exists(tp):
@@ -370,6 +407,13 @@ def main():
         "roofline": roofline,
         "verified": "final sums, p_n and no-match/bracket checked against tests/golden (bit-exact)",
     }
+    if exhaustive:
+        line["exhaustive_compare"] = {
+            "value": n_primes * K / (exhaustive[0] * 1e-3), "unit": "primes/s", "ms_per_step": exhaustive[0] / K,
+            "e2e_value": n_primes * K / (exhaustive[1] * 1e-3), "e2e_ms_per_step": exhaustive[1] / K,
+            "k_bitmap_scan<compare>_ms": exhaustive[2],
+            "note": "same query, pss_set_compare_mode(1): every prime decoded and raised to the k-th power, every S_k(n) formed and "
+                    "compared (the reference's per-n loop); identical results"}
     if world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline(args.workload, seconds=args.cpu_seconds)
     print(json.dumps(line))

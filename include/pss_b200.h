@@ -37,7 +37,7 @@
 extern "C" {
 #endif
 
-#define PSS_ABI_VERSION 1
+#define PSS_ABI_VERSION 2
 #define PSS_LIMBS 12        /* 32-bit limbs per big integer at the boundary (384 bit) */
 #define PSS_MAX_POWER 8     /* highest exponent k supported by the device kernels */
 #define PSS_MAX_PRIME_BITS 40 /* sieve value bound: primes < 2^40 */
@@ -83,6 +83,8 @@ typedef struct pss_stats {
     uint64_t launches;      /* kernels launched by this call */
     double ms_bitmap_reduce;  /* fused path: per-tile (count, sums) from the bitmap + column prefix scan (part of ms_power_scan) */
     double ms_bitmap_compare; /* fused path: re-walk with exact prefixes + compare (part of ms_power_scan) */
+    double ms_span;           /* pss_search, fused path: first launch -> last kernel end of the query on the launch stream,
+                                 gaps between kernels included (0 for multi-call sequences) */
 } pss_stats;
 
 /* ---- fused search: replaces the O(n^2) host loop utils/grammar.py:937-999 (find_matches) over

@@ -36,6 +36,7 @@ struct DevBuf {
 
 constexpr u64 kMaxValue = 1ull << PSS_MAX_PRIME_BITS;
 constexpr u32 kPatternPad = 256 * 1024;   // >= largest tile
+constexpr u32 kMaxTileBytes = 224 * 1024; // + scratch line + static shared memory < 227 KiB opt-in limit
 static const u32 kPatGroups[kMaxPatterns][5] = {{7, 11, 13, 17, 19}, {23, 29, 31, 0, 0}, {37, 41, 43, 0, 0}, {47, 53, 59, 0, 0}};
 static const u32 kFirstSievePrime[kMaxPatterns + 1] = {7, 23, 37, 47, 61};
 
@@ -46,6 +47,11 @@ struct MiscDev {   // small device-side block, one H2D / D2H per scan
     pss_power_result results[PSS_MAX_POWER];
     u32 carry[PSS_MAX_POWER * PSS_LIMBS];
     u64 last_prime;
+};
+
+struct HostBack {   // pinned: asynchronous D2H targets of one query
+    u64 sv_total;
+    u64 col_totals[1 + PSS_MAX_POWER * PSS_LIMBS];
 };
 
 }  // namespace
@@ -59,10 +65,10 @@ struct pss_handle {
     char name[256] = {0};
 
     // tuning
-    u32 tile_bytes = 112 * 1024;   // 2 CTAs x 512 threads per SM (tools/tune_sieve.py, profiles/r01/tune_sieve_*.json)
-    u32 sieve_threads = 512;
+    u32 tile_bytes = 224 * 1024;   // one 1024-thread CTA per SM (tools/tune_sieve.py, profiles/r01/tune_sieve_*.json)
+    u32 sieve_threads = 1024;
     u32 n_pat = 4;
-    u32 warp_wide_div = 128;    // p < tile_bytes / div -> dense (one warp per prime, skewed conflict-free lanes), else one lane per prime
+    u32 warp_wide_div = 160;    // p < tile_bytes / div -> dense (one warp per prime, skewed conflict-free lanes), else one lane per prime
     int search_path = 0;       // 0: fused (scan straight from the bitmap), 1: materialised u64 primes
     int compare_exhaustive = 0;  // 1: the compare pass walks every prime; 0: interval pruning (PSS_COMPARE_EXHAUSTIVE / pss_set_compare_mode)
     int reduce_moments = 1;    // k = 2 reduce pass from per-byte moment tables (0: walk every prime; PSS_REDUCE_MOMENTS)
@@ -83,6 +89,8 @@ struct pss_handle {
     u64 sv_lo = 0, sv_hi = 0, sv_B_start = 0, sv_total = 0, sv_c235 = 0;
     u32 sv_tile_bytes = 0, sv_n_tiles = 0;
     bool sv_valid = false;
+    bool sv_pending = false;   // sieve enqueued, count not read back yet (sieve_finish)
+    bool bs_pending = false;   // reduce enqueued, column totals not read back yet (reduce_finish)
 
     // resident primes
     DevBuf primes;
@@ -100,8 +108,9 @@ struct pss_handle {
     // scan workspace
     DevBuf status, agg, incl, misc, prefix_out, user_vals, tri_buf;
     MiscDev* h_misc = nullptr;   // pinned
+    HostBack* h_back = nullptr;  // pinned
 
-    cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t ev[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     u64 launches = 0;
     pss_stats acc = {};          // accumulated per-kernel device time since pss_stats_reset
 };
@@ -244,26 +253,50 @@ int build_patterns(pss_handle* h) {
     return PSS_OK;
 }
 
+// resident CTAs per SM of k_sieve<THREADS> with a tile of tile_bytes (the kernel's dynamic shared memory limit is
+// raised to the opt-in maximum on first use)
 template <int THREADS>
-int launch_sieve(pss_handle* h, const SieveParams& sp) {
+int sieve_occupancy_t(pss_handle* h, u32 tile_bytes, int* occ) {
     static bool attr_set = false;
     if (!attr_set) {
-        CU_TRY(h, cudaFuncSetAttribute(k_sieve<THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(h->smem_optin - 2048)));
+        CU_TRY(h, cudaFuncSetAttribute(k_sieve<THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(h->smem_optin - 1024)));
         attr_set = true;
     }
-    int occ = 1;
-    const size_t smem = (size_t)sp.tile_bytes + kSieveScratchBytes;
-    CU_TRY(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_sieve<THREADS>, THREADS, smem));
-    if (occ < 1) return fail(h, PSS_EINTERNAL, "sieve tile of %u bytes does not fit shared memory", sp.tile_bytes);
-    const u32 grid = std::min<u32>(sp.n_tiles, (u32)(h->sm_count * occ));
-    k_sieve<THREADS><<<grid, THREADS, smem, h->stream>>>(sp);
+    *occ = 0;
+    CU_TRY(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(occ, k_sieve<THREADS>, THREADS, (size_t)tile_bytes + kSieveScratchBytes));
+    return PSS_OK;
+}
+int sieve_occupancy(pss_handle* h, u32 threads, u32 tile_bytes, int* occ) {
+    switch (threads) {
+        case 256: return sieve_occupancy_t<256>(h, tile_bytes, occ);
+        case 512: return sieve_occupancy_t<512>(h, tile_bytes, occ);
+        case 768: return sieve_occupancy_t<768>(h, tile_bytes, occ);
+        default: return sieve_occupancy_t<1024>(h, tile_bytes, occ);
+    }
+}
+
+template <int THREADS>
+int launch_sieve(pss_handle* h, const SieveParams& sp, u32 grid) {
+    k_sieve<THREADS><<<grid, THREADS, (size_t)sp.tile_bytes + kSieveScratchBytes, h->stream>>>(sp);
     CU_TRY(h, cudaGetLastError());
     h->launches++;
     return PSS_OK;
 }
 
-// K1a + K1b: sieve [lo,hi) into the bitmap, count.  Leaves sv_* describing the bitmap.
-int sieve_range(pss_handle* h, u64 lo, u64 hi) {
+// completes an asynchronous sieve_range after the stream has been synchronised
+void sieve_finish(pss_handle* h) {
+    if (!h->sv_pending) return;
+    h->sv_pending = false;
+    h->sv_total = h->h_back->sv_total;
+    h->sv_valid = true;
+    h->acc.ms_sieve += ev_ms(h, 0, 1);
+    h->acc.ms_count_scan += ev_ms(h, 1, 2);
+}
+
+// K1a + K1b: sieve [lo,hi) into the bitmap, count.  Leaves sv_* describing the bitmap.  With defer_sync the
+// launches are only enqueued: the caller synchronises the stream later and calls sieve_finish().
+int sieve_range(pss_handle* h, u64 lo, u64 hi, bool defer_sync = false) {
+    h->sv_pending = false;
     h->sv_valid = false;
     h->bs_valid = false;
     if (hi > kMaxValue) return fail(h, PSS_EINVAL, "sieve bound %llu exceeds 2^%d", (unsigned long long)hi, PSS_MAX_PRIME_BITS);
@@ -275,11 +308,17 @@ int sieve_range(pss_handle* h, u64 lo, u64 hi) {
     const u64 B_start = (lo / 30) & ~15ull;
     const u64 B_end = (hi + 29) / 30;
     const u64 n_bytes = B_end - B_start;
-    // tile size: the tuned default, shrunk for small ranges so that every SM still gets tiles
+    // tile size: at most the tuned size, chosen so that the tile count is a whole number of rounds of the resident
+    // grid (tiles are handed out round-robin: no partial last round, no idle SMs at the tail)
+    int occ = 0;
+    PSS_TRY(sieve_occupancy(h, h->sieve_threads, h->tile_bytes, &occ));
+    if (occ < 1) return fail(h, PSS_EINTERNAL, "sieve tile of %u bytes does not fit shared memory", h->tile_bytes);
+    const u32 grid_max = (u32)(h->sm_count * occ);
     u32 tile_bytes = h->tile_bytes;
     {
-        const u64 want_tiles = (u64)h->sm_count * 4;
-        u64 per = (n_bytes + want_tiles - 1) / want_tiles;
+        const u64 per_round = (u64)grid_max * tile_bytes;
+        const u64 rounds = std::max<u64>(1, (n_bytes + per_round - 1) / per_round);
+        u64 per = (n_bytes + grid_max * rounds - 1) / (grid_max * rounds);
         per = ((per + kChunkBytes - 1) / kChunkBytes) * kChunkBytes;
         per = std::max<u64>(per, 8 * 1024);
         if (per < tile_bytes) tile_bytes = (u32)per;
@@ -332,9 +371,10 @@ int sieve_range(pss_handle* h, u64 lo, u64 hi) {
 
     CU_TRY(h, cudaEventRecord(h->ev[0], h->stream));
     switch (h->sieve_threads) {
-        case 256: PSS_TRY(launch_sieve<256>(h, sp)); break;
-        case 1024: PSS_TRY(launch_sieve<1024>(h, sp)); break;
-        default: PSS_TRY(launch_sieve<512>(h, sp)); break;
+        case 256: PSS_TRY(launch_sieve<256>(h, sp, std::min(n_tiles, grid_max))); break;
+        case 512: PSS_TRY(launch_sieve<512>(h, sp, std::min(n_tiles, grid_max))); break;
+        case 768: PSS_TRY(launch_sieve<768>(h, sp, std::min(n_tiles, grid_max))); break;
+        default: PSS_TRY(launch_sieve<1024>(h, sp, std::min(n_tiles, grid_max))); break;
     }
     CU_TRY(h, cudaEventRecord(h->ev[1], h->stream));
 
@@ -345,16 +385,16 @@ int sieve_range(pss_handle* h, u64 lo, u64 hi) {
     CU_TRY(h, cudaGetLastError());
     h->launches++;
     CU_TRY(h, cudaEventRecord(h->ev[2], h->stream));
-    u64 total = 0;
-    CU_TRY(h, cudaMemcpyAsync(&total, static_cast<u64*>(h->tile_prefix.p) + n_tiles, sizeof(u64), cudaMemcpyDeviceToHost, h->stream));
-    CU_TRY(h, cudaStreamSynchronize(h->stream));
-
-    h->sv_lo = lo; h->sv_hi = hi; h->sv_B_start = B_start; h->sv_total = total; h->sv_c235 = c235;
-    h->sv_tile_bytes = tile_bytes; h->sv_n_tiles = n_tiles; h->sv_valid = true;
-    h->acc.ms_sieve += ev_ms(h, 0, 1);
-    h->acc.ms_count_scan += ev_ms(h, 1, 2);
+    CU_TRY(h, cudaMemcpyAsync(&h->h_back->sv_total, static_cast<u64*>(h->tile_prefix.p) + n_tiles, sizeof(u64), cudaMemcpyDeviceToHost, h->stream));
+    h->sv_lo = lo; h->sv_hi = hi; h->sv_B_start = B_start; h->sv_total = 0; h->sv_c235 = c235;
+    h->sv_tile_bytes = tile_bytes; h->sv_n_tiles = n_tiles;
     h->acc.sieve_lo = lo;
     h->acc.sieve_hi = hi;
+    h->sv_pending = true;
+    if (!defer_sync) {
+        CU_TRY(h, cudaStreamSynchronize(h->stream));
+        sieve_finish(h);
+    }
     return PSS_OK;
 }
 
@@ -617,18 +657,54 @@ void fill_bscan_common(pss_handle* h, BScanParams& bp) {
     bp.warp_rec = static_cast<u32*>(h->warp_rec.p);
 }
 
-// phase A of the fused path: per-tile (count, sums) records, column prefixes, slice totals
-int bitmap_reduce(pss_handle* h, u32 K, bool multi) {
-    if (!h->sv_valid) return fail(h, PSS_EINTERNAL, "no sieve result");
+// completes an asynchronous bitmap_reduce after the stream has been synchronised
+int reduce_finish(pss_handle* h) {
+    if (!h->bs_pending) return PSS_OK;
+    h->bs_pending = false;
+    const u32 K = h->bs_K;
+    const bool multi = h->bs_multi;
+    const u32 np = n_powers_of(K, multi);
+    h->acc.ms_power_scan += ev_ms(h, 4, 5);
+    h->acc.ms_bitmap_reduce += ev_ms(h, 4, 5);
+    // normalise the deferred-carry column totals into limbs
+    const u64* totals = h->h_back->col_totals;
+    h->bs_count = totals[0];
+    u32 col = 1;
+    for (u32 j = 0; j < np; ++j) {
+        const u32 w = (u32)sum_limbs((int)expo_of(K, multi, j));
+        u64 c = 0;
+        for (u32 i = 0; i < w; ++i, ++col) {
+            const u64 v = totals[col];
+            const u64 lo = (v & 0xFFFFFFFFull) + (c & 0xFFFFFFFFull);
+            h->bs_sums[j * PSS_LIMBS + i] = (u32)lo;
+            c = (v >> 32) + (c >> 32) + (lo >> 32);
+        }
+    }
+    if (h->bs_count != h->sv_total)
+        return fail(h, PSS_EINTERNAL, "bitmap reduce counted %llu primes, sieve counted %llu", (unsigned long long)h->bs_count,
+                    (unsigned long long)h->sv_total);
+    h->bs_valid = true;
+    return PSS_OK;
+}
+
+// phase A of the fused path: per-tile (count, sums) records, column prefixes, slice totals.  The sieve may still be
+// pending (sv_pending): only its host-known geometry is used to enqueue the launches.
+int bitmap_reduce(pss_handle* h, u32 K, bool multi, bool defer_sync = false) {
+    if (!h->sv_valid && !h->sv_pending) return fail(h, PSS_EINTERNAL, "no sieve result");
     if (K < 1 || K > PSS_MAX_POWER) return fail(h, PSS_EINVAL, "power %u out of range 1..%d", K, PSS_MAX_POWER);
     if (multi && K > 6) return fail(h, PSS_EINVAL, "all_powers supports power_max <= 6");
     if (multi && K == 1) multi = false;
     h->bs_valid = false;
-    const u32 np = n_powers_of(K, multi), total = total_limbs_of(K, multi), ncols = 1 + total;
+    h->bs_pending = false;
+    const u32 total = total_limbs_of(K, multi), ncols = 1 + total;
     memset(h->bs_sums, 0, sizeof h->bs_sums);
     h->bs_count = 0;
     h->bs_K = K; h->bs_multi = multi; h->bs_total_cols = ncols;
     if (h->sv_n_tiles == 0) {   // empty range
+        if (h->sv_pending) {
+            CU_TRY(h, cudaStreamSynchronize(h->stream));
+            sieve_finish(h);
+        }
         h->bs_n_tiles = 0; h->bs_col_stride = 1; h->bs_valid = true;
         return PSS_OK;
     }
@@ -645,7 +721,12 @@ int bitmap_reduce(pss_handle* h, u32 K, bool multi) {
     CU_TRY(h, cudaEventRecord(h->ev[4], h->stream));
     CU_TRY(h, cudaMemsetAsync(bp.cols, 0, (size_t)ncols * bp.col_stride * sizeof(u64), h->stream));
     if (K == 2 && !multi && h->reduce_moments) {
-        const u32 grid = std::min<u32>(bp.n_tiles, (u32)(h->sm_count * 8));
+        static int occ = 0;
+        if (!occ) {
+            CU_TRY(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_bitmap_moments2, kBsThreads, 0));
+            if (occ < 1) occ = 1;
+        }
+        const u32 grid = std::min<u32>(bp.n_tiles, (u32)(h->sm_count * occ));
         k_bitmap_moments2<<<grid, kBsThreads, 0, h->stream>>>(bp);
         CU_TRY(h, cudaGetLastError());
         h->launches++;
@@ -656,31 +737,16 @@ int bitmap_reduce(pss_handle* h, u32 K, bool multi) {
     CU_TRY(h, cudaGetLastError());
     h->launches++;
     CU_TRY(h, cudaEventRecord(h->ev[5], h->stream));
-    std::vector<u64> totals(ncols);
-    CU_TRY(h, cudaMemcpy2DAsync(totals.data(), sizeof(u64), static_cast<const u64*>(h->col_prefix.p) + bp.n_tiles, bp.col_stride * sizeof(u64),
+    CU_TRY(h, cudaMemcpy2DAsync(h->h_back->col_totals, sizeof(u64), static_cast<const u64*>(h->col_prefix.p) + bp.n_tiles, bp.col_stride * sizeof(u64),
                                 sizeof(u64), ncols, cudaMemcpyDeviceToHost, h->stream));
-    CU_TRY(h, cudaStreamSynchronize(h->stream));
-    h->acc.ms_power_scan += ev_ms(h, 4, 5);
-    h->acc.ms_bitmap_reduce += ev_ms(h, 4, 5);
-    // normalise the deferred-carry column totals into limbs
-    h->bs_count = totals[0];
-    u32 col = 1;
-    for (u32 j = 0; j < np; ++j) {
-        const u32 w = (u32)sum_limbs((int)expo_of(K, multi, j));
-        u64 c = 0;
-        for (u32 i = 0; i < w; ++i, ++col) {
-            const u64 v = totals[col];
-            const u64 lo = (v & 0xFFFFFFFFull) + (c & 0xFFFFFFFFull);
-            h->bs_sums[j * PSS_LIMBS + i] = (u32)lo;
-            c = (v >> 32) + (c >> 32) + (lo >> 32);
-        }
-    }
-    if (h->bs_count != h->sv_total)
-        return fail(h, PSS_EINTERNAL, "bitmap reduce counted %llu primes, sieve counted %llu", (unsigned long long)h->bs_count,
-                    (unsigned long long)h->sv_total);
     h->bs_n_tiles = bp.n_tiles;
     h->bs_col_stride = bp.col_stride;
-    h->bs_valid = true;
+    h->bs_pending = true;
+    if (!defer_sync) {
+        CU_TRY(h, cudaStreamSynchronize(h->stream));
+        sieve_finish(h);
+        PSS_TRY(reduce_finish(h));
+    }
     return PSS_OK;
 }
 
@@ -697,7 +763,8 @@ void limbs_add(u32* a, const u32* b) {
 int bitmap_compare(pss_handle* h, u64 n_first, const u32* carry_in, const pss_search_args* a, pss_search_result* res) {
     const bool multi = a->all_powers && a->power_max > 1;
     const u32 K = a->power_max;
-    if (!h->bs_valid || h->bs_K != K || h->bs_multi != multi)
+    const bool pending = h->bs_pending;   // single-query chain: the sieve and the reduce are enqueued, not read back yet
+    if ((!h->bs_valid && !pending) || h->bs_K != K || h->bs_multi != multi)
         return fail(h, PSS_EINVAL, "pss_slice_sieve_sums must be called first with the same power configuration");
     const u32 np = n_powers_of(K, multi);
     static const u32 kMasks[6] = {2u, 5u, 1u, 3u, 4u, 6u};
@@ -713,8 +780,11 @@ int bitmap_compare(pss_handle* h, u64 n_first, const u32* carry_in, const pss_se
                 if (hm->carry[j * PSS_LIMBS + i]) return fail(h, PSS_EINVAL, "carry-in of power %u exceeds %d limbs", hm->results[j].power, w);
         }
     }
-    const u64 scanned = (a->n_max >= n_first) ? std::min<u64>(h->bs_count, a->n_max - n_first + 1) : 0;
-    CU_TRY(h, cudaEventRecord(h->ev[4], h->stream));
+    // with a pending reduce the slice count is not known yet: the caller (pss_search) guarantees by a proven bound
+    // that the slice holds n_max, and checks it after the synchronisation
+    u64 scanned = (a->n_max >= n_first) ? (pending ? a->n_max - n_first + 1 : std::min<u64>(h->bs_count, a->n_max - n_first + 1)) : 0;
+    if (h->bs_n_tiles == 0) scanned = 0;
+    CU_TRY(h, cudaEventRecord(h->ev[6], h->stream));
     if (scanned > 0) {
         BScanParams bp;
         fill_bscan_common(h, bp);
@@ -738,15 +808,23 @@ int bitmap_compare(pss_handle* h, u64 n_first, const u32* carry_in, const pss_se
         bp.error_flag = &dm->error_flag;
         CU_TRY(h, cudaMemcpyAsync(dm, hm, sizeof(MiscDev), cudaMemcpyHostToDevice, h->stream));
         PSS_TRY(launch_bscan<kBsCompare>(h, bp, K, multi));
-        CU_TRY(h, cudaEventRecord(h->ev[5], h->stream));
+        CU_TRY(h, cudaEventRecord(h->ev[7], h->stream));
         CU_TRY(h, cudaMemcpyAsync(hm, dm, sizeof(MiscDev), cudaMemcpyDeviceToHost, h->stream));
         CU_TRY(h, cudaStreamSynchronize(h->stream));
     } else {
-        CU_TRY(h, cudaEventRecord(h->ev[5], h->stream));
+        CU_TRY(h, cudaEventRecord(h->ev[7], h->stream));
         CU_TRY(h, cudaStreamSynchronize(h->stream));
     }
-    h->acc.ms_power_scan += ev_ms(h, 4, 5);
-    h->acc.ms_bitmap_compare += ev_ms(h, 4, 5);
+    if (pending) {
+        sieve_finish(h);
+        PSS_TRY(reduce_finish(h));
+        if (h->sv_total < a->n_max - n_first + 1)
+            return fail(h, PSS_EINTERNAL, "prime count bound failed: the slice holds %llu primes, n_max = %llu", (unsigned long long)h->sv_total,
+                        (unsigned long long)a->n_max);
+    }
+    h->acc.ms_power_scan += ev_ms(h, 6, 7);
+    h->acc.ms_bitmap_compare += ev_ms(h, 6, 7);
+    if (pending) h->acc.ms_span += ev_ms(h, 0, 7);   // sieve start -> compare end: the whole query on the stream
     h->acc.primes += scanned;
     const bool reached_n_max = scanned > 0 && (n_first + scanned - 1 == a->n_max);
     for (u32 j = 0; j < np; ++j) {
@@ -823,7 +901,8 @@ int pss_open(int device, pss_handle** out) {
     h->warp_wide_div = env_u32("PSS_WARP_WIDE_DIV", h->warp_wide_div);
     h->reduce_moments = (int)env_u32("PSS_REDUCE_MOMENTS", (u32)h->reduce_moments);
     h->compare_exhaustive = (int)env_u32("PSS_COMPARE_EXHAUSTIVE", (u32)h->compare_exhaustive);
-    h->tile_bytes = std::max<u32>(8192, std::min<u32>((h->tile_bytes / kChunkBytes) * kChunkBytes, 216 * 1024));
+    h->tile_bytes = std::max<u32>(8192, std::min<u32>((h->tile_bytes / kChunkBytes) * kChunkBytes, kMaxTileBytes));
+    if (h->sieve_threads != 256 && h->sieve_threads != 512 && h->sieve_threads != 768) h->sieve_threads = 1024;
     auto cleanup = [&](int rc) {
         pss_close(h);
         return rc;
@@ -832,6 +911,7 @@ int pss_open(int device, pss_handle** out) {
     for (auto& ev : h->ev)
         if (cudaEventCreate(&ev) != cudaSuccess) return cleanup(fail(nullptr, PSS_EINTERNAL, "event create failed"));
     if (cudaMallocHost(&h->h_misc, sizeof(MiscDev)) != cudaSuccess) return cleanup(fail(nullptr, PSS_EINTERNAL, "pinned alloc failed"));
+    if (cudaMallocHost(&h->h_back, sizeof(HostBack)) != cudaSuccess) return cleanup(fail(nullptr, PSS_EINTERNAL, "pinned alloc failed"));
     int rc = ensure(h, h->misc, sizeof(MiscDev));
     if (rc == PSS_OK) rc = build_patterns(h);
     if (rc != PSS_OK) {
@@ -853,6 +933,7 @@ int pss_close(pss_handle* h) {
     for (auto& p : h->d_pat)
         if (p) cudaFree(p);
     if (h->h_misc) cudaFreeHost(h->h_misc);
+    if (h->h_back) cudaFreeHost(h->h_back);
     for (auto& ev : h->ev)
         if (ev) cudaEventDestroy(ev);
     if (h->stream) cudaStreamDestroy(h->stream);
@@ -872,12 +953,13 @@ int pss_device_info(pss_handle* h, char* buf, size_t cap) {
 int pss_set_tuning(pss_handle* h, uint32_t tile_bytes, uint32_t sieve_threads, uint32_t n_patterns) {
     PSS_TRY(check_handle(h));
     if (tile_bytes) {
-        if (tile_bytes % kChunkBytes || tile_bytes < 8192 || tile_bytes > 216 * 1024)
-            return fail(h, PSS_EINVAL, "tile_bytes must be a multiple of %d in [8192, %d]", kChunkBytes, 216 * 1024);
+        if (tile_bytes % kChunkBytes || tile_bytes < 8192 || tile_bytes > kMaxTileBytes)
+            return fail(h, PSS_EINVAL, "tile_bytes must be a multiple of %d in [8192, %u]", kChunkBytes, kMaxTileBytes);
         h->tile_bytes = tile_bytes;
     }
     if (sieve_threads) {
-        if (sieve_threads != 256 && sieve_threads != 512 && sieve_threads != 1024) return fail(h, PSS_EINVAL, "sieve_threads must be 256, 512 or 1024");
+        if (sieve_threads != 256 && sieve_threads != 512 && sieve_threads != 768 && sieve_threads != 1024)
+            return fail(h, PSS_EINVAL, "sieve_threads must be 256, 512, 768 or 1024");
         h->sieve_threads = sieve_threads;
     }
     if (n_patterns) {
@@ -1004,6 +1086,7 @@ static void fill_stats(pss_handle* h, pss_stats* s, const pss_stats& before) {
     s->ms_power_scan = now.ms_power_scan - before.ms_power_scan;
     s->ms_bitmap_reduce = now.ms_bitmap_reduce - before.ms_bitmap_reduce;
     s->ms_bitmap_compare = now.ms_bitmap_compare - before.ms_bitmap_compare;
+    s->ms_span = now.ms_span - before.ms_span;
     s->ms_total_device = s->ms_sieve + s->ms_count_scan + s->ms_compact + s->ms_power_scan;
     s->primes = now.primes - before.primes;
     s->sieve_lo = now.sieve_lo;
@@ -1038,9 +1121,9 @@ int pss_search(pss_handle* h, const pss_search_args* a, pss_search_result* res) 
         // fused path: the bit-packed sieve output is scanned directly
         const u64 bound = pss_nth_prime_upper(a->n_max) + 1;
         if (bound > kMaxValue) return fail(h, PSS_EINVAL, "n = %llu needs primes beyond 2^%d", (unsigned long long)a->n_max, PSS_MAX_PRIME_BITS);
-        PSS_TRY(sieve_range(h, 0, bound));
-        if (h->sv_total < a->n_max) return fail(h, PSS_EINTERNAL, "prime count bound failed for n = %llu", (unsigned long long)a->n_max);
-        PSS_TRY(bitmap_reduce(h, a->power_max, multi));
+        // sieve -> reduce -> column scan -> compare are enqueued back to back; one synchronisation at the end
+        PSS_TRY(sieve_range(h, 0, bound, true));
+        PSS_TRY(bitmap_reduce(h, a->power_max, multi, true));
         PSS_TRY(bitmap_compare(h, 1, nullptr, a, res));
     }
     fill_stats(h, &res->stats, before);

@@ -581,9 +581,11 @@ __global__ void __launch_bounds__(kBsThreads, bs_min_blocks<K, MULTI>()) k_bitma
 // (thread / warp records, scan-tile columns) is bit-identical to k_bitmap_scan<2, false, kBsReduce>.
 __global__ void __launch_bounds__(kBsThreads) k_bitmap_moments2(const __grid_constant__ BScanParams P) {
     constexpr int NWARP = kBsThreads / 32, WPT = kWordsPerThread, WARP_WORDS = 32 * WPT;
-    __shared__ u32 s_lut[256];
+    // the byte table, replicated once per bank: lane l only ever reads word v * 32 + l, so the four lookups per
+    // word are bank-conflict free whatever the byte values are (32 KiB; a single copy costs ~4.5 wavefronts per LDS)
+    __shared__ u32 s_lut[256 * 32];
     {
-        const u32 v = threadIdx.x;     // kBsThreads == 256: one entry per thread
+        const u32 v = threadIdx.x;     // kBsThreads == 256: one byte value per thread
         u32 n = 0, r1 = 0, r2 = 0;
 #pragma unroll
         for (u32 j = 0; j < 8; ++j)
@@ -591,7 +593,8 @@ __global__ void __launch_bounds__(kBsThreads) k_bitmap_moments2(const __grid_con
                 const u32 r = wheel_residue(j);
                 n += 1u; r1 += r; r2 += r * r;
             }
-        s_lut[v] = n | (r1 << 6) | (r2 << 16);
+        const u32 e = n | (r1 << 6) | (r2 << 16);
+        for (u32 k = 0; k < 32; ++k) s_lut[v * 32 + ((k + v) & 31u)] = e;   // rotated: conflict-free stores too
     }
     __syncthreads();
     const u32 lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
@@ -613,7 +616,8 @@ __global__ void __launch_bounds__(kBsThreads) k_bitmap_moments2(const __grid_con
         for (int i = 0; i < WPT; ++i) {
             const uint4 vv = v[i >> 2];
             const u32 w = (i & 3) == 0 ? vv.x : (i & 3) == 1 ? vv.y : (i & 3) == 2 ? vv.z : vv.w;
-            const u32 e0 = s_lut[w & 255u], e1 = s_lut[(w >> 8) & 255u], e2 = s_lut[(w >> 16) & 255u], e3 = s_lut[w >> 24];
+            const u32* lut = s_lut + lane;
+            const u32 e0 = lut[(w & 255u) << 5], e1 = lut[((w >> 8) & 255u) << 5], e2 = lut[((w >> 16) & 255u) << 5], e3 = lut[(w >> 24) << 5];
             const u32 W = e0 + e1 + e2 + e3;                       // moments about each byte's own origin
             const u32 V = e1 + 2u * e2 + 3u * e3;                  // byte-index weighted (count and sum r fields)
             const u32 Q = (e1 & 63u) + 4u * (e2 & 63u) + 9u * (e3 & 63u);

@@ -109,7 +109,7 @@ __device__ __forceinline__ u32 inv_mod64(u32 p) { return p * (2u - p * p); }
 constexpr u32 kSieveScratchBytes = 128;
 
 template <int THREADS>
-__global__ void __launch_bounds__(THREADS) k_sieve(const SieveParams P) {
+__global__ void __launch_bounds__(THREADS, (THREADS <= 768) ? 2 : 1) k_sieve(const SieveParams P) {
     extern __shared__ uint4 smem4[];
     __shared__ u64 s_off16[kMaxPatterns];
     __shared__ u32 s_cnt[THREADS / 32];

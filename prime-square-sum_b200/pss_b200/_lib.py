@@ -15,6 +15,7 @@ import numpy as np
 
 PSS_LIMBS = 12
 PSS_MAX_POWER = 8
+ABI_VERSION = 2   # PSS_ABI_VERSION of include/pss_b200.h this binding was written against
 PSS_MAX_PRIME_BITS = 40
 PSS_OK, PSS_EINVAL, PSS_ENODEV, PSS_ENOMEM, PSS_EINTERNAL = 0, 1, 2, 3, 4
 
@@ -41,7 +42,7 @@ class Stats(ctypes.Structure):
         ("ms_sieve", ctypes.c_double), ("ms_count_scan", ctypes.c_double), ("ms_compact", ctypes.c_double),
         ("ms_power_scan", ctypes.c_double), ("ms_total_device", ctypes.c_double),
         ("primes", u64), ("sieve_lo", u64), ("sieve_hi", u64), ("launches", u64),
-        ("ms_bitmap_reduce", ctypes.c_double), ("ms_bitmap_compare", ctypes.c_double),
+        ("ms_bitmap_reduce", ctypes.c_double), ("ms_bitmap_compare", ctypes.c_double), ("ms_span", ctypes.c_double),
     ]
 
 
@@ -117,7 +118,7 @@ def load_library() -> ctypes.CDLL:
     for name in EXPORTS:
         if name not in ("pss_last_error", "pss_nth_prime_upper"):
             getattr(L, name).restype = ctypes.c_int
-    if L.pss_abi_version() != 1:
+    if L.pss_abi_version() != ABI_VERSION:
         raise RuntimeError("libpss_b200.so ABI version mismatch")
     _cdll = L
     return L
@@ -126,7 +127,7 @@ def load_library() -> ctypes.CDLL:
 def stats_to_dict(s: "Stats") -> dict:
     return {"ms_sieve": s.ms_sieve, "ms_count_scan": s.ms_count_scan, "ms_compact": s.ms_compact,
             "ms_power_scan": s.ms_power_scan, "ms_bitmap_reduce": s.ms_bitmap_reduce,
-            "ms_bitmap_compare": s.ms_bitmap_compare, "ms_total_device": s.ms_total_device, "primes": int(s.primes),
+            "ms_bitmap_compare": s.ms_bitmap_compare, "ms_total_device": s.ms_total_device, "ms_span": s.ms_span, "primes": int(s.primes),
             "sieve_lo": int(s.sieve_lo), "sieve_hi": int(s.sieve_hi), "launches": int(s.launches)}
 
 

@@ -57,7 +57,8 @@ def test_first_n_nth_count_golden(handle, golden):
 
 
 @pytest.mark.parametrize("tile,threads,npat", [(8192, 256, 4), (98304, 512, 4), (65536, 1024, 2), (16384, 512, 0),
-                                               (216 * 1024, 1024, 4), (32768, 256, 1), (49152, 512, 3)])
+                                               (216 * 1024, 1024, 4), (32768, 256, 1), (49152, 512, 3), (224 * 1024, 1024, 4),
+                                               (112 * 1024, 768, 4)])
 def test_sieve_tunings_vs_oracle(orc, tile, threads, npat):
     """Every tile size / block size / pattern count gives the same primes (segment-size independence,
     the analogue of tests/test_sieve.py:80-120)."""
