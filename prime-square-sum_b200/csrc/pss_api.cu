@@ -80,7 +80,8 @@ struct pss_handle {
     // base primes
     std::vector<u32> h_base;   // all primes >= 7 up to base_limit
     u64 base_limit = 0;
-    DevBuf d_base, d_base_inv, d_base_strand;
+    DevBuf d_base, d_base_inv, d_base_strand, d_batch_geo;
+    std::vector<u32> h_batch_geo;   // host copy of the staged sparse-batch geometry (re-uploaded only when it changes)
     u32 base_first_prime = 0;  // first sieving prime the device copy starts at
     u32 n_base_dev = 0;
 
@@ -350,8 +351,30 @@ int sieve_range(pss_handle* h, u64 lo, u64 hi, bool defer_sync = false) {
         auto b = std::lower_bound(h->h_base.begin(), h->h_base.end(), h->base_first_prime);
         auto e = std::upper_bound(h->h_base.begin(), h->h_base.end(), (u32)std::min<u64>(lim, 0xFFFFFFFFull));
         sp.n_base = (e > b) ? (u32)(e - b) : 0;
-        const u32 warp_lim = tile_bytes / std::max<u32>(h->warp_wide_div, 1);
+        // dense primes need at least 34 hits per lane: p <= tile / 136
+        const u32 warp_lim = tile_bytes / std::max<u32>(h->warp_wide_div, 136);
         sp.n_warp_wide = (e > b) ? (u32)(std::lower_bound(b, e, warp_lim) - b) : 0;
+        // sparse batches: warp-uniform trip counts per strand, staged once per (tile size, prime table)
+        {
+            const u32 n_sparse = sp.n_base - sp.n_warp_wide;
+            const u32 n_batches = (n_sparse + 31) / 32;
+            std::vector<u32> geo(std::max<u32>(n_batches, 1), 0);
+            for (u32 q = 0; q < n_batches; ++q) {
+                const u32 p_lo = b[sp.n_warp_wide + 32 * q];
+                const u32 p_hi = b[std::min<u32>(sp.n_warp_wide + 32 * q + 31, sp.n_base - 1)];
+                const u32 U = tile_bytes / p_hi;
+                const u32 n_uni = U > 1 ? U - 1 : 0;
+                const u32 n_rag = (tile_bytes - 1) / p_lo + 1 - n_uni;
+                geo[q] = n_uni | (n_rag << 16);
+            }
+            if (geo != h->h_batch_geo) {
+                PSS_TRY(ensure(h, h->d_batch_geo, geo.size() * sizeof(u32)));
+                CU_TRY(h, cudaStreamSynchronize(h->stream));   // the previous table may still be in use
+                CU_TRY(h, cudaMemcpy(h->d_batch_geo.p, geo.data(), geo.size() * sizeof(u32), cudaMemcpyHostToDevice));
+                h->h_batch_geo.swap(geo);
+            }
+            sp.batch_geo = static_cast<const u32*>(h->d_batch_geo.p);
+        }
         // per tile: how many base primes satisfy p*p < tile end (tiny device kernel, no host work)
         PSS_TRY(ensure(h, h->tile_nact, (size_t)n_tiles * sizeof(u32)));
         k_tile_nact<<<(n_tiles + 255) / 256, 256, 0, h->stream>>>(sp.base_p, sp.n_base, B_start, tile_bytes, hi, n_tiles,
@@ -927,7 +950,7 @@ int pss_close(pss_handle* h) {
     if (!h) return PSS_OK;
     cudaSetDevice(h->device);
     if (h->stream) cudaStreamSynchronize(h->stream);
-    for (DevBuf* b : {&h->d_base, &h->d_base_inv, &h->d_base_strand, &h->cols, &h->col_prefix, &h->thread_rec, &h->warp_rec, &h->tile_nact, &h->tri_buf, &h->bitmap, &h->chunk_counts, &h->tile_counts, &h->tile_prefix, &h->primes, &h->status, &h->agg,
+    for (DevBuf* b : {&h->d_base, &h->d_base_inv, &h->d_base_strand, &h->d_batch_geo, &h->cols, &h->col_prefix, &h->thread_rec, &h->warp_rec, &h->tile_nact, &h->tri_buf, &h->bitmap, &h->chunk_counts, &h->tile_counts, &h->tile_prefix, &h->primes, &h->status, &h->agg,
                       &h->incl, &h->misc, &h->prefix_out, &h->user_vals})
         if (b->p) cudaFree(b->p);
     for (auto& p : h->d_pat)

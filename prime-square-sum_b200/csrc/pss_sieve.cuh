@@ -38,7 +38,9 @@ struct SieveParams {
     const u32* base_inv;
     const u32* base_strand;   // n_base * 8
     u32 n_base;
-    u32 n_warp_wide;     // base primes [0, n_warp_wide) handled warp-wide, the rest by 8-lane groups
+    u32 n_warp_wide;     // base primes [0, n_warp_wide) are "dense" (one warp per prime), the rest go in batches of 32
+    const u32* batch_geo;     // per batch b of sparse primes [n_warp_wide + 32b, +32): n_uni | n_rag << 16, the warp-uniform
+                              // trip counts per strand (n_uni = tile/p_hi - 1 unguarded, n_rag = (tile-1)/p_lo + 1 - n_uni guarded)
     const u32* tile_nact;     // per tile: number of base primes with p*p < tile end (the only ones that can
                               // still cross something off there)
     u32 wide_index;      // 1: tile byte indices may exceed 2^32 -> 64-bit modulo path
@@ -155,41 +157,46 @@ __global__ void __launch_bounds__(THREADS, (THREADS <= 768) ? 2 : 1) k_sieve(con
             item = __shfl_sync(0xFFFFFFFFu, item, 0);
             if (item >= n_items) break;
             if (item < n_dense) {
-                // dense prime: lane -> (strand j, sub-sequence s), word stride p (byte stride 4p), constant mask.
-                // Lane l delays its start by e_l iterations with (w_l - e_l p) = l (mod 32): at every iteration the
-                // 32 lanes then address the 32 different banks (l + it*p) mod 32 -- one wavefront per warp instruction.
+                // dense prime (p <= tile/136): lane -> (strand j, sub-sequence s), word stride p (byte stride 4p),
+                // constant mask; every lane has count = H-1 .. H+1 >= 33 hits (H = tile / 4p).
+                // Bank-conflict-free order: lane l visits its hits rotated by e_l = (w_l - l) / p mod 32, i.e. first the
+                // last e_l hits (indices count-e_l .. count-1), then 0, 1, ...  Once a lane is past its wrap-around it
+                // addresses bank (l + it*p) mod 32 in iteration it: from iteration 32 on the 32 lanes hit the 32 different
+                // banks (one wavefront per warp instruction, measured 1.00); in the first 32 iterations the lanes still in
+                // their wrapped part are shifted by count*p and a bank sees at most three accesses.  No lane ever waits:
+                // count iterations cover count hits.
                 const u32 j = lane & 7u, s = lane >> 3;
                 const u32 p = __ldg(P.base_p + item), inv = __ldg(P.base_inv + item);
                 const u32 cb = __ldg(P.base_strand + item * 8u + j);
                 const u32 r = tile_mod(B0, p, inv, wide);
                 const u32 c = cb & 0xFFFFFFu;
                 const bool special = (j == 0) && (B0 <= (u64)c);      // q = 0 would be p itself: first hit is one period later
-                const u32 x = first_hit(p, c, r, j == 0, B0) + s * p;  // x < 4p unless special
+                const u32 x = first_hit(p, c, r, j == 0, B0) + s * p;  // x < 4p unless special (then x < 5p)
                 const u32 mask = ~(1u << (((x & 3u) << 3) + (cb >> 24)));
                 const u32 w = x >> 2;
                 const u32 e = special ? 0u : (((w - lane) * inv_mod64(p)) & 31u);
-                // byte offset of the lane's word; "negative" while the lane is still waiting (w < p there, so it
-                // wraps far above tile_bytes)
-                u32 a = (w - e * p) << 2;
                 const u32 step = p << 2;
-                const u32 H = tile_bytes / step;          // every lane has at least H - 2 hits
-                const u32 n_it = 32u + H;                 // ... and at most H + 1, after a delay of at most 31
-                // a lane outside the tile ANDs into the scratch word of the bank it would have used: no branch, and the
-                // instruction stays one wavefront
-                auto guarded = [&]() {
-                    cross((a < tile_bytes) ? a : ((a & 127u) | tile_bytes), mask);
+                const u32 H = tile_bytes / step;                       // >= 34 (host: n_warp_wide)
+                const u32 b0 = w << 2;                                 // byte offset of hit 0 (< 2 * step)
+                const u32 count = H - 1u + ((b0 + (H - 1u) * step < tile_bytes) ? 1u : 0u) + ((b0 + H * step < tile_bytes) ? 1u : 0u);
+                const u32 span = count * step;
+                u32 a = b0 + span - e * step;                          // hit count - e  (e = 0: wraps before the first access)
+#pragma unroll
+                for (u32 it = 0; it < 32u; ++it) {                     // lanes wrap around at it == e
+                    if (it == e) a -= span;
+                    cross(a, mask);
                     a += step;
-                };
-                u32 it = 0;
-                for (; it < 31u; ++it) guarded();                       // staggered start
-                if (H > 33u) {                                          // steady state: all 32 lanes inside the tile
-#pragma unroll 4
-                    for (; it + 2u < H; ++it) {
-                        cross(a, mask);
-                        a += step;
-                    }
                 }
-                for (; it < n_it; ++it) guarded();                      // staggered end
+#pragma unroll 4
+                for (u32 it = 32u; it + 1u < H; ++it) {                // steady state: hits e.. of every lane, conflict free
+                    cross(a, mask);
+                    a += step;
+                }
+#pragma unroll
+                for (u32 it = H - 1u; it <= H; ++it) {                 // lanes with count = H, H + 1; the others AND into the
+                    cross((it < count) ? a : ((a & 127u) | tile_bytes), mask);   // scratch word of the bank they would have used
+                    a += step;
+                }
             } else {
                 // sparse primes: one prime per lane, its 8 strands one after the other; byte stride p (odd), so the
                 // byte position inside the word advances by p & 3: the mask rotates by a per-prime constant.
@@ -209,30 +216,44 @@ __global__ void __launch_bounds__(THREADS, (THREADS <= 768) ? 2 : 1) k_sieve(con
                     s0 = __ldg(reinterpret_cast<const uint4*>(P.base_strand) + 2u * i);
                     s1 = __ldg(reinterpret_cast<const uint4*>(P.base_strand) + 2u * i + 1u);
                 }
-                const u32 p_lo = __shfl_sync(0xFFFFFFFFu, p, 0);
-                const u32 p_hi = __shfl_sync(0xFFFFFFFFu, p, n_on - 1u);
-                const u32 U = tile_bytes / p_hi;
-                const u32 n_uni = (U > 1u) ? U - 1u : 0u;
-                const u32 n_rag = (tile_bytes - 1u) / p_lo + 1u - n_uni;
+                const u32 geo = __ldg(P.batch_geo + (item - n_dense));   // host-staged: n_uni | n_rag << 16 (uniform load)
+                const u32 n_uni = geo & 0xFFFFu, n_rag = geo >> 16;
                 const u32 cbs[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
                 const u32 r = on ? tile_mod(B0, p, inv, wide) : 0u;
                 const u32 rot = (p & 3u) << 3;
+                if (n_uni == 0u && n_rag <= 2u) {
+                    // large primes (p > tile/2): at most two hits per strand -- straight-line code
+                    const bool two = n_rag == 2u;
 #pragma unroll
-                for (u32 j = 0; j < 8; ++j) {
-                    const u32 cb = cbs[j];
-                    u32 x = first_hit(p, cb & 0xFFFFFFu, r, j == 0, B0);
-                    u32 mask = ~(1u << (((x & 3u) << 3) + (cb >> 24)));
-#pragma unroll 4
-                    for (u32 k = 0; k < n_uni; ++k) {
-                        cross(x & ~3u, mask);
-                        x += p;
-                        mask = __funnelshift_l(mask, mask, rot);
-                    }
-#pragma unroll 1
-                    for (u32 k = 0; k < n_rag; ++k) {
+                    for (u32 j = 0; j < 8; ++j) {
+                        const u32 cb = cbs[j];
+                        u32 x = first_hit(p, cb & 0xFFFFFFu, r, j == 0, B0);
+                        u32 mask = ~(1u << (((x & 3u) << 3) + (cb >> 24)));
                         cross((x < tile_bytes) ? (x & ~3u) : park, mask);
-                        x += p;
-                        mask = __funnelshift_l(mask, mask, rot);
+                        if (two) {
+                            x += p;
+                            mask = __funnelshift_l(mask, mask, rot);
+                            cross((x < tile_bytes) ? (x & ~3u) : park, mask);
+                        }
+                    }
+                } else {
+#pragma unroll
+                    for (u32 j = 0; j < 8; ++j) {
+                        const u32 cb = cbs[j];
+                        u32 x = first_hit(p, cb & 0xFFFFFFu, r, j == 0, B0);
+                        u32 mask = ~(1u << (((x & 3u) << 3) + (cb >> 24)));
+#pragma unroll 4
+                        for (u32 k = 0; k < n_uni; ++k) {
+                            cross(x & ~3u, mask);
+                            x += p;
+                            mask = __funnelshift_l(mask, mask, rot);
+                        }
+#pragma unroll 1
+                        for (u32 k = 0; k < n_rag; ++k) {
+                            cross((x < tile_bytes) ? (x & ~3u) : park, mask);
+                            x += p;
+                            mask = __funnelshift_l(mask, mask, rot);
+                        }
                     }
                 }
             }

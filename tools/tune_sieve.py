@@ -7,7 +7,7 @@ from pss_b200 import _lib
 
 HI = int(os.environ.get("TUNE_HI", 22801763490))
 rows = []
-grid = list(itertools.product([int(x) for x in os.environ.get("TUNE_TILES", "96,112").split(",")], [int(x) for x in os.environ.get("TUNE_THREADS", "512").split(",")], [4], [int(x) for x in os.environ.get("TUNE_DIVS", "64,128,256").split(",")]))
+grid = list(itertools.product([int(x) for x in os.environ.get("TUNE_TILES", "216,224").split(",")], [int(x) for x in os.environ.get("TUNE_THREADS", "1024").split(",")], [int(x) for x in os.environ.get("TUNE_NPAT", "4").split(",")], [int(x) for x in os.environ.get("TUNE_DIVS", "128,160").split(",")]))
 for tile_kb, thr, npat, wdiv in grid:
     os.environ.update(PSS_TILE_BYTES=str(tile_kb * 1024), PSS_SIEVE_THREADS=str(thr), PSS_NPAT=str(npat), PSS_WARP_WIDE_DIV=str(wdiv))
     try:
