@@ -291,8 +291,9 @@ def main():
             h.stats_reset()
             o = step()
             s = h.stats()
-            # N = 1: whole-query span on the launch stream (gaps included); N > 1: sum of the kernels' event times
-            dev.append(s["ms_span"] if (world == 1 and s.get("ms_span", 0.0) > 0.0) else s["ms_total_device"])
+            # whole-query span on the launch stream (gaps and, at N > 1, the waits on the peers' publishes included);
+            # only the host-driven NCCL exchange (PSS_EXCHANGE=nccl) falls back to the sum of the kernels' event times
+            dev.append(s["ms_span"] if s.get("ms_span", 0.0) > 0.0 else s["ms_total_device"])
             if collect is not None:
                 for k in kern:
                     collect[k] += s[k]

@@ -163,6 +163,32 @@ int pss_slice_sieve_sums(pss_handle* h, uint64_t lo, uint64_t hi_excl, uint32_t 
 int pss_slice_scan_bitmap(pss_handle* h, uint64_t n_first, const uint32_t* carry_in, const pss_search_args* args,
                           pss_search_result* res);
 
+/* ---- multi-GPU query with the exchange on the device (NVLink peer memory, one process per GPU).
+ *      Every rank owns a value slice [lo, hi).  The only data the ranks exchange is the per-slice (prime count,
+ *      sums) record and the per-rank outcome record; both travel as remote stores into mailboxes
+ *      that every rank maps through CUDA IPC, inside the rank's launch chain
+ *        sieve -> block sums -> column scan -> publish -> gather -> compare -> publish outcome -> gather outcomes
+ *      with ONE host synchronisation per query and no collective library call on the data path.
+ *      Set-up: every rank calls pss_peer_export, the handles are all-gathered by the caller (any transport:
+ *      torch.distributed in pss_b200.search), every rank calls pss_peer_connect.  pss_peer_search must then be
+ *      called by all ranks for every query, in the same order (the mailbox epoch counts queries). ------------- */
+#define PSS_IPC_HANDLE_BYTES 64
+#define PSS_MAX_PEERS 16
+typedef struct pss_peer_record {
+    uint64_t valid;          /* the rank compared at least one partial sum */
+    uint64_t n_first;        /* global index of the first prime of the rank's slice */
+    uint64_t scanned;        /* primes of the slice with index <= n_max */
+    uint64_t last_prime;     /* p_{n_max} if the slice holds n_max, else 0 */
+    uint64_t count;          /* primes in the slice */
+    uint64_t error;          /* device-side error flags of the rank (0 = ok) */
+    pss_power_result powers[PSS_MAX_POWER];
+} pss_peer_record;
+int pss_peer_export(pss_handle* h, void* ipc_handle_out /* PSS_IPC_HANDLE_BYTES */);
+int pss_peer_connect(pss_handle* h, int rank, int world, const void* ipc_handles /* world * PSS_IPC_HANDLE_BYTES, rank order */);
+/* records_out[r] = outcome of rank r (identical on every rank after the call); stats: this rank's device times */
+int pss_peer_search(pss_handle* h, uint64_t lo, uint64_t hi_excl, const pss_search_args* args,
+                    pss_peer_record* records_out /* world */, pss_stats* stats);
+
 /* ---- slice API: the multi-GPU decomposition (one handle per rank).  The per-slice state
  *      (prime_count, last_prime, {k: S_k}) is exactly IncrementalSumCache's
  *      (utils/sum_cache.py:58-79,104-141) -------------------------------------------------------- */

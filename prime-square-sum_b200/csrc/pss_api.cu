@@ -22,6 +22,7 @@
 
 #include "../../include/pss_b200.h"
 #include "pss_bscan.cuh"
+#include "pss_peer.cuh"
 #include "pss_scan.cuh"
 #include "pss_sieve.cuh"
 
@@ -47,6 +48,7 @@ struct MiscDev {   // small device-side block, one H2D / D2H per scan
     pss_power_result results[PSS_MAX_POWER];
     u32 carry[PSS_MAX_POWER * PSS_LIMBS];
     u64 last_prime;
+    u64 n_first;     // peer path: global index of the slice's first prime (written by k_peer_gather)
 };
 
 struct HostBack {   // pinned: asynchronous D2H targets of one query
@@ -110,6 +112,13 @@ struct pss_handle {
     DevBuf status, agg, incl, misc, prefix_out, user_vals, tri_buf;
     MiscDev* h_misc = nullptr;   // pinned
     HostBack* h_back = nullptr;  // pinned
+
+    // peer-memory exchange (pss_peer_*): own mailbox, mapped mailboxes of all ranks, query epoch
+    PeerBox* box_local = nullptr;
+    PeerBox* box[kMaxPeers] = {nullptr};
+    int peer_rank = -1, peer_world = 0;
+    u64 peer_epoch = 0;
+    PeerResult* h_peer_results = nullptr;   // pinned, kMaxPeers records
 
     cudaEvent_t ev[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     u64 launches = 0;
@@ -866,6 +875,32 @@ int bitmap_compare(pss_handle* h, u64 n_first, const u32* carry_in, const pss_se
     return PSS_OK;
 }
 
+// BScanParams of a compare launch over the bitmap left by sieve_range / bitmap_reduce
+void fill_compare_params(pss_handle* h, BScanParams& bp, const pss_search_args* a, u64 n_first) {
+    static const u32 kMasks[6] = {2u, 5u, 1u, 3u, 4u, 6u};
+    const bool multi = a->all_powers && a->power_max > 1;
+    const u32 K = a->power_max, np = n_powers_of(K, multi);
+    fill_bscan_common(h, bp);
+    bp.cols = static_cast<u64*>(h->cols.p);
+    bp.col_prefix = static_cast<const u64*>(h->col_prefix.p);
+    bp.n_first = n_first;
+    bp.n_min = a->n_min;
+    bp.n_max = a->n_max;
+    bp.cmp_mask = kMasks[a->cmp];
+    bp.exhaustive = h->compare_exhaustive ? 1u : 0u;
+    for (u32 i = 0; i < a->target_nlimbs && i < PSS_LIMBS; ++i) bp.target[i] = a->target[i];
+    for (u32 j = 0; j < np; ++j) {
+        const u32 w = (u32)sum_limbs((int)expo_of(K, multi, j));
+        for (u32 i = w; i < a->target_nlimbs; ++i)
+            if (a->target[i]) bp.target_over_mask |= (1u << j);
+    }
+    MiscDev* dm = static_cast<MiscDev*>(h->misc.p);
+    bp.carry_in = dm->carry;
+    bp.results = dm->results;
+    bp.last_prime_out = &dm->last_prime;
+    bp.error_flag = &dm->error_flag;
+}
+
 int check_handle(pss_handle* h) {
     if (!h) return fail(nullptr, PSS_EINVAL, "null handle");
     cudaError_t e = cudaSetDevice(h->device);
@@ -957,6 +992,10 @@ int pss_close(pss_handle* h) {
         if (p) cudaFree(p);
     if (h->h_misc) cudaFreeHost(h->h_misc);
     if (h->h_back) cudaFreeHost(h->h_back);
+    if (h->h_peer_results) cudaFreeHost(h->h_peer_results);
+    for (int r = 0; r < h->peer_world; ++r)
+        if (h->box[r] && h->box[r] != h->box_local) cudaIpcCloseMemHandle(h->box[r]);
+    if (h->box_local) cudaFree(h->box_local);
     for (auto& ev : h->ev)
         if (ev) cudaEventDestroy(ev);
     if (h->stream) cudaStreamDestroy(h->stream);
@@ -1239,6 +1278,167 @@ int pss_slice_scan_bitmap(pss_handle* h, uint64_t n_first, const uint32_t* carry
     memset(res, 0, sizeof *res);
     PSS_TRY(bitmap_compare(h, n_first, carry_in, a, res));
     fill_stats(h, &res->stats, before);
+    return PSS_OK;
+}
+
+int pss_peer_export(pss_handle* h, void* ipc_handle_out) {
+    PSS_TRY(check_handle(h));
+    if (!ipc_handle_out) return fail(h, PSS_EINVAL, "null output");
+    static_assert(sizeof(cudaIpcMemHandle_t) == PSS_IPC_HANDLE_BYTES, "IPC handle size");
+    static_assert(kMaxPeers == PSS_MAX_PEERS, "peer limit");
+    if (!h->box_local) {
+        CU_TRY(h, cudaMalloc(reinterpret_cast<void**>(&h->box_local), sizeof(PeerBox)));
+        CU_TRY(h, cudaMemset(h->box_local, 0, sizeof(PeerBox)));
+        CU_TRY(h, cudaMallocHost(reinterpret_cast<void**>(&h->h_peer_results), sizeof(PeerResult) * kMaxPeers));
+    }
+    cudaIpcMemHandle_t hd;
+    CU_TRY(h, cudaIpcGetMemHandle(&hd, h->box_local));
+    memcpy(ipc_handle_out, &hd, sizeof hd);
+    return PSS_OK;
+}
+
+int pss_peer_connect(pss_handle* h, int rank, int world, const void* ipc_handles) {
+    PSS_TRY(check_handle(h));
+    if (!h->box_local) return fail(h, PSS_EINVAL, "pss_peer_export must be called first");
+    if (world < 1 || world > kMaxPeers || rank < 0 || rank >= world) return fail(h, PSS_EINVAL, "invalid rank %d / world %d (max %d)", rank, world, kMaxPeers);
+    if (!ipc_handles) return fail(h, PSS_EINVAL, "null handles");
+    for (int r = 0; r < h->peer_world; ++r)
+        if (h->box[r] && h->box[r] != h->box_local) cudaIpcCloseMemHandle(h->box[r]);
+    h->peer_world = 0;
+    for (int r = 0; r < world; ++r) {
+        if (r == rank) {
+            h->box[r] = h->box_local;
+            continue;
+        }
+        cudaIpcMemHandle_t hd;
+        memcpy(&hd, static_cast<const char*>(ipc_handles) + (size_t)r * PSS_IPC_HANDLE_BYTES, sizeof hd);
+        void* ptr = nullptr;
+        cudaError_t e = cudaIpcOpenMemHandle(&ptr, hd, cudaIpcMemLazyEnablePeerAccess);
+        if (e != cudaSuccess) {
+            cudaGetLastError();
+            return fail(h, PSS_ENODEV, "cannot map the mailbox of rank %d over peer memory: %s", r, cudaGetErrorString(e));
+        }
+        h->box[r] = static_cast<PeerBox*>(ptr);
+    }
+    h->peer_rank = rank;
+    h->peer_world = world;
+    h->peer_epoch = 0;
+    CU_TRY(h, cudaMemset(h->box_local, 0, sizeof(PeerBox)));
+    CU_TRY(h, cudaDeviceSynchronize());
+    return PSS_OK;
+}
+
+int pss_peer_search(pss_handle* h, uint64_t lo, uint64_t hi_excl, const pss_search_args* a, pss_peer_record* records_out, pss_stats* stats) {
+    PSS_TRY(check_handle(h));
+    if (!records_out) return fail(h, PSS_EINVAL, "null output");
+    pss_search_result dummy;
+    PSS_TRY(validate_search(h, a, &dummy));
+    if (h->peer_world < 1) return fail(h, PSS_EINVAL, "pss_peer_connect must be called first");
+    if (h->search_path == 1) return fail(h, PSS_EINVAL, "the peer path runs on the fused search path only");
+    const pss_stats before = stats_snapshot(h);
+    const bool multi = a->all_powers && a->power_max > 1;
+    const u32 K = a->power_max, np = n_powers_of(K, multi);
+    const u32 world = (u32)h->peer_world, rank = (u32)h->peer_rank;
+    const u64 epoch = ++h->peer_epoch;
+    const long long watchdog = 4000000000ll;   // ~2 s at 1.97 GHz
+
+    // ---- phase A: sieve + block sums + column scan of this rank's slice (enqueued, not synchronised)
+    PSS_TRY(sieve_range(h, lo, hi_excl, true));
+    const bool sv_was_pending = h->sv_pending;
+    PSS_TRY(bitmap_reduce(h, K, multi, true));
+    const bool has_tiles = h->bs_n_tiles > 0;
+    if (!sv_was_pending) CU_TRY(h, cudaEventRecord(h->ev[0], h->stream));   // empty slice: the chain starts here
+
+    MiscDev* hm = h->h_misc;
+    MiscDev* dm = static_cast<MiscDev*>(h->misc.p);
+    memset(hm, 0, sizeof(MiscDev));
+    for (u32 j = 0; j < np; ++j) {
+        hm->results[j].power = expo_of(K, multi, j);
+        hm->results[j].first_match_n = ~0ull;
+    }
+    CU_TRY(h, cudaMemcpyAsync(dm, hm, sizeof(MiscDev), cudaMemcpyHostToDevice, h->stream));
+
+    // ---- the exchange: publish the slice totals into every rank's mailbox, gather the lower ranks' totals
+    PeerPublishParams pp;
+    memset(&pp, 0, sizeof pp);
+    pp.col_prefix = has_tiles ? static_cast<const u64*>(h->col_prefix.p) : nullptr;
+    pp.col_stride = h->bs_col_stride;
+    pp.n_tiles = h->bs_n_tiles;
+    pp.np = np;
+    for (u32 j = 0; j < np; ++j) pp.width[j] = (u32)sum_limbs((int)expo_of(K, multi, j));
+    for (u32 r = 0; r < world; ++r) pp.box[r] = h->box[r];
+    pp.world = world;
+    pp.rank = rank;
+    pp.epoch = epoch;
+    k_peer_publish<<<1, 32, 0, h->stream>>>(pp);
+    CU_TRY(h, cudaGetLastError());
+    PeerGatherParams pg;
+    memset(&pg, 0, sizeof pg);
+    pg.box = h->box_local;
+    pg.world = world; pg.rank = rank; pg.np = np;
+    pg.epoch = epoch;
+    pg.watchdog = watchdog;
+    pg.n_first_out = &dm->n_first;
+    pg.carry_out = dm->carry;
+    pg.error_flag = &dm->error_flag;
+    k_peer_gather<<<1, 32, 0, h->stream>>>(pg);
+    CU_TRY(h, cudaGetLastError());
+    h->launches += 2;
+
+    // ---- phase B: compare, seeded from device memory (n_first, carry)
+    CU_TRY(h, cudaEventRecord(h->ev[6], h->stream));
+    if (has_tiles) {
+        BScanParams bp;
+        fill_compare_params(h, bp, a, 0);
+        bp.n_first_dev = &dm->n_first;
+        PSS_TRY(launch_bscan<kBsCompare>(h, bp, K, multi));
+    }
+    CU_TRY(h, cudaEventRecord(h->ev[7], h->stream));
+
+    // ---- outcome records: publish to every rank, wait for every rank's
+    PeerResultParams pr;
+    memset(&pr, 0, sizeof pr);
+    for (u32 r = 0; r < world; ++r) pr.box[r] = h->box[r];
+    pr.world = world; pr.rank = rank; pr.np = np;
+    pr.epoch = epoch;
+    pr.n_max = a->n_max;
+    pr.n_first = &dm->n_first;
+    pr.carry = dm->carry;
+    pr.results = dm->results;
+    pr.last_prime = &dm->last_prime;
+    pr.error_flag = &dm->error_flag;
+    pr.col_prefix = pp.col_prefix;
+    pr.col_stride = pp.col_stride;
+    pr.n_tiles = pp.n_tiles;
+    for (u32 j = 0; j < np; ++j) pr.width[j] = pp.width[j];
+    k_peer_publish_result<<<1, 256, 0, h->stream>>>(pr);
+    CU_TRY(h, cudaGetLastError());
+    k_peer_gather_results<<<1, 32, 0, h->stream>>>(h->box_local, world, epoch, watchdog, &dm->error_flag);
+    CU_TRY(h, cudaGetLastError());
+    h->launches += 2;
+    CU_TRY(h, cudaMemcpyAsync(h->h_peer_results, &h->box_local->r[epoch & 1ull][0], sizeof(PeerResult) * world, cudaMemcpyDeviceToHost, h->stream));
+    CU_TRY(h, cudaMemcpyAsync(hm, dm, sizeof(MiscDev), cudaMemcpyDeviceToHost, h->stream));
+    cudaEvent_t ev_end = h->ev[3];   // compaction event, unused on this path
+    CU_TRY(h, cudaEventRecord(ev_end, h->stream));
+    CU_TRY(h, cudaStreamSynchronize(h->stream));
+
+    sieve_finish(h);
+    PSS_TRY(reduce_finish(h));
+    h->acc.ms_power_scan += ev_ms(h, 6, 7);
+    h->acc.ms_bitmap_compare += ev_ms(h, 6, 7);
+    h->acc.ms_span += ev_ms(h, 0, 3);     // first launch -> all ranks' outcomes gathered (waits on peers included)
+    if (hm->error_flag) return fail(h, PSS_EINTERNAL, "peer exchange failed on the device (flags 0x%x): a rank did not publish in time", hm->error_flag);
+    u64 scanned_here = 0;
+    for (u32 r = 0; r < world; ++r) {
+        const PeerResult& s = h->h_peer_results[r];
+        pss_peer_record& o = records_out[r];
+        o.valid = s.valid; o.n_first = s.n_first; o.scanned = s.scanned; o.last_prime = s.last_prime; o.count = s.count; o.error = s.error;
+        memcpy(o.powers, s.powers, sizeof o.powers);
+        if (s.error) return fail(h, PSS_EINTERNAL, "rank %u reported device error flags 0x%llx", r, (unsigned long long)s.error);
+        if (r == rank) scanned_here = s.scanned;
+    }
+    h->acc.primes += scanned_here;
+    if (stats) fill_stats(h, stats, before);
     return PSS_OK;
 }
 

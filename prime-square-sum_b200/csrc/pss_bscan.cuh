@@ -45,6 +45,7 @@ struct BScanParams {
     u64 thread_stride;
     // compare mode
     u64 n_first;             // global 1-based index of the slice's first prime
+    const u64* n_first_dev;  // if set: read it from device memory instead (written by k_peer_gather of the same stream)
     u64 n_min, n_max;
     u32 cmp_mask, target_over_mask;
     u32 exhaustive;          // 1: walk every prime and form every S_k(n); 0: prune warp tiles / threads whose sum interval
@@ -284,12 +285,13 @@ __global__ void __launch_bounds__(kBsThreads, bs_min_blocks<K, MULTI>()) k_bitma
     my_warp_words[lane * PAD + WPT] = 0u;        // sentinel word of this thread's row (never overwritten)
     const u64 n_warp_tiles = (u64)P.n_tiles * NWARP;
     const u64 warp_stride = (u64)gridDim.x * NWARP;
+    const u64 n_first = (MODE != kBsReduce && P.n_first_dev) ? *P.n_first_dev : P.n_first;
 
     for (u64 wt = (u64)blockIdx.x * NWARP + warp; wt < n_warp_tiles; wt += warp_stride) {
         const u32 tile = (u32)(wt / NWARP);
         const u32 wit = (u32)(wt % NWARP);          // warp index inside the scan tile
         if constexpr (MODE != kBsReduce) {
-            if (P.n_first + P.col_prefix[tile] > P.n_max) break;   // prefixes are monotone in tile
+            if (n_first + P.col_prefix[tile] > P.n_max) break;   // prefixes are monotone in tile
         }
         const u64 word0 = wt * WARP_WORDS;
         // ---- warp-local staging: coalesced uint4 loads -> padded blocked layout, bit-reversed
@@ -369,7 +371,7 @@ __global__ void __launch_bounds__(kBsThreads, bs_min_blocks<K, MULTI>()) k_bitma
                 OpAdd op{wpre, v};
                 for_each_power<0, Lay>(op);
             }
-            const u64 tile_n0 = P.n_first + P.col_prefix[tile];
+            const u64 tile_n0 = n_first + P.col_prefix[tile];
             // window bounds in tile-local indices (a tile holds < 2^20 primes, so saturating to u32 is exact)
             const u32 lmin = (P.n_min > tile_n0) ? (u32)min(P.n_min - tile_n0, (u64)0xFFFFFFFFull) : 0u;
             const u32 lmax = (u32)min(P.n_max - tile_n0, (u64)0xFFFFFFFEull);   // n_max >= tile_n0 (checked above)

@@ -46,6 +46,18 @@ class Stats(ctypes.Structure):
     ]
 
 
+PSS_IPC_HANDLE_BYTES = 64
+PSS_MAX_PEERS = 16
+
+
+class PeerRecord(ctypes.Structure):
+    """pss_peer_record: the outcome of one rank of a peer-memory query"""
+    _fields_ = [
+        ("valid", u64), ("n_first", u64), ("scanned", u64), ("last_prime", u64), ("count", u64), ("error", u64),
+        ("powers", PowerResult * PSS_MAX_POWER),
+    ]
+
+
 class SearchArgs(ctypes.Structure):
     _fields_ = [
         ("n_min", u64), ("n_max", u64), ("power_max", u32), ("all_powers", u32), ("cmp", u32),
@@ -67,7 +79,7 @@ EXPORTS = [
     "pss_slice_sieve", "pss_slice_reduce", "pss_slice_scan", "pss_slice_prefix_sums", "pss_slice_primes",
     "pss_slice_device_buffer", "pss_nth_prime_upper", "pss_stats_reset", "pss_stats_get",
     "pss_set_search_path", "pss_slice_sieve_sums", "pss_slice_scan_bitmap", "pss_search_tri",
-    "pss_set_compare_mode",
+    "pss_set_compare_mode", "pss_peer_export", "pss_peer_connect", "pss_peer_search",
 ]
 
 _cdll = None
@@ -109,6 +121,9 @@ def load_library() -> ctypes.CDLL:
     L.pss_search_tri.argtypes = [H, u64, u64, u32, u64, u64, pu64, u32, pu32, ctypes.POINTER(Stats)]
     L.pss_set_search_path.argtypes = [H, ctypes.c_int]
     L.pss_set_compare_mode.argtypes = [H, ctypes.c_int]
+    L.pss_peer_export.argtypes = [H, ctypes.c_void_p]
+    L.pss_peer_connect.argtypes = [H, ctypes.c_int, ctypes.c_int, ctypes.c_void_p]
+    L.pss_peer_search.argtypes = [H, u64, u64, ctypes.POINTER(SearchArgs), ctypes.POINTER(PeerRecord), ctypes.POINTER(Stats)]
     L.pss_slice_sieve_sums.argtypes = [H, u64, u64, u32, u32, pu64, pu32]
     L.pss_slice_scan_bitmap.argtypes = [H, u64, pu32, ctypes.POINTER(SearchArgs), ctypes.POINTER(SearchResult)]
     L.pss_stats_reset.argtypes = [H]
@@ -325,6 +340,31 @@ class Handle:
     def set_compare_mode(self, exhaustive: bool):
         """fused compare pass: False (default) = interval pruning, True = walk every prime / form every S_k(n)"""
         self._check(self._L.pss_set_compare_mode(self._h, 1 if exhaustive else 0))
+
+    # -- peer-memory exchange (multi-GPU query without host / NCCL on the data path)
+    def peer_export(self) -> bytes:
+        """allocate this rank's mailbox and return its CUDA IPC handle (64 bytes) for the all-gather at set-up"""
+        buf = ctypes.create_string_buffer(PSS_IPC_HANDLE_BYTES)
+        self._check(self._L.pss_peer_export(self._h, buf))
+        return buf.raw
+
+    def peer_connect(self, rank: int, world: int, handles: Sequence[bytes]):
+        """map every rank's mailbox (handles in rank order); call a barrier afterwards, before the first query"""
+        if len(handles) != world or any(len(b) != PSS_IPC_HANDLE_BYTES for b in handles):
+            raise ValueError("need one 64-byte IPC handle per rank")
+        blob = ctypes.create_string_buffer(b"".join(handles), PSS_IPC_HANDLE_BYTES * world)
+        self._check(self._L.pss_peer_connect(self._h, rank, world, blob))
+        self.peer_world, self.peer_rank = world, rank
+
+    def peer_search(self, lo: int, hi_excl: int, n_min: int, n_max: int, power_max: int, target: int, op: str = "==",
+                    all_powers: bool = False):
+        """this rank's part of a multi-GPU query over its value slice [lo, hi); returns (records of all ranks, stats)"""
+        a, keep = self._make_args(n_min, n_max, power_max, all_powers, op, target)
+        recs = (PeerRecord * self.peer_world)()
+        st = Stats()
+        self._check(self._L.pss_peer_search(self._h, lo, hi_excl, ctypes.byref(a), recs, ctypes.byref(st)))
+        del keep
+        return recs, stats_to_dict(st)
 
     def slice_sieve_sums(self, lo: int, hi_excl: int, power_max: int, all_powers: bool = False):
         """fused phase A: (count, [sum p^k per power record]) of the primes in [lo, hi)"""

@@ -285,6 +285,8 @@ def distributed_search(target: int, n_max: int, power: int = 2, n_min: int = 1, 
     hi = h.nth_prime_upper(n_max) + 1
     lo_g, hi_g = partition_range(hi, world)[rank]
     np_ = _np(power, all_powers)
+    if gather is None and _peer_exchange_enabled(group):
+        return _peer_search(h, group, rank, world, lo_g, hi_g, target, n_max, power, n_min, op, all_powers, np_)
     # fused phase A: sieve + per-tile sums (no u64 prime buffer); leaves the slice's bitmap resident
     count_g, sums_g = h.slice_sieve_sums(lo_g, hi_g, power, all_powers)
     t1 = time.perf_counter()
@@ -331,6 +333,60 @@ def distributed_search(target: int, n_max: int, power: int = 2, n_min: int = 1, 
     t4 = time.perf_counter()
     merged.stats["host_ms"] = {"sieve_sums": (t1 - t0) * 1e3, "exchange": (t2 - t1) * 1e3, "scan": (t3 - t2) * 1e3,
                                "merge": (t4 - t3) * 1e3}
+    return merged
+
+
+def _peer_exchange_enabled(group) -> bool:
+    """the device-side exchange needs one CUDA process per GPU on one node (CUDA IPC over NVLink); PSS_EXCHANGE=nccl
+    selects the host-driven NCCL all-gathers instead"""
+    import os
+    import torch.distributed as dist
+    if os.environ.get("PSS_EXCHANGE", "peer").lower() != "peer":
+        return False
+    try:
+        return dist.get_backend(group) == "nccl" and dist.get_world_size(group) <= _lib.PSS_MAX_PEERS
+    except Exception:
+        return False
+
+
+def _peer_setup(h: "_lib.Handle", group, rank: int, world: int):
+    """once per handle: all-gather the mailbox IPC handles (torch.distributed plumbing), map them, barrier"""
+    import torch
+    import torch.distributed as dist
+    if getattr(h, "_peer_group_id", None) == (id(group), world, rank):
+        return
+    mine = torch.frombuffer(bytearray(h.peer_export()), dtype=torch.uint8).to(torch.device("cuda", torch.cuda.current_device()))
+    parts = [torch.empty_like(mine) for _ in range(world)]
+    dist.all_gather(parts, mine, group=group)
+    h.peer_connect(rank, world, [bytes(t.cpu().numpy().tobytes()) for t in parts])
+    dist.barrier(group=group)      # nobody publishes before every mailbox is mapped and zeroed
+    torch.cuda.synchronize()
+    h._peer_group_id = (id(group), world, rank)
+
+
+def _peer_search(h, group, rank, world, lo_g, hi_g, target, n_max, power, n_min, op, all_powers, np_) -> SearchOutcome:
+    """multi-GPU query with the exchange on the device: one C call, one host synchronisation per rank"""
+    _peer_setup(h, group, rank, world)
+    recs, stats = h.peer_search(lo_g, hi_g, n_min, n_max, power, target, op, all_powers)
+    if sum(int(r.count) for r in recs) < n_max:
+        raise RuntimeError("prime count bound violated")
+    outs = []
+    for g, r in enumerate(recs):
+        if not r.valid:
+            outs.append(None)
+            continue
+        powers = []
+        for j in range(np_):
+            q = r.powers[j]
+            powers.append(PowerOutcome(
+                power=int(q.power), match_count=int(q.match_count), first_match_n=int(q.first_match_n),
+                last_match_n=int(q.last_match_n), cross_n=int(q.cross_n), cross_prime=int(q.cross_prime),
+                sum_at_cross=_lib.limbs_to_int(q.sum_at_cross), sum_before_cross=_lib.limbs_to_int(q.sum_before_cross),
+                final_sum=_lib.limbs_to_int(q.final_sum)))
+        outs.append(SearchOutcome(n_min, n_max, op, target, int(r.last_prime), powers, dict(stats) if g == rank else {}))
+    merged = merge_outcomes(outs, n_min, n_max, op, target)
+    merged.stats = dict(stats)
+    merged.stats["exchange"] = "peer memory (NVLink, device-side)"
     return merged
 
 
