@@ -338,7 +338,9 @@ def main():
     else:
         wall_ms = wall * 1e3
     if os.environ.get("PSS_TRACE") and world > 1:
-        print(f"[trace rank {rank}] host phases of the last step (ms): {out.stats.get('host_ms')}", file=sys.stderr)
+        print(f"[trace rank {rank}] per-step ms: " + ", ".join(f"{k}={v / args.steps:.3f}" for k, v in kern.items()) +
+              f", span={sum(per_step_dev) / args.steps:.3f}, wall={wall * 1e3 / args.steps:.3f}; host phases: {out.stats.get('host_ms')}",
+              file=sys.stderr)
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()

@@ -14,6 +14,7 @@ its slice with that carry.  Nothing else crosses NVLink.
 """
 from __future__ import annotations
 
+import functools
 import math
 from dataclasses import dataclass, field
 from typing import Dict, Iterator, List, Optional, Sequence, Tuple
@@ -190,20 +191,25 @@ def li(x: float) -> float:
     return x / lx * (1.0 + s)
 
 
-# Cost model behind the slice cuts (measured on B200, profiles/r01): the scan passes cost is proportional to
+# Cost model behind the slice cuts (measured on B200, profiles/r01): the block-sum and compare passes cost is proportional to
 # the slice's prime count, the sieve's to its width times a slowly growing per-integer factor (more base
-# primes are active in higher tiles: ~ (x/N)^0.12); for the whole C3 range sieve : scans = 0.635 : 1.
-SIEVE_WEIGHT = 0.635
+# primes are active in higher tiles: ~ (x/N)^0.12); for the whole C3 range sieve : scans = 3.7 : 1 (2.13 ms : 0.57 ms).
+SIEVE_WEIGHT = 3.7
 SIEVE_EXPONENT = 0.12
 
 
 def partition_range(hi_excl: int, parts: int, lo: int = 0, sieve_weight: float = SIEVE_WEIGHT,
                     sieve_exponent: float = SIEVE_EXPONENT) -> List[Tuple[int, int]]:
+    return list(_partition_range(int(hi_excl), int(parts), int(lo), float(sieve_weight), float(sieve_exponent)))
+
+
+@functools.lru_cache(maxsize=64)
+def _partition_range(hi_excl: int, parts: int, lo: int, sieve_weight: float, sieve_exponent: float) -> Tuple[Tuple[int, int], ...]:
     """Cut [lo, hi_excl) into `parts` contiguous slices of ~equal estimated device time
     (sieve_weight = 0: equal prime counts); interior cuts are multiples of 480 (16 bitmap bytes) so every
     slice starts on a 16-byte aligned bitmap byte."""
     if parts <= 1 or hi_excl - lo < 480 * parts * 4:
-        return [(lo, hi_excl)] + [(hi_excl, hi_excl)] * (parts - 1)
+        return tuple([(lo, hi_excl)] + [(hi_excl, hi_excl)] * (parts - 1))
     pi_est = li(hi_excl)
 
     def cost(x: float) -> float:
@@ -223,7 +229,7 @@ def partition_range(hi_excl: int, parts: int, lo: int = 0, sieve_weight: float =
         c = int(b) // 480 * 480
         cuts.append(min(max(c, cuts[-1]), hi_excl))
     cuts.append(hi_excl)
-    return [(cuts[i], cuts[i + 1]) for i in range(parts)]
+    return tuple((cuts[i], cuts[i + 1]) for i in range(parts))
 
 
 def combine_slices(counts: Sequence[int], sums: Sequence[Sequence[int]], rank: int) -> Tuple[int, List[int]]:
