@@ -73,7 +73,8 @@ struct pss_handle {
     u32 warp_wide_div = 160;    // p < tile_bytes / div -> dense (one warp per prime, skewed conflict-free lanes), else one lane per prime
     int search_path = 0;       // 0: fused (scan straight from the bitmap), 1: materialised u64 primes
     int compare_exhaustive = 0;  // 1: the compare pass walks every prime; 0: interval pruning (PSS_COMPARE_EXHAUSTIVE / pss_set_compare_mode)
-    int reduce_moments = 1;    // k = 2 reduce pass from per-byte moment tables (0: walk every prime; PSS_REDUCE_MOMENTS)
+    int reduce_moments = 1;    // block sums from moments (k = 2: per-byte tables; other k <= 5: per-prime small moments);
+                               // 0: multi-limb power chain per prime (PSS_REDUCE_MOMENTS)
 
     // patterns
     uint4* d_pat[kMaxPatterns] = {nullptr, nullptr, nullptr, nullptr};
@@ -763,6 +764,7 @@ int bitmap_reduce(pss_handle* h, u32 K, bool multi, bool defer_sync = false) {
         CU_TRY(h, cudaGetLastError());
         h->launches++;
     } else {
+        bp.reduce_chain = h->reduce_moments ? 0u : 1u;
         PSS_TRY(launch_bscan<kBsReduce>(h, bp, K, multi));
     }
     k_scan_columns<<<ncols, 1024, 0, h->stream>>>(bp.cols, static_cast<u64*>(h->col_prefix.p), bp.n_tiles, bp.col_stride);

@@ -48,6 +48,7 @@ struct BScanParams {
     const u64* n_first_dev;  // if set: read it from device memory instead (written by k_peer_gather of the same stream)
     u64 n_min, n_max;
     u32 cmp_mask, target_over_mask;
+    u32 reduce_chain;        // reduce pass: 1 = multi-limb power chain per prime, 0 = small moments + one expansion per thread (k <= 5)
     u32 exhaustive;          // 1: walk every prime and form every S_k(n); 0: prune warp tiles / threads whose sum interval
                              // (S_before, S_after] cannot contain the target (identical results: S is strictly increasing)
     u32 target[PSS_LIMBS];
@@ -124,6 +125,91 @@ struct BsAccFn {
         return true;
     }
 };
+
+// ---- block sums for k <= 5 from small moments -----------------------------------------------------------------
+// A thread's primes lie in [B, B + 2880).  With o = p - B (12 bits) the thread accumulates M_j = sum o^j, j <= K, in
+// machine words (M_1: 32 bit, M_2..M_4: 64 bit, M_5: 96 bit; 768 set bits * 2880^5 < 2^68) -- about 12 integer
+// instructions per prime for K = 5 instead of the ~100 of the multi-limb chain p, p^2, .., p^5 -- and expands once:
+//     S_k = sum_p (B + o)^k = sum_j C(k,j) B^(k-j) M_j      evaluated by Horner in B with multi-limb arithmetic.
+template <int K>
+struct BsMomFn {
+    u32 base_lo;
+    u32 m1;
+    u64 m2, m3, m4, m5lo;
+    u32 m5hi;
+    __device__ __forceinline__ bool operator()(u32 plo, u32 /*phi*/) {
+        const u32 o = plo - base_lo;              // < 2880 (exact also across a 2^32 boundary)
+        m1 += o;
+        if constexpr (K >= 2) {
+            const u32 o2 = o * o;                 // < 2^23
+            m2 += (u64)o2;
+            if constexpr (K >= 3) m3 += (u64)o2 * o;
+            if constexpr (K >= 4) {
+                const u64 o4 = (u64)o2 * o2;      // < 2^46
+                m4 += o4;
+                if constexpr (K >= 5) {
+                    const u64 t = o4 * o;         // < 2^58
+                    const u64 s = m5lo + t;
+                    m5hi += (s < t) ? 1u : 0u;
+                    m5lo = s;
+                }
+            }
+        }
+        return true;
+    }
+};
+
+PSS_HD constexpr u32 binom(int n, int k) {
+    u32 r = 1;
+    for (int i = 1; i <= k; ++i) r = r * (u32)(n - k + i) / (u32)i;
+    return r;
+}
+
+// out[0..W) = sum_j C(k,j) B^(k-j) M_j  (Horner in B; W = sum_limbs(k) limbs, nothing can overflow them)
+template <int KK, int K>
+__device__ __forceinline__ void expand_moments(u32* out, const BsMomFn<K>& f, u32 m0, u32 blo, u32 bhi) {
+    constexpr int W = sum_limbs(KK);
+    Big<W> a;
+    big_zero(a);
+    a.v[0] = m0;
+#pragma unroll
+    for (int j = 1; j <= KK; ++j) {
+        Big<W> nx;
+        big_mul_p<W, W>(nx, a, blo, bhi);
+        // t = C(KK, j) * M_j  (at most 72 bits)
+        u64 lo = 0;
+        u32 hi = 0;
+        if (j == 1) lo = f.m1;
+        if (j == 2) lo = f.m2;
+        if (j == 3) lo = f.m3;
+        if (j == 4) lo = f.m4;
+        if (j == 5) { lo = f.m5lo; hi = f.m5hi; }
+        const u32 c = binom(KK, j);
+        const u64 p0 = (lo & 0xFFFFFFFFull) * c;
+        const u64 p1 = (lo >> 32) * c + (p0 >> 32);
+        const u64 p2 = (u64)hi * c + (p1 >> 32);
+        const u32 t[3] = {(u32)p0, (u32)p1, (u32)p2};
+        u64 cy = 0;
+#pragma unroll
+        for (int i = 0; i < W; ++i) {
+            const u64 v = (u64)nx.v[i] + (i < 3 ? (u64)t[i] : 0ull) + cy;
+            a.v[i] = (u32)v;
+            cy = v >> 32;
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < W; ++i) out[i] = a.v[i];
+}
+
+template <int J, int K, bool MULTI>
+__device__ __forceinline__ void expand_all(u32* acc, const BsMomFn<K>& f, u32 m0, u32 blo, u32 bhi) {
+    using Lay = Layout<K, MULTI>;
+    if constexpr (J < Lay::NP) {
+        constexpr int KK = MULTI ? J + 1 : K;
+        expand_moments<KK, K>(acc + Lay::offset(J), f, m0, blo, bhi);
+        expand_all<J + 1, K, MULTI>(acc, f, m0, blo, bhi);
+    }
+}
 
 // most-significant-limb-first three-way compare (the outcome is almost always decided by the top limb)
 template <int W>
@@ -325,11 +411,19 @@ __global__ void __launch_bounds__(kBsThreads, bs_min_blocks<K, MULTI>()) k_bitma
 #pragma unroll
             for (int i = 0; i < WPT; ++i) cnt += __popc(my_words[i]);
             BsAccFn<K, MULTI> fn{acc};
+            bool chain = true;
+            if constexpr (K <= 5) chain = P.reduce_chain != 0;
+            if (chain) {
+                walk_words(my_words, value_base, fn);               // per prime: p, p^2, .., p^K in multi-limb arithmetic
+            } else if constexpr (K <= 5) {
+                BsMomFn<K> mf{(u32)value_base, 0u, 0ull, 0ull, 0ull, 0ull, 0u};
+                walk_words(my_words, value_base, mf);               // per prime: small moments of p - B
+                expand_all<0, K, MULTI>(acc, mf, cnt, (u32)value_base, (u32)(value_base >> 32));
+            }
             if (has_small) {
                 for (u32 i = 0; i < P.n_small; ++i) fn((u32)P.small_primes[i], 0u);
                 cnt += P.n_small;
             }
-            walk_words(my_words, value_base, fn);
             bs_reduce_tail<K, MULTI>(P, acc, cnt, wt, tile, lane);
         } else {
             // ---- warp prefix (uniform) = carry-in + normalised deferred-carry tile prefix + earlier warps of the scan tile

@@ -298,8 +298,9 @@ def test_fused_tile_boundaries(handle, orc):
 
 
 def test_moment_reduce_matches_walk_and_oracle(orc):
-    """k = 2 reduce pass from the per-byte moment tables (default) against the per-prime walking reduce and the
-    oracle: slice counts and slice sums on ragged ranges (range edges inside a byte, below 7, around 2^32)"""
+    """block sums from moments (default: k = 2 per-byte tables, other k <= 5 per-prime small moments + one binomial
+    expansion per thread) against the per-prime multi-limb power chain and the oracle: slice counts and slice sums on
+    ragged ranges (range edges inside a byte, below 7, around 2^32, near 2^40)"""
     from pss_b200 import _lib
     os.environ["PSS_REDUCE_MOMENTS"] = "0"
     try:
@@ -307,13 +308,17 @@ def test_moment_reduce_matches_walk_and_oracle(orc):
     finally:
         del os.environ["PSS_REDUCE_MOMENTS"]
     h_mom = _lib.Handle(-1)
-    for lo, hi in [(0, 2), (0, 8), (0, 100), (3, 2881), (0, 3_000_000), (2879, 2 * 737280 + 17), (10 ** 9 + 7, 10 ** 9 + 4_000_001),
-                   (2 ** 32 - 10 ** 6, 2 ** 32 + 10 ** 6), (22_800_000_000, 22_801_763_490), (2 ** 39, 2 ** 39 + 3_000_000)]:
-        exp_p = orc.c_primes_range(lo, hi)
-        exp = orc.c_power_sums(exp_p, [2])
-        a = h_mom.slice_sieve_sums(lo, hi, 2, False)
-        b = h_walk.slice_sieve_sums(lo, hi, 2, False)
-        assert a == b == (len(exp_p), exp), (lo, hi)
+    ranges = [(0, 2), (0, 8), (0, 100), (3, 2881), (0, 3_000_000), (2879, 2 * 737280 + 17), (10 ** 9 + 7, 10 ** 9 + 4_000_001),
+              (2 ** 32 - 10 ** 6, 2 ** 32 + 10 ** 6), (22_800_000_000, 22_801_763_490), (2 ** 39, 2 ** 39 + 3_000_000),
+              (2 ** 40 - 2_000_000, 2 ** 40)]
+    for power, multi in [(2, False), (1, False), (3, False), (4, False), (5, False), (2, True), (3, True), (5, True), (6, False), (6, True)]:
+        powers = list(range(1, power + 1)) if multi else [power]
+        for lo, hi in ranges:
+            exp_p = orc.c_primes_range(lo, hi)
+            exp = orc.c_power_sums(exp_p, powers)
+            a = h_mom.slice_sieve_sums(lo, hi, power, multi)
+            b = h_walk.slice_sieve_sums(lo, hi, power, multi)
+            assert a == b == (len(exp_p), exp), (power, multi, lo, hi)
     h_walk.close()
     h_mom.close()
 
@@ -462,3 +467,22 @@ def test_at_scale_c4_c5(handle, golden):
     out = search.search(T, 10 ** 9, power=5, n_min=5 * 10 ** 7, all_powers=True)
     assert [str(p.final_sum) for p in out.powers] == [row["sums"][str(k)] for k in range(1, 6)]
     assert out.first() is None
+
+
+def test_prime_io_export_and_file_power_sum(handle, orc, tmp_path):
+    """.npy files either side of the path (reference: utils/prime_io.py:74-136): device export in value windows ==
+    oracle primes; power sums over a file in index windows == oracle sums"""
+    from pss_b200 import prime_io
+    f = tmp_path / "primes.npy"
+    n = prime_io.export_primes(f, n=300_000, window_values=1_000_000)
+    exp = orc.c_first_n_primes(300_000)
+    got = np.load(f)
+    assert n == 300_000 and got.dtype == np.int64 and np.array_equal(got.astype(np.uint64), exp)
+    assert np.array_equal(prime_io.load_primes_range(f, 1000, 1010).astype(np.uint64), exp[1000:1010])
+    g = tmp_path / "window.npy"
+    m = prime_io.export_primes(g, limit=10 ** 9 + 2_000_000, lo=10 ** 9, window_values=700_000)
+    expw = orc.c_primes_range(10 ** 9, 10 ** 9 + 2_000_000)
+    assert m == len(expw) and np.array_equal(np.load(g).astype(np.uint64), expw)
+    for k in (1, 2, 5):
+        assert prime_io.power_sum_file(f, k, window=70_000) == orc.c_power_sums(exp, [k])[0]
+    assert prime_io.power_sum_file(f, 3, window=50_000, start_idx=12_345, end_idx=222_222) == orc.c_power_sums(exp[12_345:222_222], [3])[0]

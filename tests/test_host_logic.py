@@ -307,3 +307,19 @@ def test_fastpath_recogniser_host_side(orc):
     assert fastpath.format_no_match("json") == '{"found": false, "variables": null}'
     with pytest.raises(ValueError, match="Missing bound"):
         fastpath.try_fast_query("primesum(q,2) == 4")
+
+
+def test_prime_io_window_plan():
+    """value windows of the .npy export: contiguous, cover [lo, limit), interior cuts on multiples of 480"""
+    from pss_b200 import prime_io
+    for lo, limit, w in [(0, 10_000, 960), (7, 100_003, 4_801), (10 ** 9, 10 ** 9 + 12_345, 5_000), (0, 0, 1000), (100, 50, 1000)]:
+        wins = list(prime_io.plan_value_windows(limit, w, lo))
+        if limit <= lo:
+            assert wins == []
+            continue
+        assert wins[0][0] == lo and wins[-1][1] == limit
+        for (a, b), (c, d) in zip(wins, wins[1:]):
+            assert b == c and a < b and b % 480 == 0
+        assert all(b - a <= w for a, b in wins)
+    with pytest.raises(ValueError):
+        list(prime_io.plan_value_windows(10, 100))
