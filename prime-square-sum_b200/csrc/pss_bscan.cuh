@@ -668,11 +668,20 @@ __global__ void __launch_bounds__(kBsThreads, bs_min_blocks<K, MULTI>()) k_bitma
     }
 }
 
+// s_lut[(byte q of w) * 32 + lane] through its 32-bit shared address (lut_lane = &s_lut[lane])
+__device__ __forceinline__ u32 lut_at(u32 lut_lane, u32 w, int q) {
+    u32 b, e;
+    asm("prmt.b32 %0, %1, 0, %2;" : "=r"(b) : "r"(w), "r"(0x4440u + (u32)q));   // byte q, zero extended
+    asm("ld.shared.u32 %0, [%1];" : "=r"(e) : "r"(lut_lane + (b << 7)));
+    return e;
+}
+
 // ---- reduce pass for the sum of SQUARES without touching individual primes ---------------------------------------
 // A thread's 24 words cover the 2880 integers [B, B + 2880).  With o = p - B:
 //     sum p^2 = M0 * B^2 + 2 B * M1 + M2,      M0 = #primes, M1 = sum o, M2 = sum o^2        (exact)
 // and the moments come from a 256-entry byte table (count, sum r, sum r^2 of the wheel residues r of the set bits,
-// packed 6 + 10 + 14 bits so that four entries add without overflow) plus constant byte / word position weights.
+// packed 7 + 10 + 14 bits so that the weighted sums of four entries used below cannot overflow the fields they are
+// read from) plus constant byte / word position weights.
 // ~32 instructions per 32-bit word (~5 primes) instead of ~48 per prime for decode + square + accumulate.  The output
 // (thread / warp records, scan-tile columns) is bit-identical to k_bitmap_scan<2, false, kBsReduce>.
 __global__ void __launch_bounds__(kBsThreads) k_bitmap_moments2(const __grid_constant__ BScanParams P) {
@@ -689,7 +698,7 @@ __global__ void __launch_bounds__(kBsThreads) k_bitmap_moments2(const __grid_con
                 const u32 r = wheel_residue(j);
                 n += 1u; r1 += r; r2 += r * r;
             }
-        const u32 e = n | (r1 << 6) | (r2 << 16);
+        const u32 e = n | (r1 << 7) | (r2 << 17);
         for (u32 k = 0; k < 32; ++k) s_lut[v * 32 + ((k + v) & 31u)] = e;   // rotated: conflict-free stores too
     }
     __syncthreads();
@@ -706,25 +715,32 @@ __global__ void __launch_bounds__(kBsThreads) k_bitmap_moments2(const __grid_con
             v[q] = make_uint4(0, 0, 0, 0);
             if (word0 + 4ull * q + 4 <= P.n_words) v[q] = __ldg(g4 + q);
         }
-        u32 M0 = 0, M1 = 0;
-        u64 M2 = 0;
+        // per word i (origin 120 i inside the thread's range): m0, m1, m2 about the word origin; the shift to the
+        // thread origin is deferred: M1 = sum m1 + 120 sum i m0,  M2 = sum m2 + 240 sum i m1 + 14400 sum i^2 m0
+        // (all partial sums fit 32 bits: 768 bits set at most, i <= 23)
+        u32 M0 = 0, A1 = 0, A2 = 0, C1 = 0, C2 = 0, D1 = 0;
+        const u32 lut_lane = (u32)__cvta_generic_to_shared(s_lut) + 4u * lane;
 #pragma unroll
         for (int i = 0; i < WPT; ++i) {
             const uint4 vv = v[i >> 2];
             const u32 w = (i & 3) == 0 ? vv.x : (i & 3) == 1 ? vv.y : (i & 3) == 2 ? vv.z : vv.w;
-            const u32* lut = s_lut + lane;
-            const u32 e0 = lut[(w & 255u) << 5], e1 = lut[((w >> 8) & 255u) << 5], e2 = lut[((w >> 16) & 255u) << 5], e3 = lut[(w >> 24) << 5];
+            // table word (byte value << 5) + lane: one PRMT (byte extract) + one LEA (address) + one LDS per byte
+            const u32 e0 = lut_at(lut_lane, w, 0), e1 = lut_at(lut_lane, w, 1), e2 = lut_at(lut_lane, w, 2), e3 = lut_at(lut_lane, w, 3);
             const u32 W = e0 + e1 + e2 + e3;                       // moments about each byte's own origin
-            const u32 V = e1 + 2u * e2 + 3u * e3;                  // byte-index weighted (count and sum r fields)
-            const u32 Q = (e1 & 63u) + 4u * (e2 & 63u) + 9u * (e3 & 63u);
-            const u32 m0 = W & 63u;
-            const u32 m1 = ((W >> 6) & 1023u) + 30u * (V & 63u);                     // about the word origin
-            const u32 m2 = (W >> 16) + 60u * ((V >> 6) & 1023u) + 900u * Q;
-            const u32 c = 120u * i;                                                  // word origin inside the thread's range
+            const u32 V = e1 + 2u * e2 + 3u * e3;                  // byte-index weighted: count and sum r fields are valid
+            const u32 U = e1 + 4u * e2 + 9u * e3;                  // byte-index^2 weighted: only the count field (<= 112) is valid
+            const u32 m0 = W & 127u;
+            const u32 m1 = ((W >> 7) & 1023u) + 30u * (V & 127u);                    // about the word origin
+            const u32 m2 = (W >> 17) + 60u * ((V >> 7) & 1023u) + 900u * (U & 127u);
             M0 += m0;
-            M1 += m1 + c * m0;
-            M2 += (u64)(m2 + 2u * c * m1 + c * c * m0);
+            A1 += m1;
+            A2 += m2;
+            C1 += (u32)i * m0;
+            C2 += (u32)(i * i) * m0;
+            D1 += (u32)i * m1;
         }
+        const u32 M1 = A1 + 120u * C1;
+        const u64 M2 = (u64)A2 + 240ull * D1 + 14400ull * C2;
         // thread sum = M0 * B^2 + 2 B M1 + M2
         const u64 B = (P.B_start + 4ull * word0) * 30ull;
         const u32 blo = (u32)B, bhi = (u32)(B >> 32);
