@@ -373,12 +373,113 @@ __global__ void __launch_bounds__(kBsThreads, bs_min_blocks<K, MULTI>()) k_bitma
     const u64 warp_stride = (u64)gridDim.x * NWARP;
     const u64 n_first = (MODE != kBsReduce && P.n_first_dev) ? *P.n_first_dev : P.n_first;
 
-    for (u64 wt = (u64)blockIdx.x * NWARP + warp; wt < n_warp_tiles; wt += warp_stride) {
-        const u32 tile = (u32)(wt / NWARP);
-        const u32 wit = (u32)(wt % NWARP);          // warp index inside the scan tile
-        if constexpr (MODE != kBsReduce) {
-            if (n_first + P.col_prefix[tile] > P.n_max) break;   // prefixes are monotone in tile
+    // normalised prefix of scan tile t (carry-in + deferred-carry column prefixes), uniform across the warp
+    auto tile_prefix = [&](u32 t, u32* out) {
+#pragma unroll
+        for (int jj = 0; jj < NP; ++jj) {
+            u64 c = 0;
+#pragma unroll
+            for (int i = 0; i < PSS_LIMBS; ++i) {
+                if (i < Lay::width(jj)) {
+                    const int col = 1 + Lay::offset(jj) + i;
+                    const u64 v = P.col_prefix[(u64)col * P.col_stride + t];
+                    const u64 lo = (v & 0xFFFFFFFFull) + (c & 0xFFFFFFFFull) + P.carry_in[jj * PSS_LIMBS + i];
+                    out[Lay::offset(jj) + i] = (u32)lo;
+                    c = (v >> 32) + (c >> 32) + (lo >> 32);
+                }
+            }
         }
+    };
+    // matches of a run of consecutive primes: in-window tile-local indices [a, a + n_in), of which n_lt below the
+    // target and eq_li the index of an exact hit; outcomes are  < ... < [==] > ... >  (S strictly increasing)
+    auto emit = [&](u32 a, u32 n_in, const u32* n_lt, const u32* eq_li, u64 tile_n0) {
+#pragma unroll
+        for (int jj = 0; jj < NP; ++jj) {
+            const u32 eq = (eq_li[jj] != 0xFFFFFFFFu) ? 1u : 0u;
+            const u32 lt = n_lt[jj], gt = n_in - lt - eq;
+            u32 mc = 0, mf = 0xFFFFFFFFu, ml = 0;   // count, first (tile-local), last + 1
+            if (n_in) {
+                const u32 m = P.cmp_mask;
+                // contiguous runs: [a, a+lt) below, [a+lt, a+lt+eq) equal, [a+lt+eq, a+n_in) above
+                if ((m & 1u) && lt) { mc += lt; mf = min(mf, a); ml = max(ml, a + lt); }
+                if ((m & 2u) && eq) { mc += 1; mf = min(mf, a + lt); ml = max(ml, a + lt + 1); }
+                if ((m & 4u) && gt) { mc += gt; mf = min(mf, a + lt + eq); ml = max(ml, a + n_in); }
+            }
+            if (__any_sync(0xFFFFFFFFu, mc != 0)) {
+                const u32 c = __reduce_add_sync(0xFFFFFFFFu, mc);
+                const u32 f = __reduce_min_sync(0xFFFFFFFFu, mf);
+                const u32 l = __reduce_max_sync(0xFFFFFFFFu, ml);
+                if (lane == 0) {
+                    pss_power_result* r = P.results + jj;
+                    atomicAdd(reinterpret_cast<unsigned long long*>(&r->match_count), (unsigned long long)c);
+                    atomicMin(reinterpret_cast<unsigned long long*>(&r->first_match_n), (unsigned long long)(tile_n0 + f));
+                    atomicMax(reinterpret_cast<unsigned long long*>(&r->last_match_n), (unsigned long long)(tile_n0 + l - 1));
+                }
+            }
+        }
+    };
+
+    // work units: reduce pass = warp tiles; compare passes = scan tiles (8 warp tiles), pruned as a whole when possible
+    const u64 n_units = (MODE == kBsReduce) ? n_warp_tiles : (u64)P.n_tiles;
+    for (u64 unit = (u64)blockIdx.x * NWARP + warp; unit < n_units; unit += warp_stride) {
+        u32 tile, wit_lo, wit_hi;
+        if constexpr (MODE == kBsReduce) {
+            tile = (u32)(unit / NWARP);
+            wit_lo = (u32)(unit % NWARP);
+            wit_hi = wit_lo + 1u;
+        } else {
+            tile = (u32)unit;
+            wit_lo = 0u;
+            wit_hi = NWARP;
+            if (n_first + P.col_prefix[tile] > P.n_max) break;   // prefixes are monotone in tile
+            // ---- interval pruning, scan-tile level (737 280 integers): same argument as below on the tile's exact
+            //      prefix / end sums; a pruned tile costs one warp ~100 instructions and touches no record
+            if (!P.exhaustive) {
+                const u64 t_n0 = n_first + P.col_prefix[tile];
+                const u64 tcnt64 = P.col_prefix[tile + 1] - P.col_prefix[tile];
+                const u32 tcnt = (u32)tcnt64;
+                const u32 t_lmin = (P.n_min > t_n0) ? (u32)min(P.n_min - t_n0, (u64)0xFFFFFFFFull) : 0u;
+                const u32 t_lmax = (u32)min(P.n_max - t_n0, (u64)0xFFFFFFFEull);
+                const u32 tquota = min(tcnt, t_lmax + 1u);
+                const u32 tskip = min(t_lmin, tquota);
+                const bool t_nmax = tquota > 0 && (t_n0 + tquota - 1 == P.n_max);
+                bool simple = !t_nmax && (tskip == 0 || tskip == tquota);
+                if (simple) {
+                    u32 tpre[TOTAL];
+                    tile_prefix(tile, tpre);
+                    if constexpr (MODE == kBsCompare) {
+                        u32 tend[TOTAL];
+                        tile_prefix(tile + 1, tend);
+                        int c0[NP], c1[NP];
+                        OpCmpInit o0{tpre, P.target, P.target_over_mask, c0};
+                        for_each_power<0, Lay>(o0);
+                        OpCmpInit o1{tend, P.target, P.target_over_mask, c1};
+                        for_each_power<0, Lay>(o1);
+#pragma unroll
+                        for (int jj = 0; jj < NP; ++jj) simple = simple && !(c0[jj] < 0 && c1[jj] >= 0);
+                        if (simple) {
+                            u32 t_nlt[NP], t_eq[NP];
+                            const u32 t_in = (lane == 0) ? tquota - tskip : 0u;
+#pragma unroll
+                            for (int jj = 0; jj < NP; ++jj) {
+                                t_nlt[jj] = (c0[jj] < 0) ? t_in : 0u;
+                                t_eq[jj] = 0xFFFFFFFFu;
+                            }
+                            emit(tskip, t_in, t_nlt, t_eq, t_n0);
+                            continue;
+                        }
+                    } else {
+                        bool beyond = false;
+#pragma unroll
+                        for (int i = 2; i < Lay::width(0); ++i) beyond = beyond || (tpre[i] != 0u);
+                        beyond = beyond || ((((u64)tpre[1] << 32) | tpre[0]) > P.tri_max_value);
+                        if (beyond) continue;
+                    }
+                }
+            }
+        }
+      for (u32 wit = wit_lo; wit < wit_hi; ++wit) {          // warp index inside the scan tile
+        const u64 wt = (u64)tile * NWARP + wit;
         const u64 word0 = wt * WARP_WORDS;
         // ---- warp-local staging: coalesced uint4 loads -> padded blocked layout, bit-reversed
         auto stage = [&]() {
@@ -430,20 +531,7 @@ __global__ void __launch_bounds__(kBsThreads, bs_min_blocks<K, MULTI>()) k_bitma
             u32 wpre[TOTAL];
             u32 wli0 = 0;                // tile-local index of the warp's first prime
             {
-#pragma unroll
-                for (int jj = 0; jj < NP; ++jj) {
-                    u64 c = 0;
-#pragma unroll
-                    for (int i = 0; i < PSS_LIMBS; ++i) {
-                        if (i < Lay::width(jj)) {
-                            const int col = 1 + Lay::offset(jj) + i;
-                            const u64 v = P.col_prefix[(u64)col * P.col_stride + tile];
-                            const u64 lo = (v & 0xFFFFFFFFull) + (c & 0xFFFFFFFFull) + P.carry_in[jj * PSS_LIMBS + i];
-                            wpre[Lay::offset(jj) + i] = (u32)lo;
-                            c = (v >> 32) + (c >> 32) + (lo >> 32);
-                        }
-                    }
-                }
+                tile_prefix(tile, wpre);
                 // earlier warps of this scan tile: lane l < wit fetches warp record l, butterfly sum
                 u32 v[TOTAL];
                 u32 c = 0;
@@ -637,34 +725,9 @@ __global__ void __launch_bounds__(kBsThreads, bs_min_blocks<K, MULTI>()) k_bitma
                 }
             }
             __syncwarp();
-            if constexpr (MODE == kBsCompare) {
-                // matches: in-window indices [a, a + n_in); outcomes  < ... < [==] > ... >
-#pragma unroll
-                for (int jj = 0; jj < NP; ++jj) {
-                    const u32 eq = (eq_li[jj] != 0xFFFFFFFFu) ? 1u : 0u;
-                    const u32 lt = n_lt[jj], gt = n_in - lt - eq;
-                    u32 mc = 0, mf = 0xFFFFFFFFu, ml = 0;   // count, first (tile-local), last + 1
-                    if (n_in) {
-                        const u32 m = P.cmp_mask;
-                        // contiguous runs: [a, a+lt) below, [a+lt, a+lt+eq) equal, [a+lt+eq, a+n_in) above
-                        if ((m & 1u) && lt) { mc += lt; mf = min(mf, a); ml = max(ml, a + lt); }
-                        if ((m & 2u) && eq) { mc += 1; mf = min(mf, a + lt); ml = max(ml, a + lt + 1); }
-                        if ((m & 4u) && gt) { mc += gt; mf = min(mf, a + lt + eq); ml = max(ml, a + n_in); }
-                    }
-                    if (__any_sync(0xFFFFFFFFu, mc != 0)) {
-                        const u32 c = __reduce_add_sync(0xFFFFFFFFu, mc);
-                        const u32 f = __reduce_min_sync(0xFFFFFFFFu, mf);
-                        const u32 l = __reduce_max_sync(0xFFFFFFFFu, ml);
-                        if (lane == 0) {
-                            pss_power_result* r = P.results + jj;
-                            atomicAdd(reinterpret_cast<unsigned long long*>(&r->match_count), (unsigned long long)c);
-                            atomicMin(reinterpret_cast<unsigned long long*>(&r->first_match_n), (unsigned long long)(tile_n0 + f));
-                            atomicMax(reinterpret_cast<unsigned long long*>(&r->last_match_n), (unsigned long long)(tile_n0 + l - 1));
-                        }
-                    }
-                }
-            }
+            if constexpr (MODE == kBsCompare) emit(a, n_in, n_lt, eq_li, tile_n0);
         }
+      }
     }
 }
 
@@ -769,41 +832,39 @@ __global__ void __launch_bounds__(kBsThreads) k_bitmap_moments2(const __grid_con
 // out[c * stride + t] = sum_{i<t} in[c * stride + i]  for t = 0..n  (entry n = column total)
 __global__ void __launch_bounds__(1024) k_scan_columns(const u64* in, u64* out, u32 n, u64 stride) {
     __shared__ u64 s_warp[32];
-    __shared__ u64 s_running;
     const u32 tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
     const u64* col = in + (u64)blockIdx.x * stride;
     u64* o = out + (u64)blockIdx.x * stride;
-    if (tid == 0) s_running = 0;
+    // every thread owns a contiguous run of the column: local sum -> one block-wide scan -> local prefixes
+    const u32 per = (n + 1023u) / 1024u;
+    const u32 begin = min(n, tid * per), end = min(n, begin + per);
+    u64 sum = 0;
+    for (u32 i = begin; i < end; ++i) sum += col[i];
+    u64 incl = sum;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const u64 up = __shfl_up_sync(0xFFFFFFFFu, incl, d);
+        if (lane >= (u32)d) incl += up;
+    }
+    if (lane == 31) s_warp[warp] = incl;
     __syncthreads();
-    for (u32 base = 0; base < n; base += 1024) {
-        const u32 i = base + tid;
-        const u64 v = (i < n) ? col[i] : 0;
-        u64 incl = v;
+    if (warp == 0) {
+        const u64 w = s_warp[lane];
+        u64 wi = w;
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) {
-            const u64 up = __shfl_up_sync(0xFFFFFFFFu, incl, d);
-            if (lane >= (u32)d) incl += up;
+            const u64 up = __shfl_up_sync(0xFFFFFFFFu, wi, d);
+            if (lane >= (u32)d) wi += up;
         }
-        if (lane == 31) s_warp[warp] = incl;
-        __syncthreads();
-        if (warp == 0) {
-            const u64 w = s_warp[lane];
-            u64 wi = w;
-#pragma unroll
-            for (int d = 1; d < 32; d <<= 1) {
-                const u64 up = __shfl_up_sync(0xFFFFFFFFu, wi, d);
-                if (lane >= (u32)d) wi += up;
-            }
-            s_warp[lane] = wi - w;
-        }
-        __syncthreads();
-        const u64 excl = s_running + s_warp[warp] + incl - v;
-        if (i < n) o[i] = excl;
-        __syncthreads();
-        if (tid == 1023) s_running = excl + v;
-        __syncthreads();
+        s_warp[lane] = wi - w;
     }
-    if (tid == 0) o[n] = s_running;
+    __syncthreads();
+    u64 run = s_warp[warp] + incl - sum;
+    for (u32 i = begin; i < end; ++i) {
+        o[i] = run;
+        run += col[i];
+    }
+    if (tid == 1023) o[n] = run;
 }
 
 }  // namespace pss
