@@ -136,6 +136,13 @@ int pss_primesum(pss_handle* h, uint64_t n, uint32_t power, uint32_t* limbs_out 
 /* ---- K1+K2+K3 fused search (single GPU) ---------------------------------------------------- */
 int pss_search(pss_handle* h, const pss_search_args* args, pss_search_result* res);
 
+/* Several targets / operators over the same n range and power configuration in one call: one sieve and one
+ * block-sum pass, then one pruned compare launch per target on the resident records (a few tens of microseconds
+ * each).  Serves right-hand sides that are themselves sequences -- primesum(n,k) == fibonacci(m), factorial(m),
+ * catalan(m) over an m range (utils/sequences.py:83-200, equations.json) -- and `--limit` enumerations.
+ * All args[t] must share n_min, n_max, power_max, all_powers. */
+int pss_search_targets(pss_handle* h, const pss_search_args* args, uint32_t n_targets, pss_search_result* results /* n_targets */);
+
 /* `for_any primesum(n,power) == tri(m)` (config: n <= 1e8, m <= 1e7): every partial sum S(n), n in
  * [n_min,n_max], is tested for triangularity on the device (8S+1 perfect square, utils/number_theory.py:292-354)
  * with m restricted to [m_min,m_max].  pairs_out receives up to cap (n, m) pairs (unordered); *count is the

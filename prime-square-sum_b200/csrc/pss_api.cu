@@ -110,7 +110,9 @@ struct pss_handle {
     u32 bs_sums[PSS_MAX_POWER * PSS_LIMBS] = {0};   // slice sums per power record (normalised limbs)
 
     // scan workspace
-    DevBuf status, agg, incl, misc, prefix_out, user_vals, tri_buf;
+    DevBuf status, agg, incl, misc, prefix_out, user_vals, tri_buf, misc_multi;
+    MiscDev* h_misc_multi = nullptr;   // pinned, h_misc_multi_cap blocks (pss_search_targets)
+    size_t h_misc_multi_cap = 0;
     MiscDev* h_misc = nullptr;   // pinned
     HostBack* h_back = nullptr;  // pinned
 
@@ -878,7 +880,7 @@ int bitmap_compare(pss_handle* h, u64 n_first, const u32* carry_in, const pss_se
 }
 
 // BScanParams of a compare launch over the bitmap left by sieve_range / bitmap_reduce
-void fill_compare_params(pss_handle* h, BScanParams& bp, const pss_search_args* a, u64 n_first) {
+void fill_compare_params(pss_handle* h, BScanParams& bp, const pss_search_args* a, u64 n_first, MiscDev* dm = nullptr) {
     static const u32 kMasks[6] = {2u, 5u, 1u, 3u, 4u, 6u};
     const bool multi = a->all_powers && a->power_max > 1;
     const u32 K = a->power_max, np = n_powers_of(K, multi);
@@ -896,7 +898,7 @@ void fill_compare_params(pss_handle* h, BScanParams& bp, const pss_search_args* 
         for (u32 i = w; i < a->target_nlimbs; ++i)
             if (a->target[i]) bp.target_over_mask |= (1u << j);
     }
-    MiscDev* dm = static_cast<MiscDev*>(h->misc.p);
+    if (!dm) dm = static_cast<MiscDev*>(h->misc.p);
     bp.carry_in = dm->carry;
     bp.results = dm->results;
     bp.last_prime_out = &dm->last_prime;
@@ -994,6 +996,8 @@ int pss_close(pss_handle* h) {
         if (p) cudaFree(p);
     if (h->h_misc) cudaFreeHost(h->h_misc);
     if (h->h_back) cudaFreeHost(h->h_back);
+    if (h->h_misc_multi) cudaFreeHost(h->h_misc_multi);
+    if (h->misc_multi.p) cudaFree(h->misc_multi.p);
     if (h->h_peer_results) cudaFreeHost(h->h_peer_results);
     for (int r = 0; r < h->peer_world; ++r)
         if (h->box[r] && h->box[r] != h->box_local) cudaIpcCloseMemHandle(h->box[r]);
@@ -1191,6 +1195,80 @@ int pss_search(pss_handle* h, const pss_search_args* a, pss_search_result* res) 
         PSS_TRY(bitmap_compare(h, 1, nullptr, a, res));
     }
     fill_stats(h, &res->stats, before);
+    return PSS_OK;
+}
+
+int pss_search_targets(pss_handle* h, const pss_search_args* args, uint32_t n_targets, pss_search_result* results) {
+    PSS_TRY(check_handle(h));
+    if (n_targets == 0) return PSS_OK;
+    if (!args || !results) return fail(h, PSS_EINVAL, "null argument");
+    if (n_targets > 65536) return fail(h, PSS_EINVAL, "too many targets (%u)", n_targets);
+    for (u32 t = 0; t < n_targets; ++t) {
+        PSS_TRY(validate_search(h, &args[t], &results[t]));
+        if (args[t].n_min != args[0].n_min || args[t].n_max != args[0].n_max || args[t].power_max != args[0].power_max ||
+            (args[t].all_powers != 0) != (args[0].all_powers != 0))
+            return fail(h, PSS_EINVAL, "all targets of one call must share n_min, n_max, power_max and all_powers");
+    }
+    if (h->search_path == 1) return fail(h, PSS_EINVAL, "pss_search_targets runs on the fused search path only");
+    const pss_stats before = stats_snapshot(h);
+    const pss_search_args* a0 = &args[0];
+    const bool multi = a0->all_powers && a0->power_max > 1;
+    const u32 K = a0->power_max, np = n_powers_of(K, multi);
+    const u64 bound = pss_nth_prime_upper(a0->n_max) + 1;
+    if (bound > kMaxValue) return fail(h, PSS_EINVAL, "n = %llu needs primes beyond 2^%d", (unsigned long long)a0->n_max, PSS_MAX_PRIME_BITS);
+    if (n_targets > h->h_misc_multi_cap) {
+        if (h->h_misc_multi) cudaFreeHost(h->h_misc_multi);
+        h->h_misc_multi = nullptr;
+        h->h_misc_multi_cap = 0;
+        CU_TRY(h, cudaMallocHost(reinterpret_cast<void**>(&h->h_misc_multi), sizeof(MiscDev) * n_targets));
+        h->h_misc_multi_cap = n_targets;
+    }
+    PSS_TRY(ensure(h, h->misc_multi, sizeof(MiscDev) * n_targets));
+    MiscDev* dmv = static_cast<MiscDev*>(h->misc_multi.p);
+    MiscDev* hmv = h->h_misc_multi;
+    // one sieve + one block-sum pass, then one (pruned) compare launch per target on the resident records
+    PSS_TRY(sieve_range(h, 0, bound, true));
+    PSS_TRY(bitmap_reduce(h, K, multi, true));
+    memset(hmv, 0, sizeof(MiscDev) * n_targets);
+    for (u32 t = 0; t < n_targets; ++t)
+        for (u32 j = 0; j < np; ++j) {
+            hmv[t].results[j].power = expo_of(K, multi, j);
+            hmv[t].results[j].first_match_n = ~0ull;
+        }
+    CU_TRY(h, cudaMemcpyAsync(dmv, hmv, sizeof(MiscDev) * n_targets, cudaMemcpyHostToDevice, h->stream));
+    CU_TRY(h, cudaEventRecord(h->ev[6], h->stream));
+    if (h->bs_n_tiles > 0)
+        for (u32 t = 0; t < n_targets; ++t) {
+            BScanParams bp;
+            fill_compare_params(h, bp, &args[t], 1, dmv + t);
+            PSS_TRY(launch_bscan<kBsCompare>(h, bp, K, multi));
+        }
+    CU_TRY(h, cudaEventRecord(h->ev[7], h->stream));
+    CU_TRY(h, cudaMemcpyAsync(hmv, dmv, sizeof(MiscDev) * n_targets, cudaMemcpyDeviceToHost, h->stream));
+    CU_TRY(h, cudaStreamSynchronize(h->stream));
+    sieve_finish(h);
+    PSS_TRY(reduce_finish(h));
+    if (h->sv_total < a0->n_max)
+        return fail(h, PSS_EINTERNAL, "prime count bound failed: %llu primes sieved, n_max = %llu", (unsigned long long)h->sv_total,
+                    (unsigned long long)a0->n_max);
+    h->acc.ms_power_scan += ev_ms(h, 6, 7);
+    h->acc.ms_bitmap_compare += ev_ms(h, 6, 7);
+    h->acc.ms_span += ev_ms(h, 0, 7);
+    h->acc.primes += a0->n_max;
+    for (u32 t = 0; t < n_targets; ++t) {
+        pss_search_result* res = &results[t];
+        memset(res, 0, sizeof *res);
+        if (hmv[t].error_flag) return fail(h, PSS_EINTERNAL, "device error flag %u (target %u)", hmv[t].error_flag, t);
+        for (u32 j = 0; j < np; ++j) {
+            res->powers[j] = hmv[t].results[j];
+            if (res->powers[j].match_count == 0) res->powers[j].first_match_n = 0, res->powers[j].last_match_n = 0;
+        }
+        res->n_powers = np;
+        res->primes_scanned = a0->n_max;
+        res->last_prime = hmv[t].last_prime;
+    }
+    fill_stats(h, &results[0].stats, before);
+    for (u32 t = 1; t < n_targets; ++t) results[t].stats = results[0].stats;
     return PSS_OK;
 }
 

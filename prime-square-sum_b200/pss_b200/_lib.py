@@ -79,7 +79,7 @@ EXPORTS = [
     "pss_slice_sieve", "pss_slice_reduce", "pss_slice_scan", "pss_slice_prefix_sums", "pss_slice_primes",
     "pss_slice_device_buffer", "pss_nth_prime_upper", "pss_stats_reset", "pss_stats_get",
     "pss_set_search_path", "pss_slice_sieve_sums", "pss_slice_scan_bitmap", "pss_search_tri",
-    "pss_set_compare_mode", "pss_peer_export", "pss_peer_connect", "pss_peer_search",
+    "pss_set_compare_mode", "pss_peer_export", "pss_peer_connect", "pss_peer_search", "pss_search_targets",
 ]
 
 _cdll = None
@@ -121,6 +121,7 @@ def load_library() -> ctypes.CDLL:
     L.pss_search_tri.argtypes = [H, u64, u64, u32, u64, u64, pu64, u32, pu32, ctypes.POINTER(Stats)]
     L.pss_set_search_path.argtypes = [H, ctypes.c_int]
     L.pss_set_compare_mode.argtypes = [H, ctypes.c_int]
+    L.pss_search_targets.argtypes = [H, ctypes.POINTER(SearchArgs), u32, ctypes.POINTER(SearchResult)]
     L.pss_peer_export.argtypes = [H, ctypes.c_void_p]
     L.pss_peer_connect.argtypes = [H, ctypes.c_int, ctypes.c_int, ctypes.c_void_p]
     L.pss_peer_search.argtypes = [H, u64, u64, ctypes.POINTER(SearchArgs), ctypes.POINTER(PeerRecord), ctypes.POINTER(Stats)]
@@ -270,6 +271,23 @@ class Handle:
         self._check(self._L.pss_search(self._h, ctypes.byref(a), ctypes.byref(res)))
         del keep
         return res
+
+    def search_targets(self, n_min: int, n_max: int, power_max: int, targets: Sequence[int], op: str = "==",
+                       all_powers: bool = False) -> List["SearchResult"]:
+        """several targets over the same n range: one sieve + one block-sum pass, one compare launch per target"""
+        n = len(targets)
+        if n == 0:
+            return []
+        arr = (SearchArgs * n)()
+        keep = []
+        for i, t in enumerate(targets):
+            a, k = self._make_args(n_min, n_max, power_max, all_powers, op, int(t))
+            arr[i] = a
+            keep.append(k)
+        res = (SearchResult * n)()
+        self._check(self._L.pss_search_targets(self._h, arr, n, res))
+        del keep
+        return list(res)
 
     # -- slice API (multi-GPU decomposition)
     def slice_sieve(self, lo: int, hi_excl: int):

@@ -7,7 +7,8 @@ The reference evaluates `does_exist primesum(n,2) == trisum(666) --max n:1000000
 `try_fast_query` recognises
 
     [does_exist|for_any] primesum(<var>[, <int>|<var>]) <op> <rhs>       op in == != < <= > >=
-    rhs:  <int literal> | trisum(<int>) | tri(<int>) | tri(<var>)            (only == for tri(<var>))
+    rhs:  <int literal> | trisum(<int>) | tri(<int>) | fibonacci(<int>) | factorial(<int>) | catalan(<int>)
+          | tri(<var>) | fibonacci(<var>) | factorial(<var>) | catalan(<var>)     (only == for f(<var>))
 
 and answers it with ONE device pass, producing exactly the reference's stdout lines and return code
 (format_match / format_no_match, utils/cli.py:1201-1297; rc 0 = match, 1 = none, prime-square-sum.py:452-472).
@@ -30,7 +31,7 @@ _EXPR = re.compile(
     r"^\s*(?:(?P<quant>does_exist|for_any)\s+)?primesum\(\s*(?P<nvar>[A-Za-z_]\w*)\s*(?:,\s*(?P<parg>[A-Za-z_]\w*|\d+)\s*)?\)"
     r"\s*(?P<op>==|!=|<=|>=|<|>)\s*(?P<rhs>.+?)\s*$")
 _RHS_INT = re.compile(r"^\d+$")
-_RHS_CALL = re.compile(r"^(?P<fn>trisum|tri)\(\s*(?P<arg>[A-Za-z_]\w*|\d+)\s*\)$")
+_RHS_CALL = re.compile(r"^(?P<fn>trisum|tri|fibonacci|factorial|catalan)\(\s*(?P<arg>[A-Za-z_]\w*|\d+)\s*\)$")
 
 
 def _tri(n: int) -> int:
@@ -109,7 +110,24 @@ def try_fast_query(expr: str, max_bounds: Optional[Dict[str, int]] = None, min_b
     if _RHS_INT.match(rhs):
         target = int(rhs)
     elif mt and mt.group("arg").isdigit():
-        target = _trisum(int(mt.group("arg"))) if mt.group("fn") == "trisum" else _tri(int(mt.group("arg")))
+        fn, arg = mt.group("fn"), int(mt.group("arg"))
+        target = _trisum(arg) if fn == "trisum" else _search.RHS_SEQUENCES[fn](arg)
+    elif mt and mt.group("fn") in ("fibonacci", "factorial", "catalan") and op == "==" and p_var is None:
+        # primesum(n,k) == f(m) for a non-decreasing sequence f: the reachable values f(m) are searched in one device pass
+        mvar = mt.group("arg")
+        if mvar == nvar:
+            return None
+        m_lo, m_hi = bound(mvar)
+        hits = _search.for_any_sequence(mt.group("fn"), n_hi, m_hi, power=power, n_min=n_lo, m_min=m_lo)
+        hits = [{mvar: h["m"], nvar: h["n"]} for h in hits]
+        hits.sort(key=lambda d: tuple(d[v] for v in sorted(d)))
+        if quant == "does_exist":
+            hits = hits[:1]
+        elif limit is not None:
+            hits = hits[:limit]
+        if not hits:
+            return [format_no_match(fmt)], 1
+        return [format_match(h, fmt) for h in hits], 0
     elif mt and mt.group("fn") == "tri" and op == "==" and p_var is None:
         # primesum(n,k) == tri(m): the device tests every partial sum for triangularity
         mvar = mt.group("arg")

@@ -176,6 +176,76 @@ def for_any_tri(n_max: int, m_max: int, power: int = 2, n_min: int = 1, m_min: i
     return [{"m": m, "n": n} for n, m in sorted(pairs, key=lambda t: (t[1], t[0]))]
 
 
+def search_many(targets: Sequence[int], n_max: int, power: int = 2, n_min: int = 1, op: str = "==",
+                all_powers: bool = False, handle: Optional["_lib.Handle"] = None) -> List[SearchOutcome]:
+    """Several targets over the same n range in ONE device pass over the primes (one sieve, one block-sum pass)
+    followed by one pruned compare launch per target.  outcomes[i] belongs to targets[i]."""
+    if op not in OPS:
+        raise ValueError(f"unknown comparison operator {op!r}")
+    if any(t < 0 for t in targets):
+        raise ValueError("targets must be non-negative")
+    h = handle or _lib.default_handle()
+    res = h.search_targets(n_min, n_max, power, list(targets), op, all_powers)
+    return [_outcome_from_result(r, n_min, n_max, op, t) for r, t in zip(res, targets)]
+
+
+# monotone integer sequences of the reference's registry usable as a right-hand side (utils/sequences.py:83-200,
+# utils/number_theory.py:250-289): name -> f(m)
+def _fibonacci(m: int) -> int:
+    if m < 0:
+        raise ValueError(f"fibonacci() requires non-negative n, got {m}")
+    a, b = 0, 1
+    for _ in range(m):
+        a, b = b, a + b
+    return a
+
+
+def _catalan(m: int) -> int:
+    if m < 0:
+        raise ValueError(f"catalan() requires non-negative n, got {m}")
+    return math.comb(2 * m, m) // (m + 1)
+
+
+def _factorial(m: int) -> int:
+    if m < 0:
+        raise ValueError(f"factorial() requires non-negative n, got {m}")
+    return math.factorial(m)
+
+
+RHS_SEQUENCES = {"fibonacci": _fibonacci, "factorial": _factorial, "catalan": _catalan, "tri": lambda m: m * (m + 1) // 2}
+
+
+def for_any_sequence(fn: str, n_max: int, m_max: int, power: int = 2, n_min: int = 1, m_min: int = 1,
+                     handle: Optional["_lib.Handle"] = None) -> List[Dict[str, int]]:
+    """`for_any primesum(n,power) == fn(m)`, m in [m_min, m_max], for a non-decreasing sequence fn of the reference's
+    registry: every (m, n) with primesum(n, power) == fn(m), in the reference's iteration order (m outer, n inner:
+    variables sorted by name, utils/grammar.py:939,977).  The distinct values fn(m) that can be reached at all
+    (fn(m) <= n_max * p_max^power) are searched in one device pass (`search_many`)."""
+    if fn not in RHS_SEQUENCES:
+        raise ValueError(f"unknown sequence {fn!r}")
+    h = handle or _lib.default_handle()
+    f = RHS_SEQUENCES[fn]
+    cap = n_max * (h.nth_prime_upper(n_max) ** power)        # S_power(n_max) < cap: larger values cannot match
+    values: Dict[int, List[int]] = {}
+    for m in range(max(m_min, 0), m_max + 1):
+        v = f(m)
+        if v > cap:
+            break                                            # all four sequences are non-decreasing
+        values.setdefault(v, []).append(m)
+    if not values:
+        return []
+    targets = sorted(values)
+    outs = search_many(targets, n_max, power=power, n_min=n_min, op="==", handle=h)
+    hits = []
+    for t, o in zip(targets, outs):
+        first = o.first()
+        if first is not None:
+            for m in values[t]:
+                hits.append({"m": m, "n": first[0]})         # S strictly increasing: at most one n per value
+    hits.sort(key=lambda d: (d["m"], d["n"]))
+    return hits
+
+
 # ------------------------------------------------------------------------------- multi-GPU
 def li(x: float) -> float:
     """Offset logarithmic integral estimate of pi(x) (asymptotic series; only used to balance slices)."""

@@ -486,3 +486,40 @@ def test_prime_io_export_and_file_power_sum(handle, orc, tmp_path):
     for k in (1, 2, 5):
         assert prime_io.power_sum_file(f, k, window=70_000) == orc.c_power_sums(exp, [k])[0]
     assert prime_io.power_sum_file(f, 3, window=50_000, start_idx=12_345, end_idx=222_222) == orc.c_power_sums(exp[12_345:222_222], [3])[0]
+
+
+def test_multi_target_and_sequence_rhs(handle, orc):
+    """pss_search_targets: several targets in one device pass == one pss_search per target; sequence right-hand sides
+    (fibonacci / factorial / catalan / tri over an m range) against a brute-force oracle scan"""
+    from pss_b200 import fastpath, search
+    n_max = 200_000
+    primes = orc.c_first_n_primes(n_max)
+    for power, allp in ((1, False), (2, False), (3, True)):
+        sums = orc.c_prefix_sums(primes, power)
+        targets = [sums[0], sums[6], sums[6] + 1, sums[99_999], sums[-1], sums[-1] + 1, 0, 10 ** 40]
+        for op in ("==", "<=", ">"):
+            many = search.search_many(targets, n_max, power=power, op=op, all_powers=allp)
+            for t, o in zip(targets, many):
+                one = search.search(t, n_max, power=power, op=op, all_powers=allp)
+                assert o.first() == one.first() and o.last_prime == one.last_prime, (power, op, t)
+                assert [(p.match_count, p.first_match_n, p.last_match_n, p.cross_n, p.final_sum) for p in o.powers] == \
+                       [(p.match_count, p.first_match_n, p.last_match_n, p.cross_n, p.final_sum) for p in one.powers]
+    # brute force: which primesum(n,k) values are members of the sequence?
+    for fn, power in (("fibonacci", 1), ("fibonacci", 2), ("factorial", 1), ("catalan", 1), ("tri", 2)):
+        sums = orc.c_prefix_sums(primes[:5000], power)
+        f = search.RHS_SEQUENCES[fn]
+        exp = []
+        for m in range(0, 400):
+            v = f(m)
+            if v > sums[-1]:
+                break
+            lo = int(np.searchsorted(np.array(sums, dtype=object), v))
+            if lo < len(sums) and sums[lo] == v:
+                exp.append({"m": m, "n": lo + 1})
+        got = search.for_any_sequence(fn, 5000, 399, power=power, m_min=0)
+        assert got == exp, (fn, power, got, exp)
+    # primesum(n,1): 2 = F(3), 5 = F(5); through the recogniser with the reference's output format
+    lines, rc = fastpath.try_fast_query("for_any primesum(n,1) == fibonacci(m)", {"n": 1000, "m": 60})
+    assert rc == 0 and lines[:2] == ["Found: m=3, n=1", "Found: m=5, n=2"]
+    lines, rc = fastpath.try_fast_query("does_exist primesum(n,2) == factorial(m)", {"n": 1000, "m": 30})
+    assert (lines, rc) == (["No match found within bounds."], 1) or rc == 0

@@ -295,9 +295,15 @@ def test_fastpath_recogniser_host_side(orc):
         assert fastpath._trisum(b) == orc.trisum(b)
     assert fastpath._trisum(666).bit_length() == 325
     # shapes that are NOT the hot path stay with the generic evaluator
-    for expr in ("fibonacci(n) == 8", "primesum(n,2) + 1 == 667", "does_exist primesum(n,2) == fibonacci(m)",
+    for expr in ("fibonacci(n) == 8", "primesum(n,2) + 1 == 667", "does_exist primesum(n,2) == fibonacci(m) + 1",
+                 "does_exist primesum(n,2) < fibonacci(m)", "does_exist primesum(n,2) == fibonacci(n)",
                  "for_any primesum(n,2) < tri(m)", "verify primesum(7,2) == 666", "primesum(n, n) == 4"):
         assert fastpath.try_fast_query(expr, {"n": 10, "m": 10}) is None, expr
+    assert fastpath._RHS_CALL.match("fibonacci(m)").groupdict() == {"fn": "fibonacci", "arg": "m"}
+    from pss_b200 import search
+    assert [search.RHS_SEQUENCES["fibonacci"](i) for i in range(11)] == [0, 1, 1, 2, 3, 5, 8, 13, 21, 34, 55]     # utils/sequences.py:83-117
+    assert [search.RHS_SEQUENCES["catalan"](i) for i in range(10)] == [1, 1, 2, 5, 14, 42, 132, 429, 1430, 4862]  # :160-200
+    assert [search.RHS_SEQUENCES["factorial"](i) for i in (0, 1, 5, 10)] == [1, 1, 120, 3628800]                  # :120-157
     m = fastpath._EXPR.match("for_any primesum(n,p) >= 8944")
     assert m.groupdict() == {"quant": "for_any", "nvar": "n", "parg": "p", "op": ">=", "rhs": "8944"}
     assert fastpath.format_match({"n": 7, "m": 36}) == "Found: m=36, n=7"                      # utils/cli.py:1253,1271
