@@ -70,7 +70,7 @@ struct pss_handle {
     u32 tile_bytes = 224 * 1024;   // one 1024-thread CTA per SM (tools/tune_sieve.py, profiles/r01/tune_sieve_*.json)
     u32 sieve_threads = 1024;
     u32 n_pat = 4;
-    u32 warp_wide_div = 160;    // p < tile_bytes / div -> dense (one warp per prime, skewed conflict-free lanes), else one lane per prime
+    u32 warp_wide_div = 104;    // p < tile_bytes / div -> dense (one warp per prime, skewed conflict-free lanes), else one lane per prime
     int search_path = 0;       // 0: fused (scan straight from the bitmap), 1: materialised u64 primes
     int compare_exhaustive = 0;  // 1: the compare pass walks every prime; 0: interval pruning (PSS_COMPARE_EXHAUSTIVE / pss_set_compare_mode)
     int reduce_moments = 1;    // block sums from moments (k = 2: per-byte tables; other k <= 5: per-prime small moments);
@@ -363,8 +363,8 @@ int sieve_range(pss_handle* h, u64 lo, u64 hi, bool defer_sync = false) {
         auto b = std::lower_bound(h->h_base.begin(), h->h_base.end(), h->base_first_prime);
         auto e = std::upper_bound(h->h_base.begin(), h->h_base.end(), (u32)std::min<u64>(lim, 0xFFFFFFFFull));
         sp.n_base = (e > b) ? (u32)(e - b) : 0;
-        // dense primes need at least 34 hits per lane: p <= tile / 136
-        const u32 warp_lim = tile_bytes / std::max<u32>(h->warp_wide_div, 136);
+        // dense primes need at least 17 hits per lane (18 <= tile / 4p): p <= tile / 72
+        const u32 warp_lim = tile_bytes / std::max<u32>(h->warp_wide_div, 72);
         sp.n_warp_wide = (e > b) ? (u32)(std::lower_bound(b, e, warp_lim) - b) : 0;
         // sparse batches: warp-uniform trip counts per strand, staged once per (tile size, prime table)
         {
@@ -1420,7 +1420,9 @@ int pss_peer_search(pss_handle* h, uint64_t lo, uint64_t hi_excl, const pss_sear
     const u32 K = a->power_max, np = n_powers_of(K, multi);
     const u32 world = (u32)h->peer_world, rank = (u32)h->peer_rank;
     const u64 epoch = ++h->peer_epoch;
-    const long long watchdog = 4000000000ll;   // ~2 s at 1.97 GHz
+    // watchdog of the device-side waits: ranks may enter a query skewed (first-call allocations, host jitter), but a
+    // rank that died must not leave the others spinning forever.  PSS_PEER_TIMEOUT_MS, default 10 s.
+    const long long watchdog = (long long)env_u32("PSS_PEER_TIMEOUT_MS", 10000) * 2000000ll;   // ~2e6 cycles per ms
 
     // ---- phase A: sieve + block sums + column scan of this rank's slice (enqueued, not synchronised)
     PSS_TRY(sieve_range(h, lo, hi_excl, true));

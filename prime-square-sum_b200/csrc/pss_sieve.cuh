@@ -157,8 +157,8 @@ __global__ void __launch_bounds__(THREADS, (THREADS <= 768) ? 2 : 1) k_sieve(con
             item = __shfl_sync(0xFFFFFFFFu, item, 0);
             if (item >= n_items) break;
             if (item < n_dense) {
-                // dense prime (p <= tile/136): lane -> (strand j, sub-sequence s), word stride p (byte stride 4p),
-                // constant mask; every lane has count = H-1 .. H+1 >= 33 hits (H = tile / 4p).
+                // dense prime (p <= tile/72): lane -> (strand j, sub-sequence s), word stride p (byte stride 4p),
+                // constant mask; every lane has count = H-1 .. H+1 >= 17 hits (H = tile / 4p).
                 // Bank-conflict-free order: lane l visits its hits rotated by e_l = (w_l - l) / p mod 32, i.e. first the
                 // last e_l hits (indices count-e_l .. count-1), then 0, 1, ...  Once a lane is past its wrap-around it
                 // addresses bank (l + it*p) mod 32 in iteration it: from iteration 32 on the 32 lanes hit the 32 different
@@ -174,23 +174,39 @@ __global__ void __launch_bounds__(THREADS, (THREADS <= 768) ? 2 : 1) k_sieve(con
                 const u32 x = first_hit(p, c, r, j == 0, B0) + s * p;  // x < 4p unless special (then x < 5p)
                 const u32 mask = ~(1u << (((x & 3u) << 3) + (cb >> 24)));
                 const u32 w = x >> 2;
-                const u32 e = special ? 0u : (((w - lane) * inv_mod64(p)) & 31u);
                 const u32 step = p << 2;
-                const u32 H = tile_bytes / step;                       // >= 34 (host: n_warp_wide)
+                const u32 H = tile_bytes / step;                       // >= 18 (host: n_warp_wide)
+                // full rotation (mod 32) needs 33 hits per lane; with 17..32 hits the rotation is taken mod 16: lanes l and
+                // l + 16 then share a bank class and collide half of the time (2 wavefronts instead of ~3.5 unordered)
+                const bool full = H >= 34u;
+                const u32 e = special ? 0u : (((w - lane) * inv_mod64(p)) & (full ? 31u : 15u));
                 const u32 b0 = w << 2;                                 // byte offset of hit 0 (< 2 * step)
                 const u32 count = H - 1u + ((b0 + (H - 1u) * step < tile_bytes) ? 1u : 0u) + ((b0 + H * step < tile_bytes) ? 1u : 0u);
                 const u32 span = count * step;
                 u32 a = b0 + span - e * step;                          // hit count - e  (e = 0: wraps before the first access)
+                if (full) {
 #pragma unroll
-                for (u32 it = 0; it < 32u; ++it) {                     // lanes wrap around at it == e
-                    if (it == e) a -= span;
-                    cross(a, mask);
-                    a += step;
-                }
+                    for (u32 it = 0; it < 32u; ++it) {                 // lanes wrap around at it == e
+                        if (it == e) a -= span;
+                        cross(a, mask);
+                        a += step;
+                    }
 #pragma unroll 4
-                for (u32 it = 32u; it + 1u < H; ++it) {                // steady state: hits e.. of every lane, conflict free
-                    cross(a, mask);
-                    a += step;
+                    for (u32 it = 32u; it + 1u < H; ++it) {            // steady state: hits e.. of every lane, conflict free
+                        cross(a, mask);
+                        a += step;
+                    }
+                } else {
+#pragma unroll
+                    for (u32 it = 0; it < 16u; ++it) {
+                        if (it == e) a -= span;
+                        cross(a, mask);
+                        a += step;
+                    }
+                    for (u32 it = 16u; it + 1u < H; ++it) {
+                        cross(a, mask);
+                        a += step;
+                    }
                 }
 #pragma unroll
                 for (u32 it = H - 1u; it <= H; ++it) {                 // lanes with count = H, H + 1; the others AND into the
