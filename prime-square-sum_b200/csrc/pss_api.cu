@@ -94,6 +94,7 @@ struct pss_handle {
     u32 sv_tile_bytes = 0, sv_n_tiles = 0;
     bool sv_valid = false;
     bool sv_pending = false;   // sieve enqueued, count not read back yet (sieve_finish)
+    bool sv_total_from_reduce = false;   // deferred sieve: no tile-count scan, the total comes from the block sums
     bool bs_pending = false;   // reduce enqueued, column totals not read back yet (reduce_finish)
 
     // resident primes
@@ -300,8 +301,8 @@ int launch_sieve(pss_handle* h, const SieveParams& sp, u32 grid) {
 void sieve_finish(pss_handle* h) {
     if (!h->sv_pending) return;
     h->sv_pending = false;
-    h->sv_total = h->h_back->sv_total;
-    h->sv_valid = true;
+    h->sv_total = h->sv_total_from_reduce ? 0 : h->h_back->sv_total;
+    h->sv_valid = !h->sv_total_from_reduce;    // without the tile prefix the bitmap cannot be compacted
     h->acc.ms_sieve += ev_ms(h, 0, 1);
     h->acc.ms_count_scan += ev_ms(h, 1, 2);
 }
@@ -416,11 +417,17 @@ int sieve_range(pss_handle* h, u64 lo, u64 hi, bool defer_sync = false) {
     u64 c235 = 0;
     for (u64 q : {2ull, 3ull, 5ull})
         if (q >= lo && q < hi) ++c235;
-    k_scan_tile_counts<<<1, 1024, 0, h->stream>>>(sp.tile_counts, n_tiles, c235, static_cast<u64*>(h->tile_prefix.p));
-    CU_TRY(h, cudaGetLastError());
-    h->launches++;
+    // the per-tile prefix of the prime counts is only needed by the compaction path; a deferred (query-chain) sieve
+    // takes its total from the block-sum pass instead (reduce_finish)
+    h->sv_total_from_reduce = defer_sync;
+    if (!defer_sync) {
+        k_scan_tile_counts<<<1, 1024, 0, h->stream>>>(sp.tile_counts, n_tiles, c235, static_cast<u64*>(h->tile_prefix.p));
+        CU_TRY(h, cudaGetLastError());
+        h->launches++;
+    }
     CU_TRY(h, cudaEventRecord(h->ev[2], h->stream));
-    CU_TRY(h, cudaMemcpyAsync(&h->h_back->sv_total, static_cast<u64*>(h->tile_prefix.p) + n_tiles, sizeof(u64), cudaMemcpyDeviceToHost, h->stream));
+    if (!defer_sync)
+        CU_TRY(h, cudaMemcpyAsync(&h->h_back->sv_total, static_cast<u64*>(h->tile_prefix.p) + n_tiles, sizeof(u64), cudaMemcpyDeviceToHost, h->stream));
     h->sv_lo = lo; h->sv_hi = hi; h->sv_B_start = B_start; h->sv_total = 0; h->sv_c235 = c235;
     h->sv_tile_bytes = tile_bytes; h->sv_n_tiles = n_tiles;
     h->acc.sieve_lo = lo;
@@ -715,9 +722,12 @@ int reduce_finish(pss_handle* h) {
             c = (v >> 32) + (c >> 32) + (lo >> 32);
         }
     }
-    if (h->bs_count != h->sv_total)
+    if (h->sv_total_from_reduce) {
+        h->sv_total = h->bs_count;
+    } else if (h->bs_count != h->sv_total) {
         return fail(h, PSS_EINTERNAL, "bitmap reduce counted %llu primes, sieve counted %llu", (unsigned long long)h->bs_count,
                     (unsigned long long)h->sv_total);
+    }
     h->bs_valid = true;
     return PSS_OK;
 }
