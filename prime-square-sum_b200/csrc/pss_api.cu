@@ -94,6 +94,8 @@ struct pss_handle {
     u32 sv_tile_bytes = 0, sv_n_tiles = 0;
     bool sv_valid = false;
     bool sv_pending = false;   // sieve enqueued, count not read back yet (sieve_finish)
+    int occ_cache = 0;                   // resident sieve CTAs per SM for (occ_cache_threads, occ_cache_tile)
+    u32 occ_cache_threads = 0, occ_cache_tile = 0;
     bool sv_total_from_reduce = false;   // deferred sieve: no tile-count scan, the total comes from the block sums
     bool bs_pending = false;   // reduce enqueued, column totals not read back yet (reduce_finish)
 
@@ -324,8 +326,13 @@ int sieve_range(pss_handle* h, u64 lo, u64 hi, bool defer_sync = false) {
     const u64 n_bytes = B_end - B_start;
     // tile size: at most the tuned size, chosen so that the tile count is a whole number of rounds of the resident
     // grid (tiles are handed out round-robin: no partial last round, no idle SMs at the tail)
-    int occ = 0;
-    PSS_TRY(sieve_occupancy(h, h->sieve_threads, h->tile_bytes, &occ));
+    int occ = h->occ_cache;
+    if (h->occ_cache_threads != h->sieve_threads || h->occ_cache_tile != h->tile_bytes) {   // queried once per tuning
+        PSS_TRY(sieve_occupancy(h, h->sieve_threads, h->tile_bytes, &occ));
+        h->occ_cache = occ;
+        h->occ_cache_threads = h->sieve_threads;
+        h->occ_cache_tile = h->tile_bytes;
+    }
     if (occ < 1) return fail(h, PSS_EINTERNAL, "sieve tile of %u bytes does not fit shared memory", h->tile_bytes);
     const u32 grid_max = (u32)(h->sm_count * occ);
     u32 tile_bytes = h->tile_bytes;
