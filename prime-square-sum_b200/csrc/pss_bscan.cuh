@@ -835,18 +835,20 @@ __global__ void __launch_bounds__(1024) k_scan_columns(const u64* in, u64* out, 
     const u32 tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
     const u64* col = in + (u64)blockIdx.x * stride;
     u64* o = out + (u64)blockIdx.x * stride;
-    // every thread owns a contiguous run of the column: local sum -> one block-wide scan -> local prefixes
-    const u32 per = (n + 1023u) / 1024u;
-    const u32 begin = min(n, tid * per), end = min(n, begin + per);
+    // every warp owns a contiguous run of rows of 32 elements (coalesced loads): warp total -> one block-wide scan of
+    // the 32 totals -> row-by-row warp scans seeded with the warp's offset
+    const u32 rows = (n + 31u) / 32u;
+    const u32 rows_per_warp = (rows + 31u) / 32u;
+    const u32 r0 = min(rows, warp * rows_per_warp), r1 = min(rows, r0 + rows_per_warp);
     u64 sum = 0;
-    for (u32 i = begin; i < end; ++i) sum += col[i];
-    u64 incl = sum;
-#pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-        const u64 up = __shfl_up_sync(0xFFFFFFFFu, incl, d);
-        if (lane >= (u32)d) incl += up;
+#pragma unroll 4
+    for (u32 r = r0; r < r1; ++r) {
+        const u32 i = r * 32u + lane;
+        sum += (i < n) ? col[i] : 0ull;
     }
-    if (lane == 31) s_warp[warp] = incl;
+#pragma unroll
+    for (int d = 16; d >= 1; d >>= 1) sum += __shfl_xor_sync(0xFFFFFFFFu, sum, d);
+    if (lane == 0) s_warp[warp] = sum;
     __syncthreads();
     if (warp == 0) {
         const u64 w = s_warp[lane];
@@ -859,12 +861,21 @@ __global__ void __launch_bounds__(1024) k_scan_columns(const u64* in, u64* out, 
         s_warp[lane] = wi - w;
     }
     __syncthreads();
-    u64 run = s_warp[warp] + incl - sum;
-    for (u32 i = begin; i < end; ++i) {
-        o[i] = run;
-        run += col[i];
+    u64 run = s_warp[warp];
+#pragma unroll 2
+    for (u32 r = r0; r < r1; ++r) {
+        const u32 i = r * 32u + lane;
+        const u64 v = (i < n) ? col[i] : 0ull;
+        u64 incl = v;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const u64 up = __shfl_up_sync(0xFFFFFFFFu, incl, d);
+            if (lane >= (u32)d) incl += up;
+        }
+        if (i < n) o[i] = run + incl - v;
+        run += __shfl_sync(0xFFFFFFFFu, incl, 31);
     }
-    if (tid == 1023) o[n] = run;
+    if (warp == 31 && lane == 0) o[n] = run;     // the last warp's running sum is the column total (also for empty runs)
 }
 
 }  // namespace pss
