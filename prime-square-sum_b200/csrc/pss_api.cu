@@ -90,6 +90,7 @@ struct pss_handle {
 
     // sieve workspace / state of the last sieve
     DevBuf bitmap, chunk_counts, tile_counts, tile_prefix, tile_nact;
+    DevBuf sieve_prof;   // PSS_SIEVE_PROF=1: k_sieve cycle counters, printed by pss_close
     u64 sv_lo = 0, sv_hi = 0, sv_B_start = 0, sv_total = 0, sv_c235 = 0;
     u32 sv_tile_bytes = 0, sv_n_tiles = 0;
     bool sv_valid = false;
@@ -293,7 +294,16 @@ int sieve_occupancy(pss_handle* h, u32 threads, u32 tile_bytes, int* occ) {
 
 template <int THREADS>
 int launch_sieve(pss_handle* h, const SieveParams& sp, u32 grid) {
-    k_sieve<THREADS><<<grid, THREADS, (size_t)sp.tile_bytes + kSieveScratchBytes, h->stream>>>(sp);
+    if (sp.prof && THREADS == 1024) {
+        static bool attr_set = false;
+        if (!attr_set) {
+            CU_TRY(h, cudaFuncSetAttribute(k_sieve<1024, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(h->smem_optin - 1024)));
+            attr_set = true;
+        }
+        k_sieve<1024, true><<<grid, 1024, (size_t)sp.tile_bytes + kSieveScratchBytes, h->stream>>>(sp);
+    } else {
+        k_sieve<THREADS><<<grid, THREADS, (size_t)sp.tile_bytes + kSieveScratchBytes, h->stream>>>(sp);
+    }
     CU_TRY(h, cudaGetLastError());
     h->launches++;
     return PSS_OK;
@@ -411,6 +421,7 @@ int sieve_range(pss_handle* h, u64 lo, u64 hi, bool defer_sync = false) {
     sp.bitmap = static_cast<u32*>(h->bitmap.p);
     sp.chunk_counts = static_cast<u32*>(h->chunk_counts.p);
     sp.tile_counts = static_cast<u32*>(h->tile_counts.p);
+    sp.prof = static_cast<unsigned long long*>(h->sieve_prof.p);
 
     CU_TRY(h, cudaEventRecord(h->ev[0], h->stream));
     switch (h->sieve_threads) {
@@ -981,6 +992,10 @@ int pss_open(int device, pss_handle** out) {
     h->reduce_moments = (int)env_u32("PSS_REDUCE_MOMENTS", (u32)h->reduce_moments);
     h->compare_exhaustive = (int)env_u32("PSS_COMPARE_EXHAUSTIVE", (u32)h->compare_exhaustive);
     h->tile_bytes = std::max<u32>(8192, std::min<u32>((h->tile_bytes / kChunkBytes) * kChunkBytes, kMaxTileBytes));
+    if (env_u32("PSS_SIEVE_PROF", 0) && cudaMalloc(&h->sieve_prof.p, 64) == cudaSuccess) {
+        h->sieve_prof.cap = 64;
+        cudaMemset(h->sieve_prof.p, 0, 64);
+    }
     if (h->sieve_threads != 256 && h->sieve_threads != 512 && h->sieve_threads != 768) h->sieve_threads = 1024;
     auto cleanup = [&](int rc) {
         pss_close(h);
@@ -1006,6 +1021,14 @@ int pss_close(pss_handle* h) {
     if (!h) return PSS_OK;
     cudaSetDevice(h->device);
     if (h->stream) cudaStreamSynchronize(h->stream);
+    if (h->sieve_prof.p) {   // instrumented sieve (PSS_SIEVE_PROF=1): where a tile's cycles went
+        unsigned long long c[8] = {0};
+        cudaMemcpy(c, h->sieve_prof.p, sizeof c, cudaMemcpyDeviceToHost);
+        const double n = c[3] ? (double)c[3] : 1.0;
+        fprintf(stderr, "[pss sieve prof] tiles=%llu cycles/tile: A=%.0f B=%.0f C=%.0f | warp-cycles/tile in B: dense32=%.0f dense16=%.0f sparse=%.0f large=%.0f\n", c[3],
+                c[0] / n, c[1] / n, c[2] / n, c[4] / n, c[5] / n, c[6] / n, c[7] / n);
+        cudaFree(h->sieve_prof.p);
+    }
     for (DevBuf* b : {&h->d_base, &h->d_base_inv, &h->d_base_strand, &h->d_batch_geo, &h->cols, &h->col_prefix, &h->thread_rec, &h->warp_rec, &h->tile_nact, &h->tri_buf, &h->bitmap, &h->chunk_counts, &h->tile_counts, &h->tile_prefix, &h->primes, &h->status, &h->agg,
                       &h->incl, &h->misc, &h->prefix_out, &h->user_vals})
         if (b->p) cudaFree(b->p);

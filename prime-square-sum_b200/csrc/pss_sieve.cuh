@@ -50,6 +50,7 @@ struct SieveParams {
     u32* bitmap;         // n_tiles * tile_bytes / 4 words
     u32* chunk_counts;   // n_tiles * tile_bytes / kChunkBytes
     u32* tile_counts;    // n_tiles
+    unsigned long long* prof;   // PSS_SIEVE_PROF=1: cycle counters (phase A / B / C per CTA; warp time per item class), else null
 };
 
 // ---- pattern construction -------------------------------------------------------------------
@@ -110,7 +111,7 @@ __device__ __forceinline__ u32 inv_mod64(u32 p) { return p * (2u - p * p); }
 // absorbs the cross-offs of lanes that are outside the tile in a given iteration (see the dense phase)
 constexpr u32 kSieveScratchBytes = 128;
 
-template <int THREADS>
+template <int THREADS, bool PROF = false>
 __global__ void __launch_bounds__(THREADS, (THREADS <= 768) ? 2 : 1) k_sieve(const SieveParams P) {
     extern __shared__ uint4 smem4[];
     __shared__ u64 s_off16[kMaxPatterns];
@@ -130,6 +131,10 @@ __global__ void __launch_bounds__(THREADS, (THREADS <= 768) ? 2 : 1) k_sieve(con
 
     for (u32 t = blockIdx.x; t < P.n_tiles; t += gridDim.x) {
         const u64 B0 = P.B_start + (u64)t * tile_bytes;
+        constexpr bool prof = PROF;   // instrumented instantiation (PSS_SIEVE_PROF=1)
+        long long pc0 = 0, pc1 = 0, pc2 = 0;
+        unsigned long long pw[4] = {0, 0, 0, 0};
+        if (prof) pc0 = clock64();
         if (tid < P.n_pat) s_off16[tid] = (B0 % P.pat_period16[tid]) >> 4;
         if (tid == 32) s_next = 0;
         __syncthreads();
@@ -144,6 +149,7 @@ __global__ void __launch_bounds__(THREADS, (THREADS <= 768) ? 2 : 1) k_sieve(con
             smem4[i] = v;
         }
         __syncthreads();
+        if (prof) pc1 = clock64();
 
         // ---- phase B: cross-offs.  Warps pull work items from a shared-memory queue (largest items first):
         //        items [0, n_dense)   one dense prime each (p < tile/128), whole warp, bank-conflict free
@@ -156,6 +162,9 @@ __global__ void __launch_bounds__(THREADS, (THREADS <= 768) ? 2 : 1) k_sieve(con
             if (lane == 0) item = atomicAdd(&s_next, 1u);
             item = __shfl_sync(0xFFFFFFFFu, item, 0);
             if (item >= n_items) break;
+            long long pi0 = 0;
+            u32 pcls = 0;
+            if (prof) pi0 = clock64();
             if (item < n_dense) {
                 // dense prime (p <= tile/72): lane -> (strand j, sub-sequence s), word stride p (byte stride 4p),
                 // constant mask; every lane has count = H-1 .. H+1 >= 17 hits (H = tile / 4p).
@@ -179,6 +188,7 @@ __global__ void __launch_bounds__(THREADS, (THREADS <= 768) ? 2 : 1) k_sieve(con
                 // full rotation (mod 32) needs 33 hits per lane; with 17..32 hits the rotation is taken mod 16: lanes l and
                 // l + 16 then share a bank class and collide half of the time (2 wavefronts instead of ~3.5 unordered)
                 const bool full = H >= 34u;
+                pcls = full ? 0u : 1u;
                 const u32 e = special ? 0u : (((w - lane) * inv_mod64(p)) & (full ? 31u : 15u));
                 const u32 b0 = w << 2;                                 // byte offset of hit 0 (< 2 * step)
                 const u32 count = H - 1u + ((b0 + (H - 1u) * step < tile_bytes) ? 1u : 0u) + ((b0 + H * step < tile_bytes) ? 1u : 0u);
@@ -237,6 +247,7 @@ __global__ void __launch_bounds__(THREADS, (THREADS <= 768) ? 2 : 1) k_sieve(con
                 const u32 cbs[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
                 const u32 r = on ? tile_mod(B0, p, inv, wide) : 0u;
                 const u32 rot = (p & 3u) << 3;
+                pcls = (n_uni == 0u && n_rag <= 2u) ? 3u : 2u;
                 if (n_uni == 0u && n_rag <= 2u) {
                     // large primes (p > tile/2): at most two hits per strand -- straight-line code
                     const bool two = n_rag == 2u;
@@ -273,8 +284,15 @@ __global__ void __launch_bounds__(THREADS, (THREADS <= 768) ? 2 : 1) k_sieve(con
                     }
                 }
             }
+            if (prof) pw[pcls] += (unsigned long long)(clock64() - pi0);
         }
         __syncthreads();
+        if (prof) {
+            pc2 = clock64();
+            if (lane == 0)
+                for (u32 c = 0; c < 4; ++c)
+                    if (pw[c]) atomicAdd(P.prof + 4 + c, pw[c]);
+        }
 
         // ---- phase C: edge masks, popcounts, coalesced write-out of the bitmap tile
         const bool interior = (B0 * 30ull >= P.lo) && ((B0 + tile_bytes) * 30ull <= P.hi) && (B0 >= 4);
@@ -315,6 +333,13 @@ __global__ void __launch_bounds__(THREADS, (THREADS <= 768) ? 2 : 1) k_sieve(con
         }
         // s_off16 / s_cnt / tile are rewritten only after the next iteration's first barrier
         __syncthreads();
+        if (prof && tid == 0) {
+            const long long pc3 = clock64();
+            atomicAdd(P.prof + 0, (unsigned long long)(pc1 - pc0));
+            atomicAdd(P.prof + 1, (unsigned long long)(pc2 - pc1));
+            atomicAdd(P.prof + 2, (unsigned long long)(pc3 - pc2));
+            atomicAdd(P.prof + 3, 1ull);
+        }
     }
 }
 
