@@ -656,6 +656,39 @@ int launch_bscan_t(pss_handle* h, const BScanParams& bp) {
     return PSS_OK;
 }
 
+template <int K, bool MULTI>
+int launch_moments_t(pss_handle* h, const BScanParams& bp) {
+    static int occ = 0;
+    if (!occ) {
+        CU_TRY(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_bitmap_moments<K, MULTI>, kBsThreads, 0));
+        if (occ < 1) occ = 1;
+    }
+    const u32 grid = std::min<u32>(bp.n_tiles, (u32)(h->sm_count * occ));
+    k_bitmap_moments<K, MULTI><<<grid, kBsThreads, 0, h->stream>>>(bp);
+    CU_TRY(h, cudaGetLastError());
+    h->launches++;
+    return PSS_OK;
+}
+int launch_moments(pss_handle* h, const BScanParams& bp, u32 K, bool multi) {
+    if (!multi) {
+        switch (K) {
+            case 1: return launch_moments_t<1, false>(h, bp);
+            case 2: return launch_moments_t<2, false>(h, bp);
+            case 3: return launch_moments_t<3, false>(h, bp);
+            case 4: return launch_moments_t<4, false>(h, bp);
+            case 5: return launch_moments_t<5, false>(h, bp);
+        }
+    } else {
+        switch (K) {
+            case 2: return launch_moments_t<2, true>(h, bp);
+            case 3: return launch_moments_t<3, true>(h, bp);
+            case 4: return launch_moments_t<4, true>(h, bp);
+            case 5: return launch_moments_t<5, true>(h, bp);
+        }
+    }
+    return fail(h, PSS_EINVAL, "unsupported power");
+}
+
 template <int MODE>
 int launch_bscan(pss_handle* h, const BScanParams& bp, u32 K, bool multi) {
     if (!multi) {
@@ -793,8 +826,10 @@ int bitmap_reduce(pss_handle* h, u32 K, bool multi, bool defer_sync = false) {
         k_bitmap_moments2<<<grid, kBsThreads, 0, h->stream>>>(bp);
         CU_TRY(h, cudaGetLastError());
         h->launches++;
+    } else if (K <= 5 && h->reduce_moments) {
+        PSS_TRY(launch_moments(h, bp, K, multi));
     } else {
-        bp.reduce_chain = h->reduce_moments ? 0u : 1u;
+        bp.reduce_chain = 1u;
         PSS_TRY(launch_bscan<kBsReduce>(h, bp, K, multi));
     }
     k_scan_columns<<<ncols, 1024, 0, h->stream>>>(bp.cols, static_cast<u64*>(h->col_prefix.p), bp.n_tiles, bp.col_stride);

@@ -731,6 +731,141 @@ __global__ void __launch_bounds__(kBsThreads, bs_min_blocks<K, MULTI>()) k_bitma
     }
 }
 
+// ---- reduce pass for k <= 5 (single power or all powers 1..K) from the small moments, as its own kernel --------------
+// Same records as k_bitmap_scan<K, MULTI, kBsReduce> with reduce_chain = 0 (bit-identical), but compiled on its own: the
+// walk needs ~10 accumulator registers and the powers are expanded and written out ONE AT A TIME, so the kernel fits 64
+// registers and four CTAs per SM stay resident (the generic instantiation also carries the multi-limb power chain and
+// holds all 29 limbs of a K = 5 record at once: 128 registers, two CTAs, issue-starved).
+template <int J, int K, bool MULTI>
+__device__ __forceinline__ void moments_emit(const BScanParams& P, const BsMomFn<K>& f, u32 m0, u32 blo, u32 bhi, bool has_small,
+                                              u64 gthread, u64 wt, u32 tile, u32 lane) {
+    using Lay = Layout<K, MULTI>;
+    if constexpr (J < Lay::NP) {
+        constexpr int KK = MULTI ? J + 1 : K;
+        constexpr int W = Lay::width(J), OFF = Lay::offset(J);
+        u32 out[W];
+        expand_moments<KK, K>(out, f, m0, blo, bhi);
+        if (has_small) {                      // 2, 3, 5 (one thread of the whole grid)
+            for (u32 i = 0; i < P.n_small; ++i) {
+                u64 pw = 1;
+                for (int e = 0; e < KK; ++e) pw *= P.small_primes[i];   // <= 5^5
+                const u32 t[2] = {(u32)pw, (u32)(pw >> 32)};
+                acc_add<0, W, 2>(out, t);
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < W; ++i) P.thread_rec[(u64)(1 + OFF + i) * P.thread_stride + gthread] = out[i];
+#pragma unroll
+        for (int d = 16; d >= 1; d >>= 1) {
+            u32 o[W];
+#pragma unroll
+            for (int i = 0; i < W; ++i) o[i] = __shfl_xor_sync(0xFFFFFFFFu, out[i], d);
+            acc_add<0, W, W>(out, o);
+        }
+        if (lane == 0) {
+#pragma unroll
+            for (int i = 0; i < W; ++i) {
+                P.warp_rec[(u64)(1 + OFF + i) * P.warp_stride + wt] = out[i];
+                atomicAdd(reinterpret_cast<unsigned long long*>(P.cols + (u64)(1 + OFF + i) * P.col_stride + tile), (unsigned long long)out[i]);
+            }
+        }
+        moments_emit<J + 1, K, MULTI>(P, f, m0, blo, bhi, has_small, gthread, wt, tile, lane);
+    }
+}
+
+// Lean walk for the moments kernel: only the offset o = p - B of every prime is needed (no 64-bit prime value), the word
+// refill is four predicated instructions, and the accumulators are fed with IMAD.WIDE accumulate forms / one carry chain:
+// about 30 instructions per prime for K = 5 (the generic walk_words + BsMomFn pair compiles to 49).
+template <int K>
+__device__ __forceinline__ void walk_moments(u32 row_saddr, BsMomFn<K>& f) {
+    u32 addr = row_saddr, w = 0, woff = 0u - 120u;
+    const u32 end = row_saddr + 4u * (u32)kWordsPerThread;     // the sentinel slot
+    u32 m1 = 0, m5a = 0, m5b = 0, m5c = 0;
+    u64 m2 = 0, m3 = 0, m4 = 0;
+    bool alive = true;
+    while (alive) {
+        // exhausted word: fetch the next one (the row ends with a zero sentinel)
+        asm("{\n\t.reg .pred q;\n\tsetp.eq.u32 q, %0, 0;\n\t@q ld.shared.u32 %0, [%1];\n\t@q add.u32 %1, %1, 4;\n\t@q add.u32 %2, %2, 120;\n\t}"
+            : "+r"(w), "+r"(addr), "+r"(woff));
+        // a plain if-region, so the warp reconverges every iteration (a lane that meets an empty word loses one trip; a
+        // `continue` here makes the compiler park that lane until every other lane leaves the loop: 19 of 32 lanes busy)
+        if (w == 0) {
+            alive = (addr <= end);      // empty word (rare): try the next one; past the sentinel: done
+        } else {
+        const u32 m = msb_index(w);
+        w ^= (1u << m);
+        const u32 o = woff + msb_value_offset(m);     // < 2880
+        m1 += o;
+        if constexpr (K >= 2) {
+            const u32 o2 = o * o;                     // < 2^23
+            asm("mad.wide.u32 %0, %1, %1, %0;" : "+l"(m2) : "r"(o));
+            if constexpr (K >= 3) asm("mad.wide.u32 %0, %1, %2, %0;" : "+l"(m3) : "r"(o2), "r"(o));
+            if constexpr (K >= 4) {
+                const u64 o4 = (u64)o2 * o2;          // < 2^46
+                m4 += o4;
+                if constexpr (K >= 5) {
+                    const u64 t = (u64)(u32)o4 * o + ((u64)((u32)(o4 >> 32) * o) << 32);   // o^5 < 2^58
+                    asm("add.cc.u32 %0, %0, %3;\n\taddc.cc.u32 %1, %1, %4;\n\taddc.u32 %2, %2, 0;"
+                        : "+r"(m5a), "+r"(m5b), "+r"(m5c)
+                        : "r"((u32)t), "r"((u32)(t >> 32)));
+                }
+            }
+        }
+        }
+    }
+    f.m1 = m1; f.m2 = m2; f.m3 = m3; f.m4 = m4;
+    f.m5lo = ((u64)m5b << 32) | m5a;
+    f.m5hi = m5c;
+}
+
+template <int K, bool MULTI>
+__global__ void __launch_bounds__(kBsThreads, 4) k_bitmap_moments(const __grid_constant__ BScanParams P) {
+    constexpr int T = kBsThreads, NWARP = T / 32, WPT = kWordsPerThread, PAD = WPT + 1, WARP_WORDS = 32 * WPT;
+    __shared__ u32 s_words[T * PAD];
+    const u32 tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+    u32* my_warp_words = s_words + warp * 32 * PAD;
+    const u32* my_words = my_warp_words + lane * PAD;
+    my_warp_words[lane * PAD + WPT] = 0u;        // sentinel word of this thread's row (never overwritten)
+    const u64 n_warp_tiles = (u64)P.n_tiles * NWARP;
+    const u64 warp_stride = (u64)gridDim.x * NWARP;
+    for (u64 wt = (u64)blockIdx.x * NWARP + warp; wt < n_warp_tiles; wt += warp_stride) {
+        const u32 tile = (u32)(wt / NWARP);
+        const u64 word0 = wt * WARP_WORDS;
+        {   // warp-local staging: coalesced uint4 loads -> padded blocked layout, bit-reversed
+            const uint4* g4 = reinterpret_cast<const uint4*>(P.bitmap + word0);
+            __syncwarp();
+#pragma unroll
+            for (int r = 0; r < WPT / 4; ++r) {
+                const u32 q = r * 32 + lane;
+                uint4 v = make_uint4(0, 0, 0, 0);
+                if (word0 + 4ull * q + 4 <= P.n_words) v = __ldg(g4 + q);
+                const u32 wl = 4u * q;
+                const u32 dst = (wl / WPT) * PAD + (wl % WPT);
+                my_warp_words[dst] = __brev(v.x); my_warp_words[dst + 1] = __brev(v.y);
+                my_warp_words[dst + 2] = __brev(v.z); my_warp_words[dst + 3] = __brev(v.w);
+            }
+            __syncwarp();
+        }
+        const u64 value_base = (P.B_start + 4ull * (word0 + (u64)lane * WPT)) * 30ull;
+        const bool has_small = (wt == 0 && lane == 0 && P.n_small > 0);
+        const u64 gthread = wt * 32 + lane;
+        u32 cnt = 0;
+#pragma unroll
+        for (int i = 0; i < WPT; ++i) cnt += __popc(my_words[i]);
+        BsMomFn<K> mf{(u32)value_base, 0u, 0ull, 0ull, 0ull, 0ull, 0u};
+        walk_moments<K>((u32)__cvta_generic_to_shared(my_words), mf);   // per prime: small moments of p - B
+        const u32 m0 = cnt;
+        if (has_small) cnt += P.n_small;
+        P.thread_rec[gthread] = cnt;
+        moments_emit<0, K, MULTI>(P, mf, m0, (u32)value_base, (u32)(value_base >> 32), has_small, gthread, wt, tile, lane);
+        cnt = __reduce_add_sync(0xFFFFFFFFu, cnt);
+        if (lane == 0) {
+            P.warp_rec[wt] = cnt;
+            atomicAdd(reinterpret_cast<unsigned long long*>(P.cols + tile), (unsigned long long)cnt);
+        }
+    }
+}
+
 // s_lut[(byte q of w) * 32 + lane] through its 32-bit shared address (lut_lane = &s_lut[lane])
 __device__ __forceinline__ u32 lut_at(u32 lut_lane, u32 w, int q) {
     u32 b, e;
