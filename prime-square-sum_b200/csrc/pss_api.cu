@@ -73,7 +73,7 @@ struct pss_handle {
     u32 warp_wide_div = 104;    // p < tile_bytes / div -> dense (one warp per prime, skewed conflict-free lanes), else one lane per prime
     int search_path = 0;       // 0: fused (scan straight from the bitmap), 1: materialised u64 primes
     int compare_exhaustive = 0;  // 1: the compare pass walks every prime; 0: interval pruning (PSS_COMPARE_EXHAUSTIVE / pss_set_compare_mode)
-    int reduce_moments = 1;    // block sums from moments (k = 2: per-byte tables; other k <= 5: per-prime small moments);
+    int reduce_moments = 2;    // block sums from moments (k = 2: per-byte tables; other k <= 5: per-prime small moments);
                                // 0: multi-limb power chain per prime (PSS_REDUCE_MOMENTS)
 
     // patterns
@@ -658,6 +658,18 @@ int launch_bscan_t(pss_handle* h, const BScanParams& bp) {
 
 template <int K, bool MULTI>
 int launch_moments_t(pss_handle* h, const BScanParams& bp) {
+    if (h->reduce_moments >= 2) {   // byte-table form (default); PSS_REDUCE_MOMENTS=1 selects the per-prime walk
+        static int occ_t = 0;
+        if (!occ_t) {
+            CU_TRY(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_t, k_bitmap_moments_tab<K, MULTI>, kBsThreads, 0));
+            if (occ_t < 1) occ_t = 1;
+        }
+        const u32 grid_t = std::min<u32>(bp.n_tiles, (u32)(h->sm_count * occ_t));
+        k_bitmap_moments_tab<K, MULTI><<<grid_t, kBsThreads, 0, h->stream>>>(bp);
+        CU_TRY(h, cudaGetLastError());
+        h->launches++;
+        return PSS_OK;
+    }
     static int occ = 0;
     if (!occ) {
         CU_TRY(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_bitmap_moments<K, MULTI>, kBsThreads, 0));

@@ -866,6 +866,136 @@ __global__ void __launch_bounds__(kBsThreads, 4) k_bitmap_moments(const __grid_c
     }
 }
 
+// ---- reduce pass for k <= 5 WITHOUT touching individual primes (generalisation of k_bitmap_moments2) --------------------
+// Byte table: for a bitmap byte v, mu_i(v) = sum of R[j]^i over its set bits, i = 0..5, packed in one uint4
+//     .x = mu0 | mu3 << 12      .y = mu1 | mu2 << 14      .z = mu4      .w = mu5
+// The low field of .x / .y has head-room for every byte-index weight it is used with (sum_q q^5 mu0 <= 2208 < 2^12,
+// sum_q q^4 mu1 <= 11760 < 2^14), the high field may run off the top of the word where it is not needed, so ONE 32-bit
+// multiply-add forms the weighted sum of both fields:  X_e = sum_q q^e E_q  gives  A(e,i) = sum_q q^e mu_i(byte q).
+// Word moments about the word origin (byte q sits at 30 q):  w_j = sum_i C(j,i) 30^(j-i) A(j-i, i)  -- all below 2^32 except
+// w_5 (< 2^37).  Thread moments: words are folded from the last to the first; before a word is added the running moments
+// are re-based by 120 with the triangular scheme  M_j += 120 M_(j-1)  (j = K..t, passes t = 1..K), i.e. only
+// multiplications by the constant 120.  ~150 instructions per 32-bit word (5.3 primes) with every lane busy, against
+// ~44 per prime and 27 busy lanes for the walk.  The table is replicated 8x (32 KiB): lane l reads copy l & 7, so the
+// eight lanes of every LDS.128 phase hit eight different 16-byte bank groups (conflict free).
+__device__ __forceinline__ uint4 lut4_at(u32 lut_lane, u32 w, int q) {
+    u32 b;
+    uint4 e;
+    asm("prmt.b32 %0, %1, 0, %2;" : "=r"(b) : "r"(w), "r"(0x4440u + (u32)q));   // byte q, zero extended
+    asm("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(e.x), "=r"(e.y), "=r"(e.z), "=r"(e.w) : "r"(lut_lane + (b << 7)));
+    return e;
+}
+
+template <int K, bool MULTI>
+__global__ void __launch_bounds__(kBsThreads, 3) k_bitmap_moments_tab(const __grid_constant__ BScanParams P) {
+    constexpr int NWARP = kBsThreads / 32, WPT = kWordsPerThread, WARP_WORDS = 32 * WPT;
+    __shared__ uint4 s_lut[256 * 8];
+    {
+        const u32 v = threadIdx.x;     // kBsThreads == 256: one byte value per thread
+        u32 mu[6] = {0, 0, 0, 0, 0, 0};
+#pragma unroll
+        for (u32 j = 0; j < 8; ++j)
+            if ((v >> j) & 1u) {
+                const u32 r = wheel_residue(j);
+                u32 pw = 1;
+#pragma unroll
+                for (int i = 0; i < 6; ++i) { mu[i] += pw; pw *= r; }
+            }
+        const uint4 e = make_uint4(mu[0] | (mu[3] << 12), mu[1] | (mu[2] << 14), mu[4], mu[5]);
+        for (u32 k = 0; k < 8; ++k) s_lut[v * 8 + ((k + v) & 7u)] = e;
+    }
+    __syncthreads();
+    const u32 lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    const u32 lut_lane = (u32)__cvta_generic_to_shared(s_lut) + 16u * (lane & 7u);
+    const u64 n_warp_tiles = (u64)P.n_tiles * NWARP;
+    const u64 warp_stride = (u64)gridDim.x * NWARP;
+    for (u64 wt = (u64)blockIdx.x * NWARP + warp; wt < n_warp_tiles; wt += warp_stride) {
+        const u32 tile = (u32)(wt / NWARP);
+        const u64 word0 = wt * WARP_WORDS + (u64)lane * WPT;      // this thread's first word
+        const uint4* g4 = reinterpret_cast<const uint4*>(P.bitmap + word0);
+        // D(e,i) = sum over the thread's words of (word index)^e * w_i(word); rigorous worst cases (every bit set) put
+        // D04, D05, D14, D23, D32 beyond 32 bits, everything else below 2^32 (largest: D13 <= 3.81e9)
+        u32 D00 = 0, D01 = 0, D02 = 0, D03 = 0, D10 = 0, D11 = 0, D12 = 0, D13 = 0, D20 = 0, D21 = 0, D22 = 0, D30 = 0, D31 = 0,
+            D40 = 0, D41 = 0, D50 = 0;
+        u64 D04 = 0, D05 = 0, D14 = 0, D23 = 0, D32 = 0;
+#pragma unroll 1
+        for (int g = 0; g < WPT / 4; ++g) {
+            uint4 vv = make_uint4(0, 0, 0, 0);
+            if (word0 + 4ull * g + 4 <= P.n_words) vv = __ldg(g4 + g);
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                const u32 w = c == 0 ? vv.x : c == 1 ? vv.y : c == 2 ? vv.z : vv.w;
+                const u32 wi = 4u * (u32)g + (u32)c, wi2 = wi * wi, wi3 = wi2 * wi, wi4 = wi2 * wi2, wi5 = wi4 * wi;   // <= 23^5
+                const uint4 e0 = lut4_at(lut_lane, w, 0), e1 = lut4_at(lut_lane, w, 1), e2 = lut4_at(lut_lane, w, 2), e3 = lut4_at(lut_lane, w, 3);
+                // X(field, e) = sum_q q^e E_q
+                const u32 x00 = e0.x + e1.x + e2.x + e3.x;
+                const u32 x01 = e1.x + 2u * e2.x + 3u * e3.x;
+                const u32 y00 = e0.y + e1.y + e2.y + e3.y;
+                const u32 A00 = x00 & 0xFFFu, A10 = x01 & 0xFFFu;
+                const u32 A01 = y00 & 0x3FFFu;
+                const u32 w0 = A00, w1 = A01 + 30u * A10;
+                D00 += w0; D01 += w1;
+                D10 += wi * w0;
+                if constexpr (K >= 2) {
+                    const u32 x02 = e1.x + 4u * e2.x + 9u * e3.x;
+                    const u32 y01 = e1.y + 2u * e2.y + 3u * e3.y;
+                    const u32 A20 = x02 & 0xFFFu, A11 = y01 & 0x3FFFu, A02 = y00 >> 14;
+                    const u32 w2 = A02 + 60u * A11 + 900u * A20;
+                    D02 += w2; D11 += wi * w1; D20 += wi2 * w0;
+                    if constexpr (K >= 3) {
+                        const u32 x03 = e1.x + 8u * e2.x + 27u * e3.x;
+                        const u32 y02 = e1.y + 4u * e2.y + 9u * e3.y;
+                        const u32 A30 = x03 & 0xFFFu, A21 = y02 & 0x3FFFu, A12 = y01 >> 14, A03 = x00 >> 12;
+                        const u32 w3 = A03 + 90u * A12 + 2700u * A21 + 27000u * A30;
+                        D03 += w3; D12 += wi * w2; D21 += wi2 * w1; D30 += wi3 * w0;
+                        if constexpr (K >= 4) {
+                            const u32 x04 = e1.x + 16u * e2.x + 81u * e3.x;
+                            const u32 y03 = e1.y + 8u * e2.y + 27u * e3.y;
+                            const u32 z00 = e0.z + e1.z + e2.z + e3.z;
+                            const u32 A40 = x04 & 0xFFFu, A31 = y03 & 0x3FFFu, A22 = y02 >> 14, A13 = x01 >> 12, A04 = z00;
+                            const u32 w4 = A04 + 120u * A13 + 5400u * A22 + 108000u * A31 + 810000u * A40;   // <= 1.33e9
+                            D04 += w4; D13 += wi * w3; D22 += wi2 * w2; D31 += wi3 * w1; D40 += wi4 * w0;
+                            if constexpr (K >= 5) {
+                                const u32 x05 = e1.x + 32u * e2.x + 243u * e3.x;
+                                const u32 y04 = e1.y + 16u * e2.y + 81u * e3.y;
+                                const u32 z01 = e1.z + 2u * e2.z + 3u * e3.z;
+                                const u32 t00 = e0.w + e1.w + e2.w + e3.w;
+                                const u32 A50 = x05 & 0xFFFu, A41 = y04 & 0x3FFFu, A32 = y03 >> 14, A23 = x02 >> 12, A14 = z01, A05 = t00;
+                                const u32 inner = A14 + 60u * A23 + 1800u * A32 + 27000u * A41 + 162000u * A50;   // < 8.8e8
+                                const u64 w5 = (u64)A05 + 150ull * inner;
+                                D05 += w5; D14 += (u64)wi * w4; D23 += (u64)wi2 * w3; D32 += (u64)wi3 * w2; D41 += wi4 * w1; D50 += wi5 * w0;
+                            }
+                        }
+                    }
+                }
+            }
+        }
+        // thread moments about the thread origin (word i sits at 120 i):  M_j = sum_i C(j,i) 120^(j-i) D(j-i, i)
+        const u32 M0 = D00;
+        const u32 M1 = D01 + 120u * D10;
+        const u64 M2 = (u64)D02 + 240ull * D11 + 14400ull * D20;
+        const u64 M3 = (u64)D03 + 360ull * D12 + 43200ull * D21 + 1728000ull * D30;
+        const u64 M4 = D04 + 480ull * D13 + 86400ull * D22 + 6912000ull * D31 + 207360000ull * D40;
+        const unsigned __int128 M5 = (unsigned __int128)D05 + (unsigned __int128)D14 * 600u + (unsigned __int128)D23 * 144000u +
+                                     (unsigned __int128)D32 * 17280000u + (unsigned __int128)D41 * 1036800000u +
+                                     (unsigned __int128)D50 * 24883200000ull;
+        BsMomFn<K> mf{0u, M1, M2, M3, M4, (u64)M5, (u32)(M5 >> 64)};
+        u32 cnt = M0;
+        const u64 B = (P.B_start + 4ull * word0) * 30ull;
+        const bool has_small = (wt == 0 && lane == 0 && P.n_small > 0);
+        const u64 gthread = wt * 32 + lane;
+        const u32 m0 = cnt;
+        if (has_small) cnt += P.n_small;
+        P.thread_rec[gthread] = cnt;
+        moments_emit<0, K, MULTI>(P, mf, m0, (u32)B, (u32)(B >> 32), has_small, gthread, wt, tile, lane);
+        cnt = __reduce_add_sync(0xFFFFFFFFu, cnt);
+        if (lane == 0) {
+            P.warp_rec[wt] = cnt;
+            atomicAdd(reinterpret_cast<unsigned long long*>(P.cols + tile), (unsigned long long)cnt);
+        }
+    }
+}
+
 // s_lut[(byte q of w) * 32 + lane] through its 32-bit shared address (lut_lane = &s_lut[lane])
 __device__ __forceinline__ u32 lut_at(u32 lut_lane, u32 w, int q) {
     u32 b, e;

@@ -298,29 +298,35 @@ def test_fused_tile_boundaries(handle, orc):
 
 
 def test_moment_reduce_matches_walk_and_oracle(orc):
-    """block sums from moments (default: k = 2 per-byte tables, other k <= 5 per-prime small moments + one binomial
-    expansion per thread) against the per-prime multi-limb power chain and the oracle: slice counts and slice sums on
-    ragged ranges (range edges inside a byte, below 7, around 2^32, near 2^40)"""
+    """block sums from moments (default: per-byte tables for every k <= 5; PSS_REDUCE_MOMENTS=1: per-prime small moments +
+    one binomial expansion per thread) against the per-prime multi-limb power chain (PSS_REDUCE_MOMENTS=0) and the oracle:
+    slice counts and slice sums on ragged ranges (range edges inside a byte, below 7, around 2^32, near 2^40)"""
     from pss_b200 import _lib
-    os.environ["PSS_REDUCE_MOMENTS"] = "0"
-    try:
-        h_walk = _lib.Handle(-1)
-    finally:
-        del os.environ["PSS_REDUCE_MOMENTS"]
-    h_mom = _lib.Handle(-1)
+
+    def handle_with(mode):
+        os.environ["PSS_REDUCE_MOMENTS"] = mode
+        try:
+            return _lib.Handle(-1)
+        finally:
+            del os.environ["PSS_REDUCE_MOMENTS"]
+
+    h_chain, h_walk = handle_with("0"), handle_with("1")
+    h_tab = _lib.Handle(-1)
     ranges = [(0, 2), (0, 8), (0, 100), (3, 2881), (0, 3_000_000), (2879, 2 * 737280 + 17), (10 ** 9 + 7, 10 ** 9 + 4_000_001),
               (2 ** 32 - 10 ** 6, 2 ** 32 + 10 ** 6), (22_800_000_000, 22_801_763_490), (2 ** 39, 2 ** 39 + 3_000_000),
               (2 ** 40 - 2_000_000, 2 ** 40)]
-    for power, multi in [(2, False), (1, False), (3, False), (4, False), (5, False), (2, True), (3, True), (5, True), (6, False), (6, True)]:
+    for power, multi in [(2, False), (1, False), (3, False), (4, False), (5, False), (2, True), (3, True), (4, True), (5, True),
+                         (6, False), (6, True)]:
         powers = list(range(1, power + 1)) if multi else [power]
         for lo, hi in ranges:
             exp_p = orc.c_primes_range(lo, hi)
             exp = orc.c_power_sums(exp_p, powers)
-            a = h_mom.slice_sieve_sums(lo, hi, power, multi)
+            a = h_tab.slice_sieve_sums(lo, hi, power, multi)
             b = h_walk.slice_sieve_sums(lo, hi, power, multi)
-            assert a == b == (len(exp_p), exp), (power, multi, lo, hi)
-    h_walk.close()
-    h_mom.close()
+            c = h_chain.slice_sieve_sums(lo, hi, power, multi)
+            assert a == b == c == (len(exp_p), exp), (power, multi, lo, hi)
+    for h in (h_chain, h_walk, h_tab):
+        h.close()
 
 
 def test_fused_slices_compose(handle, orc):
