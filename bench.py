@@ -359,7 +359,12 @@ def main():
     def rate(x, ms):
         return x / (ms * 1e-3) if ms else None
 
-    reduce_name = "k_bitmap_moments2+k_scan_columns" if (w["power"] == 2 and not w["all_powers"]) else "k_bitmap_scan<reduce>+k_scan_columns"
+    if w["power"] == 2 and not w["all_powers"]:
+        reduce_name = "k_bitmap_moments2+k_scan_columns"
+    elif w["power"] <= 5:
+        reduce_name = "k_bitmap_moments_tab+k_scan_columns"
+    else:
+        reduce_name = "k_bitmap_scan<reduce>+k_scan_columns"
     ms_reduce = per.get("ms_bitmap_reduce", 0.0)
     ms_compare = per.get("ms_bitmap_compare", 0.0)
     kernels = {

@@ -83,6 +83,7 @@ def main():
         return None
     pairs = {"k_sieve": ["k_sieve"], "k_bitmap_moments2+k_scan_columns": ["k_bitmap_moments2", "k_scan_columns"],
              "k_bitmap_scan<compare>": ["k_bitmap_scan<2, 0, 1>"], "k_bitmap_scan<reduce>+k_scan_columns": ["k_bitmap_scan<2, 0, 0>", "k_scan_columns"],
+             "k_bitmap_moments_tab+k_scan_columns": ["k_bitmap_moments_tab<5, 1>", "k_scan_columns"],
              "k_compact": ["k_compact"]}
     for label, names in pairs.items():
         ks = [tot(n) for n in names]
