@@ -38,8 +38,9 @@ struct DevBuf {
 constexpr u64 kMaxValue = 1ull << PSS_MAX_PRIME_BITS;
 constexpr u32 kPatternPad = 256 * 1024;   // >= largest tile
 constexpr u32 kMaxTileBytes = 224 * 1024; // + scratch line + static shared memory < 227 KiB opt-in limit
-static const u32 kPatGroups[kMaxPatterns][5] = {{7, 11, 13, 17, 19}, {23, 29, 31, 0, 0}, {37, 41, 43, 0, 0}, {47, 53, 59, 0, 0}};
-static const u32 kFirstSievePrime[kMaxPatterns + 1] = {7, 23, 37, 47, 61};
+static const u32 kPatGroups[kMaxPatterns][5] = {{7, 11, 13, 17, 19}, {23, 29, 31, 0, 0}, {37, 41, 43, 0, 0}, {47, 53, 59, 0, 0},
+                                                {61, 67, 71, 0, 0}, {73, 79, 83, 0, 0}};
+static const u32 kFirstSievePrime[kMaxPatterns + 1] = {7, 23, 37, 47, 61, 73, 89};
 
 struct MiscDev {   // small device-side block, one H2D / D2H per scan
     u32 ticket;
@@ -77,8 +78,8 @@ struct pss_handle {
                                // 0: multi-limb power chain per prime (PSS_REDUCE_MOMENTS)
 
     // patterns
-    uint4* d_pat[kMaxPatterns] = {nullptr, nullptr, nullptr, nullptr};
-    u64 pat_period16[kMaxPatterns] = {0, 0, 0, 0};
+    uint4* d_pat[kMaxPatterns] = {};
+    u64 pat_period16[kMaxPatterns] = {};
 
     // base primes
     std::vector<u32> h_base;   // all primes >= 7 up to base_limit

@@ -24,7 +24,7 @@
 
 namespace pss {
 
-constexpr int kMaxPatterns = 4;
+constexpr int kMaxPatterns = 6;
 
 struct SieveParams {
     u64 lo, hi;          // value range [lo, hi)
@@ -310,7 +310,8 @@ __global__ void __launch_bounds__(THREADS, (THREADS <= 768) ? 2 : 1) k_sieve(con
                     for (u32 k = 0; k < 4; ++k) {
                         const u64 Bw = B0 + (u64)vi * 16ull + 4ull * k;
                         u32 x = w[k];
-                        if (Bw == 0) x = (x & 0xFFFF0000u) | 0xDFFEu;  // 7..59 are prime, 1 and 49 are not
+                        if (Bw == 0) x = 0x7EEFDFFEu;   // the integers below 120: all wheel residues are prime except 1, 49, 77, 91, 119
+                                                         // (the patterns also clear their own primes, 7..83)
                         u32 m = edge_byte_mask(Bw, P.lo, P.hi) | (edge_byte_mask(Bw + 1, P.lo, P.hi) << 8) |
                                 (edge_byte_mask(Bw + 2, P.lo, P.hi) << 16) | (edge_byte_mask(Bw + 3, P.lo, P.hi) << 24);
                         w[k] = x & m;
