@@ -494,8 +494,21 @@ int compact_resident(pss_handle* h, u64 cap) {
         cp.out_cap = n_out;
         cp.error_flag = &static_cast<MiscDev*>(h->misc.p)->error_flag;
         CU_TRY(h, cudaMemsetAsync(cp.error_flag, 0, sizeof(u32), h->stream));
-        const u32 grid = std::min<u32>(cp.n_groups, (u32)h->sm_count * 16);
-        k_compact<<<grid, 256, 0, h->stream>>>(cp);
+        if (env_u32("PSS_COMPACT_BLOCK", 0)) {     // the older block-synchronous form (A/B comparison)
+            const u32 grid = std::min<u32>(cp.n_groups, (u32)h->sm_count * 16);
+            k_compact<<<grid, 256, 0, h->stream>>>(cp);
+        } else {
+            static int occ = 0;
+            if (!occ) {
+                CU_TRY(h, cudaFuncSetAttribute(k_compact_warp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kCwSmemBytes));
+                CU_TRY(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_compact_warp, kCwWarps * 32, kCwSmemBytes));
+                if (occ < 1) occ = 1;
+            }
+            cp.group = 1;
+            cp.n_groups = h->sv_n_tiles * cp.chunks_per_tile;     // one work item per chunk
+            const u32 grid = std::min<u32>((cp.n_groups + kCwWarps - 1) / kCwWarps, (u32)(h->sm_count * occ));
+            k_compact_warp<<<grid, kCwWarps * 32, kCwSmemBytes, h->stream>>>(cp);
+        }
         CU_TRY(h, cudaGetLastError());
         h->launches++;
     }

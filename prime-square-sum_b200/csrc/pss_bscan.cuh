@@ -18,6 +18,7 @@
 #pragma once
 #include "pss_common.cuh"
 #include "pss_scan.cuh"
+#include "pss_sieve.cuh"
 
 namespace pss {
 
@@ -1090,6 +1091,88 @@ __global__ void __launch_bounds__(kBsThreads) k_bitmap_moments2(const __grid_con
             cnt += P.n_small;
         }
         bs_reduce_tail<2, false>(P, acc, cnt, wt, tile, lane);
+    }
+}
+
+// ---- K1c, warp-autonomous form: compaction of bitmap chunks into the coalesced u64 prime buffer ------------------------------
+// One warp per 1 KiB chunk (30 720 integers), no block barriers.  Lane l owns the chunk's words 8l .. 8l+7 (two coalesced
+// LDG.128 per lane), so the lanes' primes are consecutive runs of the output: popc + warp scan give every lane its offset,
+// the lane walks its 256-bit stream MSB-first (bit-reversed words in a padded shared-memory row, branch-free refill, one
+// FLO + one PRMT per prime) and parks the 15-bit in-chunk offsets as u16 in the warp's staging area; the warp then writes
+// the chunk's primes as consecutive u64 (value base + offset): 256 B per store instruction, fully coalesced.  HBM traffic
+// is the algorithmic minimum (bitmap read once, 8 B per prime written); shared memory per warp 9.3 KiB (24 warps per SM).
+constexpr int kCwWarps = 8, kCwRow = 9;
+constexpr size_t kCwSmemBytes = (size_t)kCwWarps * (32 * kCwRow * sizeof(u32) + kMaxChunkPrimes * sizeof(uint16_t)) + 32 * sizeof(u32);
+
+__global__ void __launch_bounds__(kCwWarps * 32, 3) k_compact_warp(const CompactParams P) {
+    extern __shared__ u32 cw_smem[];
+    const u32 tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+    u32* my_rows = cw_smem + warp * (32 * kCwRow);
+    uint16_t* my_stage = reinterpret_cast<uint16_t*>(cw_smem + kCwWarps * 32 * kCwRow) + warp * kMaxChunkPrimes;
+    const u32 cpt = P.chunks_per_tile;
+    const u64 n_chunks = (u64)P.n_groups;      // this kernel: one work item per chunk
+    my_rows[lane * kCwRow + 8] = 0u;           // sentinel word of the lane's row
+    const u32 row_saddr = (u32)__cvta_generic_to_shared(my_rows + lane * kCwRow);
+    const u32 stage_saddr = (u32)__cvta_generic_to_shared(my_stage);
+    // in-word offset of the prime whose (bit-reversed) bit index is m: one 32-entry table, one entry per bank, so any mix
+    // of indices across the lanes is conflict free
+    u32* tab = cw_smem + kCwWarps * 32 * kCwRow + kCwWarps * (kMaxChunkPrimes / 2);
+    if (tid < 32) tab[tid] = msb_value_offset(tid);
+    __syncthreads();
+    const u32 tab_saddr = (u32)__cvta_generic_to_shared(tab);
+    for (u64 g = (u64)blockIdx.x * kCwWarps + warp; g < n_chunks; g += (u64)gridDim.x * kCwWarps) {
+        const u32 t = (u32)(g / cpt), c = (u32)(g - (u64)t * cpt);
+        // output index of the chunk's first prime = tile prefix + counts of the tile's earlier chunks
+        u32 pre = 0;
+        for (u32 i = lane; i < c; i += 32) pre += __ldg(P.chunk_counts + (u64)t * cpt + i);
+        pre = __reduce_add_sync(0xFFFFFFFFu, pre);
+        const u64 base = __ldg(P.tile_prefix + t) + pre;
+        if (base >= P.out_cap) continue;       // warp-uniform (first-n truncation)
+        const uint4* src = reinterpret_cast<const uint4*>(P.bitmap + g * kChunkWords) + 2u * lane;
+        const uint4 a = __ldg(src), b = __ldg(src + 1);
+        const u32 cnt = __popc(a.x) + __popc(a.y) + __popc(a.z) + __popc(a.w) + __popc(b.x) + __popc(b.y) + __popc(b.z) + __popc(b.w);
+        u32 incl = cnt;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const u32 o = __shfl_up_sync(0xFFFFFFFFu, incl, d);
+            if (lane >= (u32)d) incl += o;
+        }
+        u32 total = __shfl_sync(0xFFFFFFFFu, incl, 31);
+        if (total > (u32)kMaxChunkPrimes) {    // cannot happen for a correctly sieved bitmap
+            if (lane == 0) atomicExch(P.error_flag, 2u);
+            total = kMaxChunkPrimes;
+        }
+        u32* row = my_rows + lane * kCwRow;
+        row[0] = __brev(a.x); row[1] = __brev(a.y); row[2] = __brev(a.z); row[3] = __brev(a.w);
+        row[4] = __brev(b.x); row[5] = __brev(b.y); row[6] = __brev(b.z); row[7] = __brev(b.w);
+        // walk the lane's eight words (own row: no synchronisation needed before reading it back)
+        u32 off = incl - cnt;
+        u32 addr = row_saddr, w = 0, woff = 960u * lane - 120u;
+        const u32 end = row_saddr + 32u;       // the sentinel slot
+        bool alive = true;
+        while (alive) {
+            asm("{\n\t.reg .pred q;\n\tsetp.eq.u32 q, %0, 0;\n\t@q ld.shared.u32 %0, [%1];\n\t@q add.u32 %1, %1, 4;\n\t@q add.u32 %2, %2, 120;\n\t}"
+                : "+r"(w), "+r"(addr), "+r"(woff));
+            if (w == 0) {
+                alive = (addr <= end);
+            } else {
+                const u32 m = msb_index(w);
+                u32 below, o;
+                asm("bmsk.clamp.b32 %0, 0, %1;" : "=r"(below) : "r"(m));              // bits under the leading one
+                asm("ld.shared.u32 %0, [%1];" : "=r"(o) : "r"(tab_saddr + 4u * m));
+                w &= below;
+                // (off is below kMaxChunkPrimes for every valid bitmap; the mask only keeps a corrupt one inside the stage)
+                asm volatile("st.shared.u16 [%0], %1;" ::"r"(stage_saddr + 2u * (off & (u32)(kMaxChunkPrimes - 1))), "h"((unsigned short)(woff + o)) : "memory");
+                ++off;
+            }
+        }
+        __syncwarp();
+        const u64 vbase = (P.B_start + g * (u64)kChunkBytes) * 30ull;
+        for (u32 i = lane; i < total; i += 32) {
+            const u64 o = base + i;
+            if (o < P.out_cap) P.out[o] = vbase + my_stage[i];
+        }
+        __syncwarp();
     }
 }
 
