@@ -91,6 +91,7 @@ struct pss_handle {
 
     // sieve workspace / state of the last sieve
     DevBuf bitmap, chunk_counts, tile_counts, tile_prefix, tile_nact;
+    u64 nact_key[6] = {0, 0, 0, 0, 0, 0};   // geometry the cached tile_nact table was computed for
     DevBuf sieve_prof;   // PSS_SIEVE_PROF=1: k_sieve cycle counters, printed by pss_close
     u64 sv_lo = 0, sv_hi = 0, sv_B_start = 0, sv_total = 0, sv_c235 = 0;
     u32 sv_tile_bytes = 0, sv_n_tiles = 0;
@@ -407,11 +408,17 @@ int sieve_range(pss_handle* h, u64 lo, u64 hi, bool defer_sync = false) {
             sp.batch_geo = static_cast<const u32*>(h->d_batch_geo.p);
         }
         // per tile: how many base primes satisfy p*p < tile end (tiny device kernel, no host work)
-        PSS_TRY(ensure(h, h->tile_nact, (size_t)n_tiles * sizeof(u32)));
-        k_tile_nact<<<(n_tiles + 255) / 256, 256, 0, h->stream>>>(sp.base_p, sp.n_base, B_start, tile_bytes, hi, n_tiles,
-                                                                  static_cast<u32*>(h->tile_nact.p));
-        CU_TRY(h, cudaGetLastError());
-        h->launches++;
+        // (the table only depends on the geometry: a repeated query -- the steady state of a search service and of the
+        // multi-GPU ranks, whose whole step is a fraction of a millisecond -- reuses it instead of launching again)
+        const u64 nact_key[6] = {B_start, tile_bytes, hi, n_tiles, sp.n_base, h->base_first_prime};
+        if (memcmp(nact_key, h->nact_key, sizeof nact_key) != 0 || !h->tile_nact.p) {
+            PSS_TRY(ensure(h, h->tile_nact, (size_t)n_tiles * sizeof(u32)));
+            k_tile_nact<<<(n_tiles + 255) / 256, 256, 0, h->stream>>>(sp.base_p, sp.n_base, B_start, tile_bytes, hi, n_tiles,
+                                                                      static_cast<u32*>(h->tile_nact.p));
+            CU_TRY(h, cudaGetLastError());
+            h->launches++;
+            memcpy(h->nact_key, nact_key, sizeof nact_key);
+        }
         sp.tile_nact = static_cast<const u32*>(h->tile_nact.p);
     }
     sp.n_pat = h->n_pat;
@@ -1553,8 +1560,6 @@ int pss_peer_search(pss_handle* h, uint64_t lo, uint64_t hi_excl, const pss_sear
     pp.world = world;
     pp.rank = rank;
     pp.epoch = epoch;
-    k_peer_publish<<<1, 32, 0, h->stream>>>(pp);
-    CU_TRY(h, cudaGetLastError());
     PeerGatherParams pg;
     memset(&pg, 0, sizeof pg);
     pg.box = h->box_local;
@@ -1564,9 +1569,16 @@ int pss_peer_search(pss_handle* h, uint64_t lo, uint64_t hi_excl, const pss_sear
     pg.n_first_out = &dm->n_first;
     pg.carry_out = dm->carry;
     pg.error_flag = &dm->error_flag;
-    k_peer_gather<<<1, 32, 0, h->stream>>>(pg);
+    static const bool peer_split = env_u32("PSS_PEER_SPLIT", 0) != 0;   // A/B: the two halves as separate launches
+    if (peer_split) {
+        k_peer_publish<<<1, 32, 0, h->stream>>>(pp);
+        k_peer_gather<<<1, 32, 0, h->stream>>>(pg);
+        h->launches += 2;
+    } else {
+        k_peer_exchange<<<1, 32, 0, h->stream>>>(pp, pg);
+        h->launches += 1;
+    }
     CU_TRY(h, cudaGetLastError());
-    h->launches += 2;
 
     // ---- phase B: compare, seeded from device memory (n_first, carry)
     CU_TRY(h, cudaEventRecord(h->ev[6], h->stream));
@@ -1594,11 +1606,15 @@ int pss_peer_search(pss_handle* h, uint64_t lo, uint64_t hi_excl, const pss_sear
     pr.col_stride = pp.col_stride;
     pr.n_tiles = pp.n_tiles;
     for (u32 j = 0; j < np; ++j) pr.width[j] = pp.width[j];
-    k_peer_publish_result<<<1, 256, 0, h->stream>>>(pr);
+    if (peer_split) {
+        k_peer_publish_result<<<1, 256, 0, h->stream>>>(pr);
+        k_peer_gather_results<<<1, 32, 0, h->stream>>>(h->box_local, world, epoch, watchdog, &dm->error_flag);
+        h->launches += 2;
+    } else {
+        k_peer_exchange_results<<<1, 256, 0, h->stream>>>(pr, h->box_local, world, epoch, watchdog, &dm->error_flag);
+        h->launches += 1;
+    }
     CU_TRY(h, cudaGetLastError());
-    k_peer_gather_results<<<1, 32, 0, h->stream>>>(h->box_local, world, epoch, watchdog, &dm->error_flag);
-    CU_TRY(h, cudaGetLastError());
-    h->launches += 2;
     CU_TRY(h, cudaMemcpyAsync(h->h_peer_results, &h->box_local->r[epoch & 1ull][0], sizeof(PeerResult) * world, cudaMemcpyDeviceToHost, h->stream));
     CU_TRY(h, cudaMemcpyAsync(hm, dm, sizeof(MiscDev), cudaMemcpyDeviceToHost, h->stream));
     cudaEvent_t ev_end = h->ev[3];   // compaction event, unused on this path

@@ -79,7 +79,7 @@ struct PeerPublishParams {
 };
 
 // one CTA of 32 * ceil(world / 32) threads: thread t stores this rank's record into rank t's mailbox
-__global__ void k_peer_publish(const PeerPublishParams P) {
+__device__ __forceinline__ void peer_publish_body(const PeerPublishParams& P) {
     __shared__ u64 s_count;
     __shared__ u32 s_sums[PSS_MAX_POWER * PSS_LIMBS];
     if (threadIdx.x == 0) {
@@ -121,7 +121,7 @@ struct PeerGatherParams {
     u32* error_flag;
 };
 
-__global__ void k_peer_gather(const PeerGatherParams P) {
+__device__ __forceinline__ void peer_gather_body(const PeerGatherParams& P) {
     __shared__ u32 s_bad;
     if (threadIdx.x == 0) s_bad = 0;
     __syncthreads();
@@ -169,7 +169,7 @@ struct PeerResultParams {
 };
 
 // one CTA: builds this rank's outcome record and stores it into every rank's mailbox
-__global__ void k_peer_publish_result(const PeerResultParams P) {
+__device__ __forceinline__ void peer_publish_result_body(const PeerResultParams& P) {
     __shared__ PeerResult s_rec;
     if (threadIdx.x == 0) {
         const u64 n_first = *P.n_first;
@@ -221,10 +221,30 @@ __global__ void k_peer_publish_result(const PeerResultParams P) {
     if (threadIdx.x < P.world) st_release_sys(&P.box[threadIdx.x]->r[P.epoch & 1ull][P.rank].flag, P.epoch);
 }
 
-__global__ void k_peer_gather_results(PeerBox* box, u32 world, u64 epoch, long long watchdog, u32* error_flag) {
+__device__ __forceinline__ void peer_gather_results_body(PeerBox* box, u32 world, u64 epoch, long long watchdog, u32* error_flag) {
     if (threadIdx.x < world) {
         if (!wait_flag(&box->r[epoch & 1ull][threadIdx.x].flag, epoch, watchdog)) atomicOr(error_flag, 0x200u);
     }
+}
+
+// The two halves of an exchange step run in ONE launch: publish first (remote stores + release of the epoch flag), then wait
+// for the peers.  Every rank publishes before it waits, so the waits cannot cycle; one launch less per step matters because a
+// rank's whole query is a few hundred microseconds at 8 GPUs.
+__global__ void k_peer_publish(const PeerPublishParams P) { peer_publish_body(P); }
+__global__ void k_peer_gather(const PeerGatherParams P) { peer_gather_body(P); }
+__global__ void k_peer_publish_result(const PeerResultParams P) { peer_publish_result_body(P); }
+__global__ void k_peer_gather_results(PeerBox* box, u32 world, u64 epoch, long long watchdog, u32* error_flag) {
+    peer_gather_results_body(box, world, epoch, watchdog, error_flag);
+}
+__global__ void k_peer_exchange(const PeerPublishParams PP, const PeerGatherParams PG) {
+    peer_publish_body(PP);
+    __syncthreads();
+    peer_gather_body(PG);
+}
+__global__ void k_peer_exchange_results(const PeerResultParams PR, PeerBox* box, u32 world, u64 epoch, long long watchdog, u32* error_flag) {
+    peer_publish_result_body(PR);
+    __syncthreads();
+    peer_gather_results_body(box, world, epoch, watchdog, error_flag);
 }
 
 }  // namespace pss
