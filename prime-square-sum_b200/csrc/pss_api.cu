@@ -504,6 +504,17 @@ int compact_resident(pss_handle* h, u64 cap) {
         if (env_u32("PSS_COMPACT_BLOCK", 0)) {     // the older block-synchronous form (A/B comparison)
             const u32 grid = std::min<u32>(cp.n_groups, (u32)h->sm_count * 16);
             k_compact<<<grid, 256, 0, h->stream>>>(cp);
+        } else if (!env_u32("PSS_COMPACT_WALK", 0)) {   // default: table form
+            static int occ_l = 0;
+            if (!occ_l) {
+                CU_TRY(h, cudaFuncSetAttribute(k_compact_lut, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kClSmemBytes));
+                CU_TRY(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_l, k_compact_lut, kCwWarps * 32, kClSmemBytes));
+                if (occ_l < 1) occ_l = 1;
+            }
+            cp.group = 1;
+            cp.n_groups = h->sv_n_tiles * cp.chunks_per_tile;     // one work item per chunk
+            const u32 grid = std::min<u32>((cp.n_groups + kCwWarps - 1) / kCwWarps, (u32)(h->sm_count * occ_l));
+            k_compact_lut<<<grid, kCwWarps * 32, kClSmemBytes, h->stream>>>(cp);
         } else {
             static int occ = 0;
             if (!occ) {

@@ -1176,6 +1176,99 @@ __global__ void __launch_bounds__(kCwWarps * 32, 3) k_compact_warp(const Compact
     }
 }
 
+// ---- K1c, table form: the same warp-per-chunk compaction without a data-dependent loop -----------------------------------
+// A 256-entry byte table lists the wheel residues of a byte's set bits in ascending order (5 bits each) and their count.
+// Every lane runs the SAME 32 steps, one per bitmap byte it owns: one table lookup, up to four predicated 16-bit stores into
+// the warp's staging area (bytes with more than four primes only occur below 120 and take a rare branch), offset += count.
+// No FLO, no refill, no lane ever idles: ~25 issue slots per byte instead of ~26 per prime with 25 of 32 lanes busy.
+// The table is replicated 8x (16 KiB): lane l reads copy l & 7.
+constexpr int kClStage = 3584;      // >= pi(30720) = 3316 primes in the densest chunk
+constexpr size_t kClSmemBytes = 256 * 8 * sizeof(uint2) + (size_t)kCwWarps * kClStage * sizeof(uint16_t);
+
+__global__ void __launch_bounds__(kCwWarps * 32, 3) k_compact_lut(const CompactParams P) {
+    extern __shared__ u32 cl_smem[];
+    const u32 tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+    uint2* lut = reinterpret_cast<uint2*>(cl_smem);
+    uint16_t* my_stage = reinterpret_cast<uint16_t*>(cl_smem + 256 * 8 * 2) + warp * kClStage;
+    {
+        const u32 v = tid;               // 256 threads: one byte value each
+        u32 lo = 0, hi = 0, n = 0;
+#pragma unroll
+        for (u32 j = 0; j < 8; ++j)
+            if ((v >> j) & 1u) {
+                const u32 r = wheel_residue(j);
+                if (n < 6) lo |= r << (5 * n); else hi |= r << (5 * (n - 6));
+                ++n;
+            }
+        hi |= n << 16;
+        for (u32 c = 0; c < 8; ++c) lut[v * 8 + ((c + v) & 7u)] = make_uint2(lo, hi);
+    }
+    __syncthreads();
+    const u32 lut_lane = (u32)__cvta_generic_to_shared(lut) + 8u * (lane & 7u);
+    const u32 cpt = P.chunks_per_tile;
+    const u64 n_chunks = (u64)P.n_groups;      // one work item per chunk
+    for (u64 g = (u64)blockIdx.x * kCwWarps + warp; g < n_chunks; g += (u64)gridDim.x * kCwWarps) {
+        const u32 t = (u32)(g / cpt), c = (u32)(g - (u64)t * cpt);
+        u32 pre = 0;
+        for (u32 i = lane; i < c; i += 32) pre += __ldg(P.chunk_counts + (u64)t * cpt + i);
+        pre = __reduce_add_sync(0xFFFFFFFFu, pre);
+        const u64 base = __ldg(P.tile_prefix + t) + pre;
+        if (base >= P.out_cap) continue;       // warp-uniform (first-n truncation)
+        const uint4* src = reinterpret_cast<const uint4*>(P.bitmap + g * kChunkWords) + 2u * lane;
+        const uint4 a = __ldg(src), b = __ldg(src + 1);
+        const u32 wd[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+        u32 cnt = 0;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) cnt += __popc(wd[i]);
+        u32 incl = cnt;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const u32 o = __shfl_up_sync(0xFFFFFFFFu, incl, d);
+            if (lane >= (u32)d) incl += o;
+        }
+        const u32 total = __shfl_sync(0xFFFFFFFFu, incl, 31);
+        if (total > (u32)kClStage) {            // cannot happen for a correctly sieved bitmap
+            if (lane == 0) atomicExch(P.error_flag, 2u);
+            continue;
+        }
+        u32 st = (u32)__cvta_generic_to_shared(my_stage) + 2u * (incl - cnt);   // shared address of the lane's next slot
+        const u32 obase = 960u * lane;          // in-chunk offset of the lane's first byte
+#pragma unroll
+        for (int wi = 0; wi < 8; ++wi) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                u32 byte;
+                uint2 e;
+                asm("prmt.b32 %0, %1, 0, %2;" : "=r"(byte) : "r"(wd[wi]), "r"(0x4440u + (u32)q));
+                asm("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(e.x), "=r"(e.y) : "r"(lut_lane + (byte << 6)));
+                const u32 n = e.y >> 16;
+                const u32 x = obase + 30u * (u32)(4 * wi + q);
+                // four predicated stores (inline PTX: the compiler turns `if (n > k) st[k] = ..` into a branch each)
+                asm volatile("{\n\t.reg .pred p0, p1, p2, p3;\n\t"
+                             "setp.gt.u32 p0, %0, 0;\n\tsetp.gt.u32 p1, %0, 1;\n\tsetp.gt.u32 p2, %0, 2;\n\tsetp.gt.u32 p3, %0, 3;\n\t"
+                             "@p0 st.shared.u16 [%1], %2;\n\t@p1 st.shared.u16 [%1+2], %3;\n\t@p2 st.shared.u16 [%1+4], %4;\n\t@p3 st.shared.u16 [%1+6], %5;\n\t}"
+                             ::"r"(n), "r"(st), "h"((unsigned short)(x + (e.x & 31u))), "h"((unsigned short)(x + ((e.x >> 5) & 31u))),
+                               "h"((unsigned short)(x + ((e.x >> 10) & 31u))), "h"((unsigned short)(x + ((e.x >> 15) & 31u)))
+                             : "memory");
+                if (n > 4) {                     // only bytes 0..3 of the number line hold more than four primes
+                    asm volatile("st.shared.u16 [%0+8], %1;" ::"r"(st), "h"((unsigned short)(x + ((e.x >> 20) & 31u))) : "memory");
+                    if (n > 5) asm volatile("st.shared.u16 [%0+10], %1;" ::"r"(st), "h"((unsigned short)(x + ((e.x >> 25) & 31u))) : "memory");
+                    if (n > 6) asm volatile("st.shared.u16 [%0+12], %1;" ::"r"(st), "h"((unsigned short)(x + (e.y & 31u))) : "memory");
+                    if (n > 7) asm volatile("st.shared.u16 [%0+14], %1;" ::"r"(st), "h"((unsigned short)(x + ((e.y >> 5) & 31u))) : "memory");
+                }
+                st += 2u * n;
+            }
+        }
+        __syncwarp();
+        const u64 vbase = (P.B_start + g * (u64)kChunkBytes) * 30ull;
+        for (u32 i = lane; i < total; i += 32) {
+            const u64 o = base + i;
+            if (o < P.out_cap) P.out[o] = vbase + my_stage[i];
+        }
+        __syncwarp();
+    }
+}
+
 // ---- grid level of the scan: exclusive u64 prefix of every (deferred-carry) column, one CTA per column --------------
 // out[c * stride + t] = sum_{i<t} in[c * stride + i]  for t = 0..n  (entry n = column total)
 __global__ void __launch_bounds__(1024) k_scan_columns(const u64* in, u64* out, u32 n, u64 stride) {
