@@ -1207,15 +1207,25 @@ __global__ void __launch_bounds__(kCwWarps * 32, 3) k_compact_lut(const CompactP
     const u32 lut_lane = (u32)__cvta_generic_to_shared(lut) + 8u * (lane & 7u);
     const u32 cpt = P.chunks_per_tile;
     const u64 n_chunks = (u64)P.n_groups;      // one work item per chunk
-    for (u64 g = (u64)blockIdx.x * kCwWarps + warp; g < n_chunks; g += (u64)gridDim.x * kCwWarps) {
+    const u64 g_stride = (u64)gridDim.x * kCwWarps;
+    auto load_chunk = [&](u64 g, uint4& a, uint4& b) {      // the lane's eight words of chunk g (zeros past the end)
+        a = make_uint4(0, 0, 0, 0); b = a;
+        if (g < n_chunks) {
+            const uint4* src = reinterpret_cast<const uint4*>(P.bitmap + g * kChunkWords) + 2u * lane;
+            a = __ldg(src); b = __ldg(src + 1);
+        }
+    };
+    uint4 na, nb;
+    load_chunk((u64)blockIdx.x * kCwWarps + warp, na, nb);
+    for (u64 g = (u64)blockIdx.x * kCwWarps + warp; g < n_chunks; g += g_stride) {
+        const uint4 a = na, b = nb;
+        load_chunk(g + g_stride, na, nb);       // the next chunk's words fly while this one is decoded and written out
         const u32 t = (u32)(g / cpt), c = (u32)(g - (u64)t * cpt);
         u32 pre = 0;
         for (u32 i = lane; i < c; i += 32) pre += __ldg(P.chunk_counts + (u64)t * cpt + i);
         pre = __reduce_add_sync(0xFFFFFFFFu, pre);
         const u64 base = __ldg(P.tile_prefix + t) + pre;
         if (base >= P.out_cap) continue;       // warp-uniform (first-n truncation)
-        const uint4* src = reinterpret_cast<const uint4*>(P.bitmap + g * kChunkWords) + 2u * lane;
-        const uint4 a = __ldg(src), b = __ldg(src + 1);
         const u32 wd[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
         u32 cnt = 0;
 #pragma unroll
@@ -1261,10 +1271,17 @@ __global__ void __launch_bounds__(kCwWarps * 32, 3) k_compact_lut(const CompactP
         }
         __syncwarp();
         const u64 vbase = (P.B_start + g * (u64)kChunkBytes) * 30ull;
-        for (u32 i = lane; i < total; i += 32) {
-            const u64 o = base + i;
-            if (o < P.out_cap) P.out[o] = vbase + my_stage[i];
+        const u32 n_out = (u32)min((u64)total, P.out_cap - base);      // first-n truncation
+        // 16-byte stores: entry pairs (i, i+1) with base + i even; a leading odd entry and a trailing single go alone
+        const u32 head = (u32)(base & 1ull) & (n_out ? 1u : 0u);
+        if (lane == 0 && head) P.out[base] = vbase + my_stage[0];
+        const u32 n_pairs = (n_out - head) >> 1;
+        ulonglong2* out2 = reinterpret_cast<ulonglong2*>(P.out + base + head);
+        for (u32 i = lane; i < n_pairs; i += 32) {
+            const u32 k = head + 2u * i;
+            out2[i] = make_ulonglong2(vbase + my_stage[k], vbase + my_stage[k + 1]);
         }
+        if (lane == 0 && ((n_out - head) & 1u)) P.out[base + n_out - 1] = vbase + my_stage[n_out - 1];
         __syncwarp();
     }
 }
