@@ -688,6 +688,14 @@ int launch_bscan_t(pss_handle* h, const BScanParams& bp) {
     return PSS_OK;
 }
 
+// column scan: one CTA per column; up to 8192 scan tiles the register-resident kernel (rows loaded once)
+template <class... A>
+void launch_scan_columns(pss_handle* h, u32 ncols, const u64* in, u64* out, u32 n, u64 stride) {
+    const u32 rows = (n + 31u) / 32u;
+    if ((rows + 15u) / 16u <= 16u) k_scan_columns_small<<<ncols, 512, 0, h->stream>>>(in, out, n, stride);
+    else k_scan_columns<<<ncols, 1024, 0, h->stream>>>(in, out, n, stride);
+}
+
 template <int K, bool MULTI>
 int launch_moments_t(pss_handle* h, const BScanParams& bp) {
     if (h->reduce_moments >= 2) {   // byte-table form (default); PSS_REDUCE_MOMENTS=1 selects the per-prime walk
@@ -876,7 +884,7 @@ int bitmap_reduce(pss_handle* h, u32 K, bool multi, bool defer_sync = false) {
         bp.reduce_chain = 1u;
         PSS_TRY(launch_bscan<kBsReduce>(h, bp, K, multi));
     }
-    k_scan_columns<<<ncols, 1024, 0, h->stream>>>(bp.cols, static_cast<u64*>(h->col_prefix.p), bp.n_tiles, bp.col_stride);
+    launch_scan_columns(h, ncols, bp.cols, static_cast<u64*>(h->col_prefix.p), bp.n_tiles, bp.col_stride);
     CU_TRY(h, cudaGetLastError());
     h->launches++;
     CU_TRY(h, cudaEventRecord(h->ev[5], h->stream));

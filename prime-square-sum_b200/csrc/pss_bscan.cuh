@@ -95,15 +95,14 @@ __device__ __forceinline__ u64 walk_words(const u32* my_words, u64 value_base, F
     // into two opaque registers (otherwise ptxas rematerialises "byte index * 30" inside the loop)
     u32 base_lo = (u32)value_base, base_hi = (u32)(value_base >> 32);
     asm volatile("" : "+r"(base_lo), "+r"(base_hi));
-    u32 wi = 0, w = 0, woff = 0u - 120u;
+    // refill of an exhausted word as four predicated instructions (the C++ select form compiles to thirteen)
+    u32 addr = (u32)__cvta_generic_to_shared(my_words), w = 0, woff = 0u - 120u;
+    const u32 end = addr + 4u * (u32)kWordsPerThread;      // the sentinel slot of this thread's padded row
     u32 plo = 0, phi = 0;
     bool alive = true;
     while (alive) {
-        const bool need = (w == 0);
-        const u32 nw = my_words[wi];     // wi <= kWordsPerThread: the sentinel slot of this thread's padded row
-        w = need ? nw : w;
-        wi += need ? 1u : 0u;
-        woff += need ? 120u : 0u;
+        asm volatile("{\n\t.reg .pred q;\n\tsetp.eq.u32 q, %0, 0;\n\t@q ld.shared.u32 %0, [%1];\n\t@q add.u32 %1, %1, 4;\n\t@q add.u32 %2, %2, 120;\n\t}"
+                     : "+r"(w), "+r"(addr), "+r"(woff) :: "memory");
         if (w != 0) {
             const u32 m = msb_index(w);
             w ^= (1u << m);
@@ -111,7 +110,7 @@ __device__ __forceinline__ u64 walk_words(const u32* my_words, u64 value_base, F
             asm("add.cc.u32 %0, %2, %3;\n\taddc.u32 %1, %4, 0;" : "=r"(plo), "=r"(phi) : "r"(base_lo), "r"(off), "r"(base_hi));
             alive = f(plo, phi);
         } else {
-            alive = (wi <= (u32)kWordsPerThread);   // empty word (rare): try the next one; sentinel: done
+            alive = (addr <= end);   // empty word (rare): try the next one; past the sentinel: done
         }
     }
     return ((u64)phi << 32) | plo;
@@ -1334,6 +1333,63 @@ __global__ void __launch_bounds__(1024) k_scan_columns(const u64* in, u64* out, 
         run += __shfl_sync(0xFFFFFFFFu, incl, 31);
     }
     if (warp == 31 && lane == 0) o[n] = run;     // the last warp's running sum is the column total (also for empty runs)
+}
+
+// register-resident form for n <= 16384 rows-of-32 per warp budget (host: launch_scan_columns)
+__global__ void __launch_bounds__(512) k_scan_columns_small(const u64* in, u64* out, u32 n, u64 stride) {
+    __shared__ u64 s_warp[32];          // 16 warps: entries 16..31 stay zero
+    const u32 tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+    const u64* col = in + (u64)blockIdx.x * stride;
+    u64* o = out + (u64)blockIdx.x * stride;
+    // every warp owns a contiguous run of rows of 32 elements (coalesced loads): warp total -> one block-wide scan of
+    // the 32 totals -> row-by-row warp scans seeded with the warp's offset
+    const u32 rows = (n + 31u) / 32u;
+    const u32 rows_per_warp = (rows + 15u) / 16u;     // 16 warps
+    const u32 r0 = min(rows, warp * rows_per_warp), r1 = min(rows, r0 + rows_per_warp);
+    // up to 8192 scan tiles (6e9 integers per slice: the slices of the headline job from 4 GPUs up): the warp's rows are
+    // loaded ONCE, all loads in flight together (the kernel is pure latency: one CTA per column), and both passes run
+    // out of registers (16 x u64 per thread, 512-thread CTA)
+    u64 v[16];
+#pragma unroll
+    for (u32 k = 0; k < 16u; ++k) {
+        const u32 i = (r0 + k) * 32u + lane;
+        v[k] = (r0 + k < r1 && i < n) ? col[i] : 0ull;
+    }
+    u64 sum = 0;
+#pragma unroll
+    for (u32 k = 0; k < 16u; ++k) sum += v[k];
+#pragma unroll
+    for (int d = 16; d >= 1; d >>= 1) sum += __shfl_xor_sync(0xFFFFFFFFu, sum, d);
+    if (lane == 0) s_warp[warp] = sum;
+    if (tid < 16) s_warp[16 + tid] = 0;
+    __syncthreads();
+    if (warp == 0) {
+        const u64 w = s_warp[lane];
+        u64 wi = w;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const u64 up = __shfl_up_sync(0xFFFFFFFFu, wi, d);
+            if (lane >= (u32)d) wi += up;
+        }
+        s_warp[lane] = wi - w;
+    }
+    __syncthreads();
+    u64 run = s_warp[warp];
+#pragma unroll
+    for (u32 k = 0; k < 16u; ++k) {
+        if (r0 + k < r1) {             // warp-uniform
+            const u32 i = (r0 + k) * 32u + lane;
+            u64 incl = v[k];
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const u64 up = __shfl_up_sync(0xFFFFFFFFu, incl, d);
+                if (lane >= (u32)d) incl += up;
+            }
+            if (i < n) o[i] = run + incl - v[k];
+            run += __shfl_sync(0xFFFFFFFFu, incl, 31);
+        }
+    }
+    if (warp == 15 && lane == 0) o[n] = run;
 }
 
 }  // namespace pss
