@@ -58,7 +58,7 @@ def test_first_n_nth_count_golden(handle, golden):
 
 @pytest.mark.parametrize("tile,threads,npat", [(8192, 256, 4), (98304, 512, 4), (65536, 1024, 2), (16384, 512, 0),
                                                (216 * 1024, 1024, 4), (32768, 256, 1), (49152, 512, 3), (224 * 1024, 1024, 4),
-                                               (112 * 1024, 768, 4)])
+                                               (112 * 1024, 768, 4), (224 * 1024, 1024, 5), (96 * 1024, 512, 6)])
 def test_sieve_tunings_vs_oracle(orc, tile, threads, npat):
     """Every tile size / block size / pattern count gives the same primes (segment-size independence,
     the analogue of tests/test_sieve.py:80-120)."""
@@ -75,6 +75,28 @@ def test_sieve_tunings_vs_oracle(orc, tile, threads, npat):
         exp = orc.c_primes_range(lo, hi)
         assert np.array_equal(got, exp), (lo, hi, len(got), len(exp))
     h.close()
+
+
+@pytest.mark.parametrize("env", [None, "PSS_COMPACT_WALK", "PSS_COMPACT_BLOCK"])
+def test_compaction_kernels_vs_oracle(orc, env):
+    """The three stream-compaction kernels (byte-table form = default, per-prime walk, block-synchronous) write the same
+    sorted u64 buffer: ranges below 120 (bytes with more than four primes), ragged edges, first-n truncation, 2^32, 2^39."""
+    from pss_b200 import _lib
+    if env:
+        os.environ[env] = "1"
+    try:
+        h = _lib.Handle(-1)
+        for lo, hi in [(0, 10), (0, 121), (0, 30_721), (7, 3_000_000), (30_719, 30_722), (10 ** 9, 10 ** 9 + 3_000_000),
+                       (2 ** 32 - 10 ** 6, 2 ** 32 + 10 ** 6), (2 ** 39, 2 ** 39 + 500_000)]:
+            got = h.generate_primes(lo, hi).astype(np.uint64)
+            assert np.array_equal(got, orc.c_primes_range(lo, hi)), (env, lo, hi)
+        for n in (1, 3, 4, 10, 3316, 3317, 100_000, 1_000_003):
+            got = h.generate_n_primes(n).astype(np.uint64)
+            assert np.array_equal(got, orc.c_first_n_primes(n)), (env, n)
+        h.close()
+    finally:
+        if env:
+            del os.environ[env]
 
 
 def test_sieve_medium_vs_oracle(handle, orc):
