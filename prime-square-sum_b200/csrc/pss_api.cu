@@ -408,10 +408,10 @@ int sieve_range(pss_handle* h, u64 lo, u64 hi, bool defer_sync = false) {
             sp.batch_geo = static_cast<const u32*>(h->d_batch_geo.p);
         }
         // per tile: how many base primes satisfy p*p < tile end (tiny device kernel, no host work)
-        // (the table only depends on the geometry: a repeated query -- the steady state of a search service and of the
-        // multi-GPU ranks, whose whole step is a fraction of a millisecond -- reuses it instead of launching again)
+        // (the table only depends on the geometry; PSS_NACT_CACHE=1 reuses it for a repeated query instead of launching again)
         const u64 nact_key[6] = {B_start, tile_bytes, hi, n_tiles, sp.n_base, h->base_first_prime};
-        if (memcmp(nact_key, h->nact_key, sizeof nact_key) != 0 || !h->tile_nact.p) {
+        static const bool nact_cache = env_u32("PSS_NACT_CACHE", 0) != 0;   // off: see the 8-GPU A/B in DESIGN.md section 5
+        if (!nact_cache || memcmp(nact_key, h->nact_key, sizeof nact_key) != 0 || !h->tile_nact.p) {
             PSS_TRY(ensure(h, h->tile_nact, (size_t)n_tiles * sizeof(u32)));
             k_tile_nact<<<(n_tiles + 255) / 256, 256, 0, h->stream>>>(sp.base_p, sp.n_base, B_start, tile_bytes, hi, n_tiles,
                                                                       static_cast<u32*>(h->tile_nact.p));
@@ -1588,7 +1588,7 @@ int pss_peer_search(pss_handle* h, uint64_t lo, uint64_t hi_excl, const pss_sear
     pg.n_first_out = &dm->n_first;
     pg.carry_out = dm->carry;
     pg.error_flag = &dm->error_flag;
-    static const bool peer_split = env_u32("PSS_PEER_SPLIT", 0) != 0;   // A/B: the two halves as separate launches
+    static const bool peer_split = env_u32("PSS_PEER_MERGE", 0) == 0;   // default: the two halves as separate launches (8-GPU A/B)
     if (peer_split) {
         k_peer_publish<<<1, 32, 0, h->stream>>>(pp);
         k_peer_gather<<<1, 32, 0, h->stream>>>(pg);
