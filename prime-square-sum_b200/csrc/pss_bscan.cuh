@@ -1178,7 +1178,7 @@ __global__ void __launch_bounds__(kCwWarps * 32, 3) k_compact_warp(const Compact
 // ---- K1c, table form: the same warp-per-chunk compaction without a data-dependent loop -----------------------------------
 // A 256-entry byte table lists the wheel residues of a byte's set bits in ascending order (5 bits each) and their count.
 // Every lane runs the SAME 32 steps, one per bitmap byte it owns: one table lookup, up to four predicated 16-bit stores into
-// the warp's staging area (bytes with more than four primes only occur below 120 and take a rare branch), offset += count.
+// the warp's staging area (bytes with five or more primes take a branch: common only near the origin), offset += count.
 // No FLO, no refill, no lane ever idles: ~25 issue slots per byte instead of ~26 per prime with 25 of 32 lanes busy.
 // The table is replicated 8x (16 KiB): lane l reads copy l & 7.
 constexpr int kClStage = 3584;      // >= pi(30720) = 3316 primes in the densest chunk
@@ -1259,7 +1259,7 @@ __global__ void __launch_bounds__(kCwWarps * 32, 3) k_compact_lut(const CompactP
                              ::"r"(n), "r"(st), "h"((unsigned short)(x + (e.x & 31u))), "h"((unsigned short)(x + ((e.x >> 5) & 31u))),
                                "h"((unsigned short)(x + ((e.x >> 10) & 31u))), "h"((unsigned short)(x + ((e.x >> 15) & 31u)))
                              : "memory");
-                if (n > 4) {                     // only bytes 0..3 of the number line hold more than four primes
+                if (n > 4) {                     // rare away from the origin (at 4 % prime density about one byte in 10^4)
                     asm volatile("st.shared.u16 [%0+8], %1;" ::"r"(st), "h"((unsigned short)(x + ((e.x >> 20) & 31u))) : "memory");
                     if (n > 5) asm volatile("st.shared.u16 [%0+10], %1;" ::"r"(st), "h"((unsigned short)(x + ((e.x >> 25) & 31u))) : "memory");
                     if (n > 6) asm volatile("st.shared.u16 [%0+12], %1;" ::"r"(st), "h"((unsigned short)(x + (e.y & 31u))) : "memory");
