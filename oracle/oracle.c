@@ -255,6 +255,112 @@ uint64_t orc_block_sieve_sum(uint64_t lo, uint64_t hi, uint64_t segment_size, co
     return count;
 }
 
+/* ------------------------------------------------------------------------------------------------------------------
+ * CPU stand-in for the reference's preferred third-party sieve (primesieve: PyPI, version unpinned by the reference, not
+ * installed and not installable offline -- SURVEY 8(c)).  NOT a restatement of reference code: a conventional cache-blocked,
+ * bit-packed wheel-30 segmented sieve (the published primesieve design without its bucket lists) plus 256-bit accumulators,
+ * so that bench.py can report a CPU number that is not handicapped by the reference's byte-per-number numpy formulation.
+ * Checked against orc_block_sieve_sum in tests/test_oracle.py.  Same unit of work: one value block [lo, hi).
+ * ------------------------------------------------------------------------------------------------------------------ */
+static const uint8_t W30_RES[8] = {1, 7, 11, 13, 17, 19, 23, 29};
+static int w30_bit_of(uint32_t r) {
+    for (int j = 0; j < 8; ++j) if (W30_RES[j] == r) return j;
+    return -1;
+}
+typedef struct { uint64_t v[4]; } acc256;
+static inline void acc256_add_pow(acc256* a, uint64_t p, unsigned power) {
+    /* a += p^power, p < 2^40, power <= 5: p^power < 2^200 */
+    uint64_t w[4] = {1, 0, 0, 0};
+    if (power <= 3 && p < (1ull << 40)) {                         /* p^power < 2^120: one 128-bit product chain */
+        unsigned __int128 x = 1;
+        for (unsigned e = 0; e < power; ++e) x *= p;
+        unsigned __int128 c = (unsigned __int128)a->v[0] + (uint64_t)x;
+        a->v[0] = (uint64_t)c;
+        c = (c >> 64) + a->v[1] + (uint64_t)(x >> 64);
+        a->v[1] = (uint64_t)c;
+        c = (c >> 64) + a->v[2];
+        a->v[2] = (uint64_t)c;
+        a->v[3] += (uint64_t)(c >> 64);
+        return;
+    }
+    for (unsigned e = 0; e < power; ++e) {
+        unsigned __int128 c = 0;
+        for (int i = 0; i < 4; ++i) {
+            c += (unsigned __int128)w[i] * p;
+            w[i] = (uint64_t)c;
+            c >>= 64;
+        }
+    }
+    unsigned __int128 c = 0;
+    for (int i = 0; i < 4; ++i) {
+        c += (unsigned __int128)a->v[i] + w[i];
+        a->v[i] = (uint64_t)c;
+        c >>= 64;
+    }
+}
+uint64_t orc_fast_block_sieve_sum(uint64_t lo, uint64_t hi, const uint32_t* powers, uint32_t n_powers, uint32_t* sums_out,
+                                  uint64_t* last_prime) {
+    acc256 s[8];
+    memset(s, 0, sizeof s);
+    if (n_powers > 8) n_powers = 8;
+    uint64_t count = 0, last = 0;
+    if (hi >= 2 && lo < hi) {
+        for (uint64_t q = 2; q <= 5; q += (q == 2) ? 1 : 2)       /* 2, 3, 5 are not on the wheel */
+            if (q >= lo && q < hi) {
+                for (uint32_t j = 0; j < n_powers; ++j) acc256_add_pow(&s[j], q, powers[j]);
+                ++count; last = q;
+            }
+        uint64_t sqrt_limit = (uint64_t)sqrt((double)hi) + 1;
+        while (sqrt_limit * sqrt_limit < hi) ++sqrt_limit;
+        uint64_t* base = NULL;
+        const uint64_t n_base = basic_sieve(sqrt_limit + 1, &base);
+        enum { SEG_BYTES = 256 * 1024 };                           /* 7.9 M integers per segment: L2 resident */
+        uint8_t* seg = (uint8_t*)malloc(SEG_BYTES);
+        const uint64_t B_first = lo / 30, B_end = (hi + 29) / 30;  /* bitmap bytes [B_first, B_end) */
+        for (uint64_t B0 = B_first; B0 < B_end; B0 += SEG_BYTES) {
+            const uint64_t nb = (B_end - B0 < SEG_BYTES) ? (B_end - B0) : SEG_BYTES;
+            memset(seg, 0xFF, nb);
+            const uint64_t seg_hi = (B0 + nb) * 30;
+            for (uint64_t k = 0; k < n_base; ++k) {
+                const uint64_t p = base[k];
+                if (p < 7) continue;
+                if (p * p >= seg_hi) break;
+                for (int j = 0; j < 8; ++j) {                       /* cofactor residue R[j]: bytes c + p*q, one fixed bit */
+                    const uint64_t prod = p * W30_RES[j];
+                    const uint64_t c = prod / 30;
+                    const uint8_t mask = (uint8_t)~(1u << w30_bit_of((uint32_t)(prod % 30)));
+                    /* first byte index >= B0 on the strand, cofactor >= p (multiples below p*p are already crossed) */
+                    uint64_t q = (B0 > c) ? (B0 - c + p - 1) / p : 0;
+                    const uint64_t q_min = (p - W30_RES[j] + 29) / 30;   /* 30 q + R[j] >= p */
+                    if (q < q_min) q = q_min;
+                    if (j == 0 && q == 0) q = 1;                    /* cofactor 1 is the prime itself */
+                    for (uint64_t b = c + p * q; b < B0 + nb; b += p) seg[b - B0] &= mask;
+                }
+            }
+            for (uint64_t i = 0; i < nb; ++i) {
+                unsigned bits = seg[i];
+                while (bits) {
+                    const int j = __builtin_ctz(bits);
+                    bits &= bits - 1;
+                    const uint64_t v = (B0 + i) * 30 + W30_RES[j];
+                    if (v < lo || v >= hi || v < 7) continue;
+                    for (uint32_t jj = 0; jj < n_powers; ++jj) acc256_add_pow(&s[jj], v, powers[jj]);
+                    ++count; last = v;
+                }
+            }
+        }
+        free(seg);
+        free(base);
+    }
+    for (uint32_t j = 0; j < n_powers; ++j) {
+        uint32_t* o = sums_out + (size_t)j * ORC_LIMBS;
+        memset(o, 0, ORC_LIMBS * sizeof(uint32_t));
+        for (int i = 0; i < 4 && 2 * i + 1 < ORC_LIMBS; ++i) { o[2 * i] = (uint32_t)s[j].v[i]; o[2 * i + 1] = (uint32_t)(s[j].v[i] >> 32); }
+    }
+    if (last_prime) *last_prime = last;
+    return count;
+}
+
 int orc_limbs(void) { return ORC_LIMBS; }
 
 /* unused-function guard for big_sub when compiled with -Wall */

@@ -128,6 +128,24 @@ def test_block_sieve_sum_equals_two_step(orc):
         assert n == len(p) and last == int(p[-1]) and sums == orc.c_power_sums(p, [1, 2, 5])
 
 
+def test_primesieve_standin_equals_the_port(orc, golden):
+    """bench.py's second CPU number (bit-packed wheel-30 segmented sieve + 256-bit sums, a stand-in for the primesieve
+    library the reference prefers) gives exactly the port's counts, sums and last primes: range edges inside a wheel byte,
+    below 7, a segment boundary, around 2^32, near 2^40, and the reference's KATs (sum of p^k over the first 7 primes)."""
+    import random
+    rng = random.Random(5)
+    cases = [(0, 2), (0, 3), (2, 3), (0, 8), (5, 8), (0, 18), (7, 8), (49, 50), (0, 30), (29, 32), (0, 1000), (0, 3_000_000),
+             (30 * 262144 - 40, 30 * 262144 + 40), (10 ** 9, 10 ** 9 + 300_000), (2 ** 32 - 10 ** 5, 2 ** 32 + 10 ** 5),
+             (2 ** 40 - 200_000, 2 ** 40)]
+    for _ in range(25):
+        lo = rng.randrange(0, 10 ** 7)
+        cases.append((lo, lo + rng.randrange(1, 200_000)))
+    for lo, hi in cases:
+        for powers in ([2], [1, 2, 3, 4, 5]):
+            assert orc.c_fast_block_sieve_sum(lo, hi, powers) == orc.c_block_sieve_sum(lo, hi, powers), (lo, hi, powers)
+    assert orc.c_fast_block_sieve_sum(0, 18, [1, 2, 3]) == (7, [58, 666, 8944], 17)      # tests/test_gpu.py:20-23 of the reference
+
+
 def test_at_scale_consistency(golden):
     # rows recorded from SURVEY.md Appendix B: internal consistency checks that need no sieve
     rows = golden["at_scale"]
