@@ -470,13 +470,58 @@ def test_at_scale_1e9_c3(handle, golden, search_path):
     assert out.last_prime == row["p_n"] == 22801763489
     assert str(out.powers[0].final_sum) == row["sums"]["2"]
     assert out.powers[0].final_sum % 6 == (10 ** 9 + 5) % 6
-    # sampled partial sums at the Appendix-B checkpoints through synthetic hit targets
+    # every Appendix-B checkpoint (n = 1e8 .. 1e9) through a synthetic hit target: match index, p_n, S(n-1) < T
     for r in golden["at_scale"]:
         tgt = int(r["sums"]["2"])
         o = search.search(tgt, 10 ** 9, power=2)
         assert o.first() == (r["n"], 2), r["n"]
-        assert o.powers[0].cross_prime == r["p_n"]
-        break   # one extra full pass keeps the GPU test time bounded; the others run in bench --verify
+        po = o.powers[0]
+        assert po.cross_prime == r["p_n"] and po.sum_at_cross == tgt
+        assert po.sum_before_cross == tgt - r["p_n"] ** 2
+        assert str(po.final_sum) == row["sums"]["2"]
+
+
+def test_at_scale_checkpoints_all_powers(handle, golden):
+    """C5 shape at every Appendix-B checkpoint: S_1..S_5(n) and p_n for n = 1e8, 2e8, .., 1e9 (all powers in one pass),
+    and a synthetic hit of the all-powers search on each checkpoint (power rotating 1..5)"""
+    from pss_b200 import search
+    T = int(golden["trisum"][-1]["value"])
+    rows = sorted(golden["at_scale"], key=lambda r: r["n"])
+    for i, r in enumerate(rows):
+        out = search.search(T, r["n"], power=5, n_min=min(5 * 10 ** 7, r["n"]), all_powers=True)
+        assert out.last_prime == r["p_n"], r["n"]
+        assert [str(p.final_sum) for p in out.powers] == [r["sums"][str(k)] for k in range(1, 6)], r["n"]
+        assert out.first() is None
+        k = 1 + i % 5
+        o = search.search(int(r["sums"][str(k)]), 10 ** 9, power=5, all_powers=True)
+        po = next(p for p in o.powers if p.power == k)
+        assert (po.match_count, po.first_match_n, po.cross_n, po.cross_prime) == (1, r["n"], r["n"], r["p_n"]), (r["n"], k)
+        assert [str(p.final_sum) for p in o.powers] == [rows[-1]["sums"][str(j)] for j in range(1, 6)]
+
+
+def test_at_scale_prime_buffer_sha256(handle, golden):
+    """the u64 prime buffer of the first 1e9 primes against the SHA-256 rows of SURVEY Appendix B (n = 1e8 .. 1e9),
+    hashed window by window (value windows of 2^31 integers through pss_generate_primes: sieve -> k_compact_lut -> D2H)"""
+    rows = sorted(golden["at_scale"], key=lambda r: r["n"])
+    hsh = hashlib.sha256()
+    done, lo, idx = 0, 0, 0
+    end = rows[-1]["p_n"] + 1
+    while idx < len(rows):
+        assert lo < end, "ran out of range before the last checkpoint"
+        hi = min(lo + (1 << 31), end)
+        p = np.ascontiguousarray(handle.generate_primes(lo, hi), dtype="<u8")
+        pos = 0
+        while idx < len(rows) and rows[idx]["n"] <= done + len(p):
+            take = rows[idx]["n"] - done
+            hsh.update(p[pos:take].tobytes())
+            pos = take
+            assert int(p[take - 1]) == rows[idx]["p_n"], rows[idx]["n"]
+            assert hsh.copy().hexdigest() == rows[idx]["sha256_primes_le_u64"], rows[idx]["n"]
+            idx += 1
+        hsh.update(p[pos:].tobytes())
+        done += len(p)
+        lo = hi
+    assert done == 10 ** 9
 
 
 def test_at_scale_c4_c5(handle, golden):
