@@ -64,7 +64,10 @@ typedef struct pss_power_result {
     uint64_t match_count;        /* #n in [n_min,n_max] with S_k(n) <cmp> target */
     uint64_t first_match_n;      /* smallest such n, 0 if none */
     uint64_t last_match_n;       /* largest such n, 0 if none */
-    /* bracket: first n (>= first scanned n) with S_k(n) >= target, 0 if every scanned S_k(n) < target */
+    /* bracket: the n with S_k(n-1) < target <= S_k(n) when that crossing lies inside the scanned primes (S_k before the
+     * first scanned prime = carry_in, 0 for a search from n = 1).  0 when there is no crossing inside the scan: either every
+     * scanned S_k(n) < target, or carry_in >= target already (then final_sum >= target tells the two apart: the crossing
+     * lies at or before the first scanned n; for a search from n = 1 that only happens for target = 0). */
     uint64_t cross_n;
     uint64_t cross_prime;        /* p_{cross_n} */
     uint32_t sum_at_cross[PSS_LIMBS];      /* S_k(cross_n) */
@@ -178,7 +181,12 @@ int pss_slice_scan_bitmap(pss_handle* h, uint64_t n_first, const uint32_t* carry
  *      with ONE host synchronisation per query and no collective library call on the data path.
  *      Set-up: every rank calls pss_peer_export, the handles are all-gathered by the caller (any transport:
  *      torch.distributed in pss_b200.search), every rank calls pss_peer_connect.  pss_peer_search must then be
- *      called by all ranks for every query, in the same order (the mailbox epoch counts queries). ------------- */
+ *      called by all ranks for every query, in the same order (the mailbox epoch counts queries).
+ *      pss_peer_connect zeroes this rank's mailbox: it MUST be followed by a barrier over all ranks (any transport)
+ *      before the first pss_peer_search, and a re-connect must not overlap a query of any rank.  A rank whose
+ *      pss_peer_search fails on the host after the query was opened publishes an error record (pss_peer_record.error
+ *      bit 0x400, status code in bits 16..) so that the other ranks return at once instead of waiting for the
+ *      watchdog (PSS_PEER_TIMEOUT_MS, default 10 s). --------------------------------------------------------- */
 #define PSS_IPC_HANDLE_BYTES 64
 #define PSS_MAX_PEERS 16
 typedef struct pss_peer_record {

@@ -18,6 +18,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <string>
+#include <unordered_map>
 #include <vector>
 
 #include "../../include/pss_b200.h"
@@ -128,6 +129,10 @@ struct pss_handle {
     int peer_rank = -1, peer_world = 0;
     u64 peer_epoch = 0;
     PeerResult* h_peer_results = nullptr;   // pinned, kMaxPeers records
+
+    // resident CTAs per SM, per kernel and launch shape.  Kept in the handle: occupancy and the opt-in shared-memory
+    // attribute belong to the handle's device (a process may hold handles on several GPUs)
+    std::unordered_map<const void*, int> occ_map;
 
     cudaEvent_t ev[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     u64 launches = 0;
@@ -272,15 +277,40 @@ int build_patterns(pss_handle* h) {
     return PSS_OK;
 }
 
-// resident CTAs per SM of k_sieve<THREADS> with a tile of tile_bytes (the kernel's dynamic shared memory limit is
-// raised to the opt-in maximum on first use)
+// resident CTAs per SM of `kernel` for a launch shape, queried once per handle (= per device) and kernel
+template <class Kern>
+int occ_of(pss_handle* h, Kern kernel, int threads, size_t smem, int* occ) {
+    const void* key = reinterpret_cast<const void*>(kernel);
+    auto it = h->occ_map.find(key);
+    if (it != h->occ_map.end()) {
+        *occ = it->second;
+        return PSS_OK;
+    }
+    int v = 0;
+    CU_TRY(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&v, kernel, threads, smem));
+    if (v < 1) v = 1;
+    h->occ_map[key] = v;
+    *occ = v;
+    return PSS_OK;
+}
+
+// opt-in dynamic shared memory limits of the kernels that need more than 48 KiB: cudaFuncSetAttribute acts on the CURRENT
+// device only, so pss_open runs this for every handle (a second handle on another GPU would otherwise find a 48 KiB limit)
+int set_kernel_attributes(pss_handle* h) {
+    const int big = (int)(h->smem_optin - 1024);
+    CU_TRY(h, cudaFuncSetAttribute(k_sieve<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+    CU_TRY(h, cudaFuncSetAttribute(k_sieve<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+    CU_TRY(h, cudaFuncSetAttribute(k_sieve<768>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+    CU_TRY(h, cudaFuncSetAttribute(k_sieve<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+    CU_TRY(h, cudaFuncSetAttribute(k_sieve<1024, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+    CU_TRY(h, cudaFuncSetAttribute(k_compact_lut, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kClSmemBytes));
+    CU_TRY(h, cudaFuncSetAttribute(k_compact_warp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kCwSmemBytes));
+    return PSS_OK;
+}
+
+// resident CTAs per SM of k_sieve<THREADS> with a tile of tile_bytes
 template <int THREADS>
 int sieve_occupancy_t(pss_handle* h, u32 tile_bytes, int* occ) {
-    static bool attr_set = false;
-    if (!attr_set) {
-        CU_TRY(h, cudaFuncSetAttribute(k_sieve<THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(h->smem_optin - 1024)));
-        attr_set = true;
-    }
     *occ = 0;
     CU_TRY(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(occ, k_sieve<THREADS>, THREADS, (size_t)tile_bytes + kSieveScratchBytes));
     return PSS_OK;
@@ -297,11 +327,6 @@ int sieve_occupancy(pss_handle* h, u32 threads, u32 tile_bytes, int* occ) {
 template <int THREADS>
 int launch_sieve(pss_handle* h, const SieveParams& sp, u32 grid) {
     if (sp.prof && THREADS == 1024) {
-        static bool attr_set = false;
-        if (!attr_set) {
-            CU_TRY(h, cudaFuncSetAttribute(k_sieve<1024, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(h->smem_optin - 1024)));
-            attr_set = true;
-        }
         k_sieve<1024, true><<<grid, 1024, (size_t)sp.tile_bytes + kSieveScratchBytes, h->stream>>>(sp);
     } else {
         k_sieve<THREADS><<<grid, THREADS, (size_t)sp.tile_bytes + kSieveScratchBytes, h->stream>>>(sp);
@@ -505,23 +530,15 @@ int compact_resident(pss_handle* h, u64 cap) {
             const u32 grid = std::min<u32>(cp.n_groups, (u32)h->sm_count * 16);
             k_compact<<<grid, 256, 0, h->stream>>>(cp);
         } else if (!env_u32("PSS_COMPACT_WALK", 0)) {   // default: table form
-            static int occ_l = 0;
-            if (!occ_l) {
-                CU_TRY(h, cudaFuncSetAttribute(k_compact_lut, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kClSmemBytes));
-                CU_TRY(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_l, k_compact_lut, kCwWarps * 32, kClSmemBytes));
-                if (occ_l < 1) occ_l = 1;
-            }
+            int occ_l = 1;
+            PSS_TRY(occ_of(h, k_compact_lut, kCwWarps * 32, kClSmemBytes, &occ_l));
             cp.group = 1;
             cp.n_groups = h->sv_n_tiles * cp.chunks_per_tile;     // one work item per chunk
             const u32 grid = std::min<u32>((cp.n_groups + kCwWarps - 1) / kCwWarps, (u32)(h->sm_count * occ_l));
             k_compact_lut<<<grid, kCwWarps * 32, kClSmemBytes, h->stream>>>(cp);
         } else {
-            static int occ = 0;
-            if (!occ) {
-                CU_TRY(h, cudaFuncSetAttribute(k_compact_warp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kCwSmemBytes));
-                CU_TRY(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_compact_warp, kCwWarps * 32, kCwSmemBytes));
-                if (occ < 1) occ = 1;
-            }
+            int occ = 1;
+            PSS_TRY(occ_of(h, k_compact_warp, kCwWarps * 32, kCwSmemBytes, &occ));
             cp.group = 1;
             cp.n_groups = h->sv_n_tiles * cp.chunks_per_tile;     // one work item per chunk
             const u32 grid = std::min<u32>((cp.n_groups + kCwWarps - 1) / kCwWarps, (u32)(h->sm_count * occ));
@@ -558,11 +575,8 @@ int launch_scan_t(pss_handle* h, ScanParams& sp) {
     sp.tile_agg = static_cast<u32*>(h->agg.p);
     sp.tile_incl = static_cast<u32*>(h->incl.p);
     CU_TRY(h, cudaMemsetAsync(sp.tile_status, 0, (size_t)sp.n_tiles * sizeof(u32), h->stream));
-    static int occ = 0;
-    if (!occ) {
-        CU_TRY(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_power_scan<K, MULTI, MODE, ITEMS>, kScanThreads, 0));
-        if (occ < 1) occ = 1;
-    }
+    int occ = 1;
+    PSS_TRY(occ_of(h, k_power_scan<K, MULTI, MODE, ITEMS>, kScanThreads, 0, &occ));
     const u32 grid = std::min<u32>(sp.n_tiles, (u32)(h->sm_count * occ));
     k_power_scan<K, MULTI, MODE, ITEMS><<<grid, kScanThreads, 0, h->stream>>>(sp);
     CU_TRY(h, cudaGetLastError());
@@ -676,11 +690,8 @@ int run_scan(pss_handle* h, const u64* d_vals, u64 count, u64 n_first, const u32
 // ---- fused path: K2/K3 straight from the bitmap -------------------------------------------------------
 template <int K, bool MULTI, int MODE>
 int launch_bscan_t(pss_handle* h, const BScanParams& bp) {
-    static int occ = 0;
-    if (!occ) {
-        CU_TRY(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_bitmap_scan<K, MULTI, MODE>, kBsThreads, 0));
-        if (occ < 1) occ = 1;
-    }
+    int occ = 1;
+    PSS_TRY(occ_of(h, k_bitmap_scan<K, MULTI, MODE>, kBsThreads, 0, &occ));
     const u32 grid = std::min<u32>(bp.n_tiles, (u32)(h->sm_count * occ));
     k_bitmap_scan<K, MULTI, MODE><<<grid, kBsThreads, 0, h->stream>>>(bp);
     CU_TRY(h, cudaGetLastError());
@@ -699,22 +710,16 @@ void launch_scan_columns(pss_handle* h, u32 ncols, const u64* in, u64* out, u32 
 template <int K, bool MULTI>
 int launch_moments_t(pss_handle* h, const BScanParams& bp) {
     if (h->reduce_moments >= 2) {   // byte-table form (default); PSS_REDUCE_MOMENTS=1 selects the per-prime walk
-        static int occ_t = 0;
-        if (!occ_t) {
-            CU_TRY(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_t, k_bitmap_moments_tab<K, MULTI>, kBsThreads, 0));
-            if (occ_t < 1) occ_t = 1;
-        }
+        int occ_t = 1;
+        PSS_TRY(occ_of(h, k_bitmap_moments_tab<K, MULTI>, kBsThreads, 0, &occ_t));
         const u32 grid_t = std::min<u32>(bp.n_tiles, (u32)(h->sm_count * occ_t));
         k_bitmap_moments_tab<K, MULTI><<<grid_t, kBsThreads, 0, h->stream>>>(bp);
         CU_TRY(h, cudaGetLastError());
         h->launches++;
         return PSS_OK;
     }
-    static int occ = 0;
-    if (!occ) {
-        CU_TRY(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_bitmap_moments<K, MULTI>, kBsThreads, 0));
-        if (occ < 1) occ = 1;
-    }
+    int occ = 1;
+    PSS_TRY(occ_of(h, k_bitmap_moments<K, MULTI>, kBsThreads, 0, &occ));
     const u32 grid = std::min<u32>(bp.n_tiles, (u32)(h->sm_count * occ));
     k_bitmap_moments<K, MULTI><<<grid, kBsThreads, 0, h->stream>>>(bp);
     CU_TRY(h, cudaGetLastError());
@@ -869,11 +874,8 @@ int bitmap_reduce(pss_handle* h, u32 K, bool multi, bool defer_sync = false) {
     CU_TRY(h, cudaEventRecord(h->ev[4], h->stream));
     CU_TRY(h, cudaMemsetAsync(bp.cols, 0, (size_t)ncols * bp.col_stride * sizeof(u64), h->stream));
     if (K == 2 && !multi && h->reduce_moments) {
-        static int occ = 0;
-        if (!occ) {
-            CU_TRY(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_bitmap_moments2, kBsThreads, 0));
-            if (occ < 1) occ = 1;
-        }
+        int occ = 1;
+        PSS_TRY(occ_of(h, k_bitmap_moments2, kBsThreads, 0, &occ));
         const u32 grid = std::min<u32>(bp.n_tiles, (u32)(h->sm_count * occ));
         k_bitmap_moments2<<<grid, kBsThreads, 0, h->stream>>>(bp);
         CU_TRY(h, cudaGetLastError());
@@ -1094,6 +1096,7 @@ int pss_open(int device, pss_handle** out) {
     if (cudaMallocHost(&h->h_misc, sizeof(MiscDev)) != cudaSuccess) return cleanup(fail(nullptr, PSS_EINTERNAL, "pinned alloc failed"));
     if (cudaMallocHost(&h->h_back, sizeof(HostBack)) != cudaSuccess) return cleanup(fail(nullptr, PSS_EINTERNAL, "pinned alloc failed"));
     int rc = ensure(h, h->misc, sizeof(MiscDev));
+    if (rc == PSS_OK) rc = set_kernel_attributes(h);
     if (rc == PSS_OK) rc = build_patterns(h);
     if (rc != PSS_OK) {
         std::string msg = h->err;
@@ -1551,113 +1554,134 @@ int pss_peer_search(pss_handle* h, uint64_t lo, uint64_t hi_excl, const pss_sear
     // rank that died must not leave the others spinning forever.  PSS_PEER_TIMEOUT_MS, default 10 s.
     const long long watchdog = (long long)env_u32("PSS_PEER_TIMEOUT_MS", 10000) * 2000000ll;   // ~2e6 cycles per ms
 
-    // ---- phase A: sieve + block sums + column scan of this rank's slice (enqueued, not synchronised)
-    PSS_TRY(sieve_range(h, lo, hi_excl, true));
-    const bool sv_was_pending = h->sv_pending;
-    PSS_TRY(bitmap_reduce(h, K, multi, true));
-    const bool has_tiles = h->bs_n_tiles > 0;
-    if (!sv_was_pending) CU_TRY(h, cudaEventRecord(h->ev[0], h->stream));   // empty slice: the chain starts here
+    // Everything below can fail on the host (allocations, launches).  The epoch is open: a failure before this rank's two
+    // publishes must still release the peers (k_peer_publish_failure), or they would spin until the watchdog fires.
+    int stage = 0;           // publishes done: 1 = slice totals, 2 = outcome record
+    auto run = [&]() -> int {
+        // ---- phase A: sieve + block sums + column scan of this rank's slice (enqueued, not synchronised)
+        PSS_TRY(sieve_range(h, lo, hi_excl, true));
+        const bool sv_was_pending = h->sv_pending;
+        PSS_TRY(bitmap_reduce(h, K, multi, true));
+        const bool has_tiles = h->bs_n_tiles > 0;
+        if (!sv_was_pending) CU_TRY(h, cudaEventRecord(h->ev[0], h->stream));   // empty slice: the chain starts here
 
-    MiscDev* hm = h->h_misc;
-    MiscDev* dm = static_cast<MiscDev*>(h->misc.p);
-    memset(hm, 0, sizeof(MiscDev));
-    for (u32 j = 0; j < np; ++j) {
-        hm->results[j].power = expo_of(K, multi, j);
-        hm->results[j].first_match_n = ~0ull;
-    }
-    CU_TRY(h, cudaMemcpyAsync(dm, hm, sizeof(MiscDev), cudaMemcpyHostToDevice, h->stream));
+        MiscDev* hm = h->h_misc;
+        MiscDev* dm = static_cast<MiscDev*>(h->misc.p);
+        memset(hm, 0, sizeof(MiscDev));
+        for (u32 j = 0; j < np; ++j) {
+            hm->results[j].power = expo_of(K, multi, j);
+            hm->results[j].first_match_n = ~0ull;
+        }
+        CU_TRY(h, cudaMemcpyAsync(dm, hm, sizeof(MiscDev), cudaMemcpyHostToDevice, h->stream));
 
-    // ---- the exchange: publish the slice totals into every rank's mailbox, gather the lower ranks' totals
-    PeerPublishParams pp;
-    memset(&pp, 0, sizeof pp);
-    pp.col_prefix = has_tiles ? static_cast<const u64*>(h->col_prefix.p) : nullptr;
-    pp.col_stride = h->bs_col_stride;
-    pp.n_tiles = h->bs_n_tiles;
-    pp.np = np;
-    for (u32 j = 0; j < np; ++j) pp.width[j] = (u32)sum_limbs((int)expo_of(K, multi, j));
-    for (u32 r = 0; r < world; ++r) pp.box[r] = h->box[r];
-    pp.world = world;
-    pp.rank = rank;
-    pp.epoch = epoch;
-    PeerGatherParams pg;
-    memset(&pg, 0, sizeof pg);
-    pg.box = h->box_local;
-    pg.world = world; pg.rank = rank; pg.np = np;
-    pg.epoch = epoch;
-    pg.watchdog = watchdog;
-    pg.n_first_out = &dm->n_first;
-    pg.carry_out = dm->carry;
-    pg.error_flag = &dm->error_flag;
-    static const bool peer_split = env_u32("PSS_PEER_MERGE", 0) == 0;   // default: the two halves as separate launches (8-GPU A/B)
-    if (peer_split) {
-        k_peer_publish<<<1, 32, 0, h->stream>>>(pp);
-        k_peer_gather<<<1, 32, 0, h->stream>>>(pg);
-        h->launches += 2;
-    } else {
-        k_peer_exchange<<<1, 32, 0, h->stream>>>(pp, pg);
-        h->launches += 1;
-    }
-    CU_TRY(h, cudaGetLastError());
+        // ---- the exchange: publish the slice totals into every rank's mailbox, gather the lower ranks' totals
+        PeerPublishParams pp;
+        memset(&pp, 0, sizeof pp);
+        pp.col_prefix = has_tiles ? static_cast<const u64*>(h->col_prefix.p) : nullptr;
+        pp.col_stride = h->bs_col_stride;
+        pp.n_tiles = h->bs_n_tiles;
+        pp.np = np;
+        for (u32 j = 0; j < np; ++j) pp.width[j] = (u32)sum_limbs((int)expo_of(K, multi, j));
+        for (u32 r = 0; r < world; ++r) pp.box[r] = h->box[r];
+        pp.world = world;
+        pp.rank = rank;
+        pp.epoch = epoch;
+        PeerGatherParams pg;
+        memset(&pg, 0, sizeof pg);
+        pg.box = h->box_local;
+        pg.world = world; pg.rank = rank; pg.np = np;
+        pg.epoch = epoch;
+        pg.watchdog = watchdog;
+        pg.n_first_out = &dm->n_first;
+        pg.carry_out = dm->carry;
+        pg.error_flag = &dm->error_flag;
+        static const bool peer_split = env_u32("PSS_PEER_MERGE", 0) == 0;   // default: the two halves as separate launches (8-GPU A/B)
+        if (peer_split) {
+            k_peer_publish<<<1, 32, 0, h->stream>>>(pp);
+            k_peer_gather<<<1, 32, 0, h->stream>>>(pg);
+            h->launches += 2;
+        } else {
+            k_peer_exchange<<<1, 32, 0, h->stream>>>(pp, pg);
+            h->launches += 1;
+        }
+        CU_TRY(h, cudaGetLastError());
+        stage = 1;
 
-    // ---- phase B: compare, seeded from device memory (n_first, carry)
-    CU_TRY(h, cudaEventRecord(h->ev[6], h->stream));
-    if (has_tiles) {
-        BScanParams bp;
-        fill_compare_params(h, bp, a, 0);
-        bp.n_first_dev = &dm->n_first;
-        PSS_TRY(launch_bscan<kBsCompare>(h, bp, K, multi));
-    }
-    CU_TRY(h, cudaEventRecord(h->ev[7], h->stream));
+        // ---- phase B: compare, seeded from device memory (n_first, carry)
+        CU_TRY(h, cudaEventRecord(h->ev[6], h->stream));
+        if (has_tiles) {
+            BScanParams bp;
+            fill_compare_params(h, bp, a, 0);
+            bp.n_first_dev = &dm->n_first;
+            PSS_TRY(launch_bscan<kBsCompare>(h, bp, K, multi));
+        }
+        CU_TRY(h, cudaEventRecord(h->ev[7], h->stream));
 
-    // ---- outcome records: publish to every rank, wait for every rank's
-    PeerResultParams pr;
-    memset(&pr, 0, sizeof pr);
-    for (u32 r = 0; r < world; ++r) pr.box[r] = h->box[r];
-    pr.world = world; pr.rank = rank; pr.np = np;
-    pr.epoch = epoch;
-    pr.n_max = a->n_max;
-    pr.n_first = &dm->n_first;
-    pr.carry = dm->carry;
-    pr.results = dm->results;
-    pr.last_prime = &dm->last_prime;
-    pr.error_flag = &dm->error_flag;
-    pr.col_prefix = pp.col_prefix;
-    pr.col_stride = pp.col_stride;
-    pr.n_tiles = pp.n_tiles;
-    for (u32 j = 0; j < np; ++j) pr.width[j] = pp.width[j];
-    if (peer_split) {
-        k_peer_publish_result<<<1, 256, 0, h->stream>>>(pr);
-        k_peer_gather_results<<<1, 32, 0, h->stream>>>(h->box_local, world, epoch, watchdog, &dm->error_flag);
-        h->launches += 2;
-    } else {
-        k_peer_exchange_results<<<1, 256, 0, h->stream>>>(pr, h->box_local, world, epoch, watchdog, &dm->error_flag);
-        h->launches += 1;
-    }
-    CU_TRY(h, cudaGetLastError());
-    CU_TRY(h, cudaMemcpyAsync(h->h_peer_results, &h->box_local->r[epoch & 1ull][0], sizeof(PeerResult) * world, cudaMemcpyDeviceToHost, h->stream));
-    CU_TRY(h, cudaMemcpyAsync(hm, dm, sizeof(MiscDev), cudaMemcpyDeviceToHost, h->stream));
-    cudaEvent_t ev_end = h->ev[3];   // compaction event, unused on this path
-    CU_TRY(h, cudaEventRecord(ev_end, h->stream));
-    CU_TRY(h, cudaStreamSynchronize(h->stream));
+        // ---- outcome records: publish to every rank, wait for every rank's
+        PeerResultParams pr;
+        memset(&pr, 0, sizeof pr);
+        for (u32 r = 0; r < world; ++r) pr.box[r] = h->box[r];
+        pr.world = world; pr.rank = rank; pr.np = np;
+        pr.epoch = epoch;
+        pr.n_max = a->n_max;
+        pr.n_first = &dm->n_first;
+        pr.carry = dm->carry;
+        pr.results = dm->results;
+        pr.last_prime = &dm->last_prime;
+        pr.error_flag = &dm->error_flag;
+        pr.col_prefix = pp.col_prefix;
+        pr.col_stride = pp.col_stride;
+        pr.n_tiles = pp.n_tiles;
+        for (u32 j = 0; j < np; ++j) pr.width[j] = pp.width[j];
+        if (peer_split) {
+            k_peer_publish_result<<<1, 256, 0, h->stream>>>(pr);
+            k_peer_gather_results<<<1, 32, 0, h->stream>>>(h->box_local, world, epoch, watchdog, &dm->error_flag);
+            h->launches += 2;
+        } else {
+            k_peer_exchange_results<<<1, 256, 0, h->stream>>>(pr, h->box_local, world, epoch, watchdog, &dm->error_flag);
+            h->launches += 1;
+        }
+        CU_TRY(h, cudaGetLastError());
+        stage = 2;
+        CU_TRY(h, cudaMemcpyAsync(h->h_peer_results, &h->box_local->r[epoch & 1ull][0], sizeof(PeerResult) * world, cudaMemcpyDeviceToHost, h->stream));
+        CU_TRY(h, cudaMemcpyAsync(hm, dm, sizeof(MiscDev), cudaMemcpyDeviceToHost, h->stream));
+        cudaEvent_t ev_end = h->ev[3];   // compaction event, unused on this path
+        CU_TRY(h, cudaEventRecord(ev_end, h->stream));
+        CU_TRY(h, cudaStreamSynchronize(h->stream));
 
-    sieve_finish(h);
-    PSS_TRY(reduce_finish(h));
-    h->acc.ms_power_scan += ev_ms(h, 6, 7);
-    h->acc.ms_bitmap_compare += ev_ms(h, 6, 7);
-    h->acc.ms_span += ev_ms(h, 0, 3);     // first launch -> all ranks' outcomes gathered (waits on peers included)
-    if (hm->error_flag) return fail(h, PSS_EINTERNAL, "peer exchange failed on the device (flags 0x%x): a rank did not publish in time", hm->error_flag);
-    u64 scanned_here = 0;
-    for (u32 r = 0; r < world; ++r) {
-        const PeerResult& s = h->h_peer_results[r];
-        pss_peer_record& o = records_out[r];
-        o.valid = s.valid; o.n_first = s.n_first; o.scanned = s.scanned; o.last_prime = s.last_prime; o.count = s.count; o.error = s.error;
-        memcpy(o.powers, s.powers, sizeof o.powers);
-        if (s.error) return fail(h, PSS_EINTERNAL, "rank %u reported device error flags 0x%llx", r, (unsigned long long)s.error);
-        if (r == rank) scanned_here = s.scanned;
+        sieve_finish(h);
+        PSS_TRY(reduce_finish(h));
+        h->acc.ms_power_scan += ev_ms(h, 6, 7);
+        h->acc.ms_bitmap_compare += ev_ms(h, 6, 7);
+        h->acc.ms_span += ev_ms(h, 0, 3);     // first launch -> all ranks' outcomes gathered (waits on peers included)
+        if (hm->error_flag) return fail(h, PSS_EINTERNAL, "peer exchange failed on the device (flags 0x%x): a rank did not publish in time", hm->error_flag);
+        u64 scanned_here = 0;
+        for (u32 r = 0; r < world; ++r) {
+            const PeerResult& s = h->h_peer_results[r];
+            pss_peer_record& o = records_out[r];
+            o.valid = s.valid; o.n_first = s.n_first; o.scanned = s.scanned; o.last_prime = s.last_prime; o.count = s.count; o.error = s.error;
+            memcpy(o.powers, s.powers, sizeof o.powers);
+            if (s.error) return fail(h, PSS_EINTERNAL, "rank %u reported device error flags 0x%llx", r, (unsigned long long)s.error);
+            if (r == rank) scanned_here = s.scanned;
+        }
+        h->acc.primes += scanned_here;
+        if (stats) fill_stats(h, stats, before);
+        return PSS_OK;
+    };
+    const int rc = run();
+    if (rc != PSS_OK && stage < 2) {
+        const std::string keep = h->err;
+        PeerFailParams pf;
+        memset(&pf, 0, sizeof pf);
+        for (u32 r = 0; r < world; ++r) pf.box[r] = h->box[r];
+        pf.world = world; pf.rank = rank; pf.stage = (u32)stage; pf.epoch = epoch;
+        pf.code = 0x400ull | ((u64)rc << 16);
+        k_peer_publish_failure<<<1, 32, 0, h->stream>>>(pf);
+        cudaStreamSynchronize(h->stream);
+        cudaGetLastError();
+        h->err = keep;
     }
-    h->acc.primes += scanned_here;
-    if (stats) fill_stats(h, stats, before);
-    return PSS_OK;
+    return rc;
 }
 
 int pss_slice_reduce(pss_handle* h, uint64_t first, uint64_t count, uint32_t power_max, uint32_t all_powers, uint32_t* sums_out) {

@@ -236,6 +236,34 @@ __global__ void k_peer_publish_result(const PeerResultParams P) { peer_publish_r
 __global__ void k_peer_gather_results(PeerBox* box, u32 world, u64 epoch, long long watchdog, u32* error_flag) {
     peer_gather_results_body(box, world, epoch, watchdog, error_flag);
 }
+// A rank whose host side failed after the query's epoch was opened (allocation, launch error) still has to release its
+// peers: it publishes empty slice totals (stage 0) and an outcome record whose error field carries `code` (stages 0, 1), so
+// the other ranks leave their waits at once and report the failing rank instead of running into the watchdog.
+struct PeerFailParams {
+    PeerBox* box[kMaxPeers];
+    u32 world, rank;
+    u32 stage;               // publishes already done by this rank: 0 none, 1 slice totals
+    u64 epoch;
+    u64 code;
+};
+__global__ void k_peer_publish_failure(const PeerFailParams P) {
+    const u32 t = threadIdx.x;
+    if (t >= P.world) return;
+    if (P.stage < 1) {
+        PeerSlot* s = &P.box[t]->a[P.epoch & 1ull][P.rank];
+        s->count = 0;
+        for (u32 i = 0; i < PSS_MAX_POWER * PSS_LIMBS; ++i) s->sums[i] = 0;
+        __threadfence_system();
+        st_release_sys(&s->flag, P.epoch);
+    }
+    PeerResult* r = &P.box[t]->r[P.epoch & 1ull][P.rank];
+    u64* w = reinterpret_cast<u64*>(r);
+    for (u32 i = 1; i < sizeof(PeerResult) / 8; ++i) w[i] = 0;
+    r->error = P.code;
+    __threadfence_system();
+    st_release_sys(&r->flag, P.epoch);
+}
+
 __global__ void k_peer_exchange(const PeerPublishParams PP, const PeerGatherParams PG) {
     peer_publish_body(PP);
     __syncthreads();

@@ -61,6 +61,11 @@ class SearchOutcome:
         po = self.powers[0] if power is None else next(p for p in self.powers if p.power == power)
         if po.cross_n:
             return po.cross_n - 1, po.cross_n
+        if po.final_sum >= self.target:
+            # no crossing inside the scan although S(n_max) >= target: the running sum was already >= target before the
+            # first scanned prime (target = 0, or a resumed / sliced scan whose carry-in is past the target)
+            first = int(self.stats.get("resumed_from_n", 0)) + 1
+            return first - 1, first
         return self.n_max, self.n_max + 1
 
 
@@ -140,15 +145,42 @@ def _outcome_from_result(res: "_lib.SearchResult", n_min, n_max, op, target) -> 
 
 
 def search(target: int, n_max: int, power: int = 2, n_min: int = 1, op: str = "==",
-           all_powers: bool = False, handle: Optional["_lib.Handle"] = None) -> SearchOutcome:
-    """Single-GPU fused search.  `all_powers=True` evaluates every p in 1..power in the same pass."""
+           all_powers: bool = False, handle: Optional["_lib.Handle"] = None, resume=None) -> SearchOutcome:
+    """Single-GPU fused search.  `all_powers=True` evaluates every p in 1..power in the same pass.
+
+    `resume`: an IncrementalSumCache-like state (this package's or the reference's class: .metadata.prime_count,
+    .metadata.last_prime, .sums) that already holds S_k(c) of the first c primes.  The search then covers
+    n in (c, n_max] only: the sieve starts above last_prime and the running sums start from the checkpointed
+    values instead of being re-accumulated from n = 1 (reference ROADMAP #26 `--start-n`,
+    utils/sum_cache.py:169-261 is the file format)."""
     if op not in OPS:
         raise ValueError(f"unknown comparison operator {op!r}")
     if target < 0:
         raise ValueError("target must be non-negative")
     h = handle or _lib.default_handle()
+    if resume is not None and int(resume.metadata.prime_count) > 0:
+        return _resume_search(h, resume, target, n_max, power, n_min, op, all_powers)
     res = h.search(n_min, n_max, power, target, op, all_powers)
     return _outcome_from_result(res, n_min, n_max, op, target)
+
+
+def _resume_search(h, state, target, n_max, power, n_min, op, all_powers) -> SearchOutcome:
+    c0, p0 = int(state.metadata.prime_count), int(state.metadata.last_prime)
+    ks = list(range(1, power + 1)) if (all_powers and power > 1) else [power]
+    missing = [k for k in ks if k not in state.sums]
+    if missing:
+        raise ValueError(f"the checkpoint does not track power(s) {missing}; tracked: {sorted(state.sums)}")
+    if n_max <= c0:
+        raise ValueError(f"nothing to search: the checkpoint already covers n <= {c0} (n_max = {n_max})")
+    lo_n = max(int(n_min), c0 + 1)
+    hi = h.nth_prime_upper(n_max) + 1
+    cnt, _ = h.slice_sieve_sums(p0 + 1, hi, power, all_powers)
+    if c0 + cnt < n_max:
+        raise RuntimeError("prime count bound violated")
+    res = h.slice_scan_bitmap(c0 + 1, [int(state.sums[k]) for k in ks], lo_n, n_max, power, target, op, all_powers)
+    out = _outcome_from_result(res, lo_n, n_max, op, target)
+    out.stats["resumed_from_n"] = c0
+    return out
 
 
 def does_exist(target: int, n_max: int, power: int = 2, n_min: int = 1, op: str = "==",

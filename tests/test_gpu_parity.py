@@ -209,6 +209,13 @@ def test_fastpath_reproduces_reference_cli_output(handle, golden):
     assert try_fast_query("does_exist primesum(n,2) == trisum(666)", {"n": 200000}) == (["No match found within bounds."], 1)
     assert try_fast_query("does_exist primesum(n,2) == 666", {"n": 100}, {"n": 8}) == (["No match found within bounds."], 1)
     assert try_fast_query("primesum(n,2) + 1 == 667") is None and try_fast_query("fibonacci(n) == 8") is None
+    # shapes a regex would miss: parentheses, qualified name, reversed comparison
+    assert try_fast_query("does_exist (primesum(n, 2)) == (666)") == (["Found: n=7"], 0)
+    assert try_fast_query("does_exist pss.primesum(n,2) == 666") == (["Found: n=7"], 0)
+    assert try_fast_query("does_exist trisum(10) == primesum(n,2)") == (["Found: n=7"], 0)
+    assert try_fast_query("for_any 100 < primesum(n,2)", {"n": 8}) == (["Found: n=5", "Found: n=6", "Found: n=7", "Found: n=8"], 0)
+    assert try_fast_query("for_any primesum(n,p) == 8944", {"n": 12, "p": 3}) == (["Found: n=7, p=3"], 0)
+    assert try_fast_query("for_any primesum(n,p) == 8944", {"n": 12, "p": 7}) is None       # p beyond the all-powers pass
     for case in golden["find_matches"]:
         res = try_fast_query(case["expr"], case["bounds"])
         exp = ["Found: " + ", ".join(f"{k}={v}" for k, v in sorted(mm.items())) for mm in case["matches"]]
@@ -436,6 +443,55 @@ def test_sum_cache_device_advance(handle, orc, tmp_path):
     d.advance_to(120000)
     primes = orc.c_first_n_primes(120000)
     assert [d.get_sum(k) for k in (2, 3, 4)] == orc.c_power_sums(primes, [2, 3, 4])
+
+
+def test_primesum_window_walk_and_jumps(handle, orc):
+    """the plugin's primesum: sequential n (the evaluator's loop) crosses several device windows, each continued from the
+    end of the previous one; jumps to arbitrary n take their carry from one fused pass"""
+    from pss_b200 import sequences
+    sequences.clear_cache()
+    old = sequences.WINDOW
+    sequences.WINDOW = 1000
+    try:
+        primes = orc.c_first_n_primes(60000)
+        for k in (1, 2, 5):
+            sums = orc.c_prefix_sums(primes, k)
+            sequences.clear_cache()
+            for n in list(range(1, 7001)) + [7, 6999, 20000, 20001, 59999, 60000, 12345, 1]:
+                assert sequences.primesum(n, k) == sums[n - 1], (n, k)
+    finally:
+        sequences.WINDOW = old
+        sequences.clear_cache()
+    assert sequences.primesum(10 ** 7, 2) == 103158861357874372432083          # SURVEY 8(c) table
+    assert sequences.primesum(10 ** 7 + 1, 2) == 103158861357874372432083 + 179424691 ** 2
+
+
+def test_search_resumes_from_checkpoint(handle, orc, tmp_path):
+    """a search continued from an IncrementalSumCache checkpoint (reference ROADMAP #26 --start-n) gives the answer of
+    the search from n = 1, for hits after the checkpoint, and never looks below it"""
+    from pss_b200 import search
+    from pss_b200.sum_cache import IncrementalSumCache
+    n_max = 250000
+    primes = orc.c_first_n_primes(n_max)
+    c = IncrementalSumCache(powers=[1, 2, 3])
+    c.advance_to(100000)
+    c.save_checkpoint(tmp_path / "ck.npz")
+    st = IncrementalSumCache.load_checkpoint(tmp_path / "ck.npz")
+    for k, allp in ((2, False), (3, True)):
+        sums = orc.c_prefix_sums(primes, k)
+        for hit in (100001, 100002, 180000, n_max):
+            full = search.search(sums[hit - 1], n_max, power=k, all_powers=allp)
+            res = search.search(sums[hit - 1], n_max, power=k, all_powers=allp, resume=st)
+            assert res.first() == full.first() == (hit, k)
+            assert [(p.cross_n, p.cross_prime, p.sum_at_cross, p.sum_before_cross, p.final_sum) for p in res.powers] == \
+                   [(p.cross_n, p.cross_prime, p.sum_at_cross, p.sum_before_cross, p.final_sum) for p in full.powers]
+            assert res.last_prime == full.last_prime == int(primes[-1]) and res.stats["resumed_from_n"] == 100000
+        assert search.search(sums[49999], n_max, power=k, all_powers=allp, resume=st).first() is None    # hit below the checkpoint
+        o = search.search(10 ** 80, n_max, power=k, all_powers=allp, resume=st)
+        assert o.first() is None and o.bracket() == (n_max, n_max + 1) and o.powers[-1].final_sum == sums[-1]
+    assert st.resume_search(orc.c_prefix_sums(primes, 2)[199999], n_max).first() == (200000, 2)
+    with pytest.raises(ValueError, match="does not track"):
+        search.search(1, n_max, power=5, resume=st)
 
 
 # ------------------------------------------------------------------------------- at scale

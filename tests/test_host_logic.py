@@ -193,6 +193,54 @@ def test_sum_cache_checkpoint_matches_reference_format(tmp_path, orc):
             sys.path.remove("/root/reference")
 
 
+def test_sum_cache_advance_equals_per_prime_path(tmp_path, orc):
+    """sum_cache.advance (one fused device pass; here through the oracle stand-in handle) leaves exactly the state the
+    per-prime path leaves: counts, last prime, sums, head and tail windows — on this package's class and, when the
+    reference tree is present, on an instance of the reference's own class (state in / state out)."""
+    from pss_b200 import sum_cache
+    h = OracleHandle()
+    primes = [int(p) for p in orc.c_first_n_primes(3000)]
+    classes = [sum_cache.IncrementalSumCache]
+    if os.path.exists("/root/reference/utils/sum_cache.py"):
+        sys.path.insert(0, "/root/reference")
+        try:
+            from utils.sum_cache import IncrementalSumCache as Ref
+            classes.append(Ref)
+        finally:
+            sys.path.remove("/root/reference")
+    for cls in classes:
+        for powers in ([2, 3, 4], [2], [5, 1], [0, 3], [7, 2]):
+            for start, stops in ((0, (1, 2, 3, 700, 3000)), (1, (2, 50)), (2, (3, 4)), (40, (41, 42, 45, 2999))):
+                ref, dev = cls(powers=list(powers)), cls(powers=list(powers))
+                for p in primes[:start]:
+                    ref.add_prime(p)
+                    dev.add_prime(p)
+                done = start
+                for stop in stops:
+                    for p in primes[done:stop]:
+                        ref.add_prime(p)
+                    done = stop
+                    sum_cache.advance(dev, stop, handle=h)
+                    assert dev.sums == ref.sums, (cls.__name__, powers, start, stop)
+                    assert (dev.metadata.prime_count, dev.metadata.last_prime) == (stop, primes[stop - 1])
+                    assert [tuple(r) for r in dev.initial_values] == [tuple(r) for r in ref.initial_values]
+                    assert [tuple(r) for r in dev.recent_values] == [tuple(r) for r in ref.recent_values], (cls.__name__, powers, start, stop)
+                sum_cache.advance(dev, 1, handle=h)           # going backwards is a no-op
+                assert dev.metadata.prime_count == done
+    # numpy powers must serialise (the reference converts them; ADVICE r1)
+    c = sum_cache.IncrementalSumCache(powers=list(np.arange(2, 4)))
+    c.add_prime(np.int64(2))
+    c.save_checkpoint(tmp_path / "np.npz")
+    assert sum_cache.IncrementalSumCache.load_checkpoint(tmp_path / "np.npz").sums == {2: 4, 3: 8}
+    # old JSON checkpoints (utils/sum_cache.py:324-368)
+    import json
+    (tmp_path / "old.json").write_text(json.dumps({"primes_processed": 7, "last_prime": 17, "current_sum": "666"}))
+    sum_cache.migrate_old_checkpoint(tmp_path / "old.json", tmp_path / "new.npz")
+    m = sum_cache.IncrementalSumCache.load_checkpoint(tmp_path / "new.npz")
+    assert (m.get_sum(2), m.get_prime_count(), m.get_last_prime()) == (666, 7, 17)
+    m.report()
+
+
 # --------------------------------------------------------------------------- N > 1 over gloo
 class OracleHandle:
     """Stand-in for _lib.Handle implementing the fused slice API with the oracle (host logic tests only)."""
@@ -209,11 +257,34 @@ class OracleHandle:
         b = n * (math.log(n) + math.log(math.log(n)) - (0.9484 if n >= 39017 else 0.0))
         return int(b) + 3
 
+    def generate_primes(self, lo, hi):
+        return self.orc.c_primes_range(lo, hi).astype(np.int64)
+
+    def nth_prime(self, n):
+        return int(self.orc.c_first_n_primes(n)[-1])
+
     def slice_sieve_sums(self, lo, hi, power_max, all_powers=False):
         self.primes = self.orc.c_primes_range(lo, hi)
         powers = list(range(1, power_max + 1)) if (all_powers and power_max > 1) else [power_max]
         self.cfg = powers
         return len(self.primes), self.orc.c_power_sums(self.primes, powers)
+
+    def search(self, n_min, n_max, power_max, target, op="==", all_powers=False):
+        self.primes = self.orc.c_first_n_primes(n_max)
+        self.cfg = list(range(1, power_max + 1)) if (all_powers and power_max > 1) else [power_max]
+        return self.slice_scan_bitmap(1, [0] * len(self.cfg), n_min, n_max, power_max, target, op, all_powers)
+
+    def search_targets(self, n_min, n_max, power_max, targets, op="==", all_powers=False):
+        return [self.search(n_min, n_max, power_max, t, op, all_powers) for t in targets]
+
+    def search_tri(self, n_min, n_max, power, m_min, m_max, cap=4096):
+        sums = self.orc.c_prefix_sums(self.orc.c_first_n_primes(n_max), power)
+        pairs = []
+        for i, s_ in enumerate(sums):
+            m = self.orc.qtri(s_)
+            if i + 1 >= n_min and m is not None and max(m_min, 1) <= m <= m_max:
+                pairs.append((i + 1, m))
+        return pairs, {}
 
     def slice_scan_bitmap(self, n_first, carry, n_min, n_max, power_max, target, op="==", all_powers=False):
         from pss_b200 import _lib
@@ -297,22 +368,45 @@ def test_fastpath_recogniser_host_side(orc):
     # shapes that are NOT the hot path stay with the generic evaluator
     for expr in ("fibonacci(n) == 8", "primesum(n,2) + 1 == 667", "does_exist primesum(n,2) == fibonacci(m) + 1",
                  "does_exist primesum(n,2) < fibonacci(m)", "does_exist primesum(n,2) == fibonacci(n)",
-                 "for_any primesum(n,2) < tri(m)", "verify primesum(7,2) == 666", "primesum(n, n) == 4"):
+                 "for_any primesum(n,2) < tri(m)", "verify primesum(7,2) == 666", "primesum(n, n) == 4",
+                 "primesum(n,2) == 666 == 666", "does_exist primesum(n,9) == 4", "primesum(n,p) == 4 and n > 2"):
         assert fastpath.try_fast_query(expr, {"n": 10, "m": 10}) is None, expr
-    assert fastpath._RHS_CALL.match("fibonacci(m)").groupdict() == {"fn": "fibonacci", "arg": "m"}
     from pss_b200 import search
     assert [search.RHS_SEQUENCES["fibonacci"](i) for i in range(11)] == [0, 1, 1, 2, 3, 5, 8, 13, 21, 34, 55]     # utils/sequences.py:83-117
     assert [search.RHS_SEQUENCES["catalan"](i) for i in range(10)] == [1, 1, 2, 5, 14, 42, 132, 429, 1430, 4862]  # :160-200
     assert [search.RHS_SEQUENCES["factorial"](i) for i in (0, 1, 5, 10)] == [1, 1, 120, 3628800]                  # :120-157
-    m = fastpath._EXPR.match("for_any primesum(n,p) >= 8944")
-    assert m.groupdict() == {"quant": "for_any", "nvar": "n", "parg": "p", "op": ">=", "rhs": "8944"}
+    Q = fastpath.Query
+    table = {
+        "for_any primesum(n,p) >= 8944": Q("for_any", "n", ">=", pvar="p", target=8944),
+        "primesum(n,2) == 666": Q("does_exist", "n", "==", power=2, target=666),
+        "does_exist primesum(n) == 666": Q("does_exist", "n", "==", power=2, target=666),
+        "does_exist (primesum(n, 2)) == (666)": Q("does_exist", "n", "==", power=2, target=666),
+        "does_exist (primesum(n,2) == 666)": Q("does_exist", "n", "==", power=2, target=666),
+        "does_exist pss.primesum(k,3) != trisum(10)": Q("does_exist", "k", "!=", power=3, target=666),
+        "does_exist trisum(666) == primesum(n,2)": Q("does_exist", "n", "==", power=2, target=orc.trisum(666)),
+        "for_any 100 < primesum(n,2)": Q("for_any", "n", ">", power=2, target=100),
+        "for_any 100 >= primesum(n,1)": Q("for_any", "n", "<=", power=1, target=100),
+        "for_any tri(m) == primesum(n,2)": Q("for_any", "n", "==", power=2, seq_fn="tri", mvar="m"),
+        "for_any primesum(n,1) == pss.fibonacci(j)": Q("for_any", "n", "==", power=1, seq_fn="fibonacci", mvar="j"),
+        "primesum(n,2) == factorial(5)": Q("does_exist", "n", "==", power=2, target=120),
+    }
+    for text, want in table.items():
+        tree = fastpath.parse(text)
+        got = fastpath.recognise(tree) if tree is not None else None
+        assert got == want, (text, got)
     assert fastpath.format_match({"n": 7, "m": 36}) == "Found: m=36, n=7"                      # utils/cli.py:1253,1271
     assert fastpath.format_match({"n": 7}, "json") == '{"found": true, "variables": {"n": 7}}'  # tests/test_cli_integration.py:257-267
     assert fastpath.format_match({"n": 7}, "csv") == "n=7"
     assert fastpath.format_no_match() == "No match found within bounds."
     assert fastpath.format_no_match("json") == '{"found": false, "variables": null}'
-    with pytest.raises(ValueError, match="Missing bound"):
+    with pytest.raises(ValueError, match=r"Missing bounds for variable\(s\): q. Use --max q:VALUE to specify."):
         fastpath.try_fast_query("primesum(q,2) == 4")
+    # free power variable beyond the device's all-powers pass: generic path, not an error
+    h = OracleHandle()
+    q = fastpath.recognise(fastpath.parse("for_any primesum(n,p) == 8944"))
+    assert fastpath.matches(q, {"n": (1, 20), "p": (1, 7)}, handle=h) is None
+    assert fastpath.matches(q, {"n": (1, 20), "p": (1, 3)}, handle=h) == [{"n": 7, "p": 3}]
+    assert fastpath.matches(q, {"n": (8, 20), "p": (1, 3)}, handle=h) == []
 
 
 def test_prime_io_window_plan():

@@ -53,37 +53,39 @@ __global__ void __launch_bounds__(1024, 1) k_alu(unsigned* out, unsigned seed) {
     if (r == 0x12345u) out[0] = r;
 }
 
-// MODE 0: lane l -> bank l (conflict free), 1: pseudo-random word per lane and iteration, 2: LDS.32, 3: LDS.128
+// MODE 0: ATOMS.AND, lane l -> bank l (conflict free); 1: ATOMS.AND, 32 pseudo-random words per instruction (fixed per
+// lane, the whole pattern shifted every iteration); 2: LDS.32 conflict free; 3: LDS.128; 4: ATOMS.AND, all lanes of a warp
+// on ONE bank (32 different words): the serialisation rate.  Addressing is one add per 8 accesses (immediate offsets),
+// so the loop issues ~1.4 instructions per access and the shared-memory pipe is what is measured.
 template <int MODE>
 __global__ void __launch_bounds__(1024, 1) k_smem(unsigned* out, unsigned seed, unsigned words) {
     extern __shared__ unsigned sm[];
     for (unsigned i = threadIdx.x; i < words; i += blockDim.x) sm[i] = ~0u;
     __syncthreads();
-    const unsigned lane = threadIdx.x & 31u;
-    unsigned x = seed * 2654435761u + threadIdx.x * 40503u, acc = 0;
-    unsigned off = (threadIdx.x * 32u + lane) % words;
+    const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    unsigned acc = 0;
+    // per-lane word offset inside a 4096-word window; 8 accesses at +0, +4096, .. (same bank), window start moves by 32 words
+    unsigned w0;
+    if (MODE == 1) w0 = ((seed * 2654435761u + threadIdx.x * 40503u) * 1664525u + 1013904223u) >> 20;   // 0..4095, random bank
+    else if (MODE == 4) w0 = (lane * 32u + warp) & 4095u;                                                // bank = warp & 31 for all lanes
+    else if (MODE == 3) w0 = (lane * 4u + warp * 128u) & 4095u;                                          // 16-byte vector per lane
+    else w0 = (lane + warp * 32u) & 4095u;                                                                // bank = lane
+    const unsigned mask = ~(1u << (seed & 31u));
+    unsigned base = w0;
 #pragma unroll 1
     for (int it = 0; it < kIters; ++it) {
+        unsigned* p = sm + base;
 #pragma unroll
         for (int u = 0; u < 8; ++u) {
-            if (MODE == 0) {
-                off += 32u * 37u;                      // stays on bank `lane`
-                if (off >= words) off -= words;
-                atomicAnd(sm + off, ~(1u << (u + (it & 7))));
-            } else if (MODE == 1) {
-                x = x * 1664525u + 1013904223u;
-                atomicAnd(sm + (unsigned)(((unsigned long long)x * words) >> 32), ~(1u << u));
-            } else if (MODE == 2) {
-                off += 32u * 37u;
-                if (off >= words) off -= words;
-                acc += sm[off];
-            } else {
-                off += 128u * 9u;
-                if (off >= words) off -= words;
-                const uint4 v = reinterpret_cast<const uint4*>(sm)[(off & ~127u) / 4u + lane];
+            if (MODE == 0 || MODE == 1 || MODE == 4) atomicAnd(p + u * 4096, mask);
+            else if (MODE == 2) acc += p[u * 4096];
+            else {
+                const uint4 v = *reinterpret_cast<const uint4*>(p + u * 4096);
                 acc += v.x ^ v.y ^ v.z ^ v.w;
             }
         }
+        base = (base + (MODE == 3 ? 128u : 32u)) & 4095u;       // keeps every lane's bank
+        base += w0 & ((MODE == 3) ? 3u : 0u);                   // (no-op; keeps w0 live for MODE 3 alignment)
     }
     if (acc == 0x12345u) out[0] = acc;
 }
@@ -134,20 +136,22 @@ int main() {
         printf(", \"%s\": {\"thread_instr_per_s\": %.4e, \"per_clk_per_sm_at_nominal\": %.2f}", names[op], instr / (ms * 1e-3),
                instr / (ms * 1e-3) / clk / sms);
     }
-    const unsigned words = 48 * 1024;   // 192 KiB
+    const unsigned words = 9 * 4096;   // 144 KiB: 8 immediate offsets of 4096 words + a 4096-word window
     const size_t smem = words * 4;
     CK(cudaFuncSetAttribute(k_smem<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     CK(cudaFuncSetAttribute(k_smem<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     CK(cudaFuncSetAttribute(k_smem<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     CK(cudaFuncSetAttribute(k_smem<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    const char* sn[4] = {"atoms_and_conflict_free", "atoms_and_random_words", "lds32_conflict_free", "lds128"};
-    for (int mode = 0; mode < 4; ++mode) {
+    CK(cudaFuncSetAttribute(k_smem<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const char* sn[5] = {"atoms_and_conflict_free", "atoms_and_random_words", "lds32_conflict_free", "lds128", "atoms_and_single_bank"};
+    for (int mode = 0; mode < 5; ++mode) {
         auto go = [&]() {
             switch (mode) {
                 case 0: k_smem<0><<<sms, 1024, smem>>>(d, 777u, words); break;
                 case 1: k_smem<1><<<sms, 1024, smem>>>(d, 777u, words); break;
                 case 2: k_smem<2><<<sms, 1024, smem>>>(d, 777u, words); break;
-                default: k_smem<3><<<sms, 1024, smem>>>(d, 777u, words); break;
+                case 3: k_smem<3><<<sms, 1024, smem>>>(d, 777u, words); break;
+                default: k_smem<4><<<sms, 1024, smem>>>(d, 777u, words); break;
             }
         };
         const double ms = time_ms(go);
