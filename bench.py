@@ -516,9 +516,14 @@ def main():
                           "note": "byte-table moments: work is per bitmap word, not per prime; issue-bound (see profiles/ ncu summary)"},
             "k_bitmap_scan<compare>": {"ms": ms_compare, "mode": "interval pruning: only bracketing / n_max / window-edge blocks are walked"},
         }
-        if per.get("ms_compact", 0.0) or per.get("ms_count_scan", 0.0):
+        if per.get("ms_compact", 0.0):        # materialised path (PSS_SEARCH_PATH=materialised): u64 primes in HBM
+            ms_mat = max(per["ms_power_scan"] - ms_reduce - ms_compare, 0.0)
             kernels["k_scan_tile_counts"] = {"ms": per["ms_count_scan"]}
-            kernels["k_compact_lut"] = {"ms": per["ms_compact"]}
+            kernels["k_compact_lut"] = {"ms": per["ms_compact"], "hbm_GBps": (rate(bitmap_bytes + 8.0 * n_primes / world, per["ms_compact"]) or 0.0) / 1e9,
+                                        "hbm_peak_GBps": load_peaks()[0]}
+            kernels["k_power_tiles+k_scan_columns+k_power_walk"] = {
+                "ms": ms_mat, "hbm_GBps_read_once": (rate(8.0 * n_primes / world, ms_mat) or 0.0) / 1e9, "hbm_peak_GBps": load_peaks()[0],
+                "note": "8 B per prime read once by pass A; pass B re-reads only the tiles that can hold the target (interval pruning)"}
         dev_step = r["dev_ms"] / K
         d = {
             "value": n_primes * K / (r["dev_ms"] * 1e-3), "unit": "primes/s", "ms_per_step": dev_step,

@@ -561,6 +561,15 @@ int compact_resident(pss_handle* h, u64 cap) {
 }
 
 // ---- K2/K3 dispatch --------------------------------------------------------------------------------
+// column scan: one CTA per column; up to 8192 scan tiles the register-resident kernel (rows loaded once)
+void launch_scan_columns(pss_handle* h, u32 ncols, const u64* in, u64* out, u32 n, u64 stride) {
+    const u32 rows = (n + 31u) / 32u;
+    if ((rows + 15u) / 16u <= 16u) k_scan_columns_small<<<ncols, 512, 0, h->stream>>>(in, out, n, stride);
+    else k_scan_columns<<<ncols, 1024, 0, h->stream>>>(in, out, n, stride);
+}
+
+// pass A (tile sums) -> column scan -> pass B (walk; compare / prefix modes only).  Leaves the column totals on their way
+// to h->h_back->col_totals (TOTAL entries, deferred-carry lanes).
 template <int K, bool MULTI, int MODE, int ITEMS>
 int launch_scan_t(pss_handle* h, ScanParams& sp) {
     using Lay = Layout<K, MULTI>;
@@ -568,19 +577,28 @@ int launch_scan_t(pss_handle* h, ScanParams& sp) {
     const u64 n_tiles64 = (sp.count + TILE - 1) / TILE;
     if (n_tiles64 > 0x7FFFFFFFull) return fail(h, PSS_EINVAL, "range too large for one scan");
     sp.n_tiles = (u32)n_tiles64;
-    PSS_TRY(ensure(h, h->status, (size_t)sp.n_tiles * sizeof(u32)));
-    PSS_TRY(ensure(h, h->agg, (size_t)sp.n_tiles * Lay::TOTAL * sizeof(u32)));
-    PSS_TRY(ensure(h, h->incl, (size_t)sp.n_tiles * Lay::TOTAL * sizeof(u32)));
-    sp.tile_status = static_cast<u32*>(h->status.p);
-    sp.tile_agg = static_cast<u32*>(h->agg.p);
-    sp.tile_incl = static_cast<u32*>(h->incl.p);
-    CU_TRY(h, cudaMemsetAsync(sp.tile_status, 0, (size_t)sp.n_tiles * sizeof(u32), h->stream));
+    sp.col_stride = (u64)sp.n_tiles + 1;
+    const size_t col_bytes = (size_t)Lay::TOTAL * sp.col_stride * sizeof(u64);
+    PSS_TRY(ensure(h, h->agg, col_bytes));
+    PSS_TRY(ensure(h, h->incl, col_bytes));
+    sp.cols = static_cast<u64*>(h->agg.p);
+    sp.col_prefix = static_cast<const u64*>(h->incl.p);
     int occ = 1;
-    PSS_TRY(occ_of(h, k_power_scan<K, MULTI, MODE, ITEMS>, kScanThreads, 0, &occ));
-    const u32 grid = std::min<u32>(sp.n_tiles, (u32)(h->sm_count * occ));
-    k_power_scan<K, MULTI, MODE, ITEMS><<<grid, kScanThreads, 0, h->stream>>>(sp);
+    PSS_TRY(occ_of(h, k_power_tiles<K, MULTI, ITEMS>, kScanThreads, 0, &occ));
+    k_power_tiles<K, MULTI, ITEMS><<<std::min<u32>(sp.n_tiles, (u32)(h->sm_count * occ)), kScanThreads, 0, h->stream>>>(sp);
     CU_TRY(h, cudaGetLastError());
-    h->launches++;
+    launch_scan_columns(h, (u32)Lay::TOTAL, sp.cols, static_cast<u64*>(h->incl.p), sp.n_tiles, sp.col_stride);
+    CU_TRY(h, cudaGetLastError());
+    h->launches += 2;
+    if constexpr (MODE != kModeReduce) {
+        int occ_w = 1;
+        PSS_TRY(occ_of(h, k_power_walk<K, MULTI, MODE, ITEMS>, kScanThreads, 0, &occ_w));
+        k_power_walk<K, MULTI, MODE, ITEMS><<<std::min<u32>(sp.n_tiles, (u32)(h->sm_count * occ_w)), kScanThreads, 0, h->stream>>>(sp);
+        CU_TRY(h, cudaGetLastError());
+        h->launches++;
+    }
+    CU_TRY(h, cudaMemcpy2DAsync(h->h_back->col_totals, sizeof(u64), static_cast<const u64*>(h->incl.p) + sp.n_tiles, sp.col_stride * sizeof(u64),
+                                sizeof(u64), (size_t)Lay::TOTAL, cudaMemcpyDeviceToHost, h->stream));
     return PSS_OK;
 }
 
@@ -656,10 +674,10 @@ int run_scan(pss_handle* h, const u64* d_vals, u64 count, u64 n_first, const u32
     }
     MiscDev* dm = static_cast<MiscDev*>(h->misc.p);
     sp.carry_in = dm->carry;
-    sp.ticket = &dm->ticket;
     sp.error_flag = &dm->error_flag;
     sp.results = dm->results;
     sp.prefix_out = d_prefix_out;
+    sp.exhaustive = h->compare_exhaustive ? 1u : 0u;
 
     CU_TRY(h, cudaEventRecord(h->ev[4], h->stream));
     if (count > 0) {
@@ -672,7 +690,21 @@ int run_scan(pss_handle* h, const u64* d_vals, u64 count, u64 n_first, const u32
         CU_TRY(h, cudaEventRecord(h->ev[5], h->stream));
         CU_TRY(h, cudaMemcpyAsync(hm, dm, sizeof(MiscDev), cudaMemcpyDeviceToHost, h->stream));
         CU_TRY(h, cudaStreamSynchronize(h->stream));
-        if (hm->error_flag) return fail(h, PSS_EINTERNAL, "scan look-back watchdog fired (flag %u)", hm->error_flag);
+        if (hm->error_flag) return fail(h, PSS_EINTERNAL, "scan kernel reported error flag %u", hm->error_flag);
+        // S_k(last element) = carry-in + column totals (deferred-carry lanes, normalised here)
+        const u64* totals = h->h_back->col_totals;
+        u32 col = 0;
+        for (u32 j = 0; j < np; ++j) {
+            const u32 w = (u32)sum_limbs((int)expo_of(K, multi, j));
+            u64 c = 0;
+            for (u32 i = 0; i < (u32)PSS_LIMBS; ++i) {
+                const u64 v = (i < w) ? totals[col + i] : 0ull;
+                const u64 lo = (v & 0xFFFFFFFFull) + (c & 0xFFFFFFFFull) + hm->carry[j * PSS_LIMBS + i];
+                hm->results[j].final_sum[i] = (u32)lo;
+                c = (v >> 32) + (c >> 32) + (lo >> 32);
+            }
+            col += w;
+        }
     } else {
         CU_TRY(h, cudaEventRecord(h->ev[5], h->stream));
         CU_TRY(h, cudaStreamSynchronize(h->stream));
@@ -697,14 +729,6 @@ int launch_bscan_t(pss_handle* h, const BScanParams& bp) {
     CU_TRY(h, cudaGetLastError());
     h->launches++;
     return PSS_OK;
-}
-
-// column scan: one CTA per column; up to 8192 scan tiles the register-resident kernel (rows loaded once)
-template <class... A>
-void launch_scan_columns(pss_handle* h, u32 ncols, const u64* in, u64* out, u32 n, u64 stride) {
-    const u32 rows = (n + 31u) / 32u;
-    if ((rows + 15u) / 16u <= 16u) k_scan_columns_small<<<ncols, 512, 0, h->stream>>>(in, out, n, stride);
-    else k_scan_columns<<<ncols, 1024, 0, h->stream>>>(in, out, n, stride);
 }
 
 template <int K, bool MULTI>
@@ -1263,10 +1287,25 @@ int pss_primesum(pss_handle* h, uint64_t n, uint32_t power, uint32_t* limbs_out)
         return PSS_OK;
     }
     if (power > PSS_MAX_POWER) return fail(h, PSS_EINVAL, "power %u out of range 0..%d", power, PSS_MAX_POWER);
-    PSS_TRY(sieve_first_n(h, n));
-    pss_power_result r[PSS_MAX_POWER];
-    PSS_TRY(run_scan(h, static_cast<const u64*>(h->primes.p), n, 1, nullptr, power, false, kModeReduce, 0, 0, 0, nullptr, 0, nullptr, r));
-    memcpy(limbs_out, r[0].final_sum, PSS_LIMBS * sizeof(u32));
+    if (h->search_path == 1) {   // materialised route (kept as a cross-check): u64 primes + streaming reduction
+        PSS_TRY(sieve_first_n(h, n));
+        pss_power_result r[PSS_MAX_POWER];
+        PSS_TRY(run_scan(h, static_cast<const u64*>(h->primes.p), n, 1, nullptr, power, false, kModeReduce, 0, 0, 0, nullptr, 0, nullptr, r));
+        memcpy(limbs_out, r[0].final_sum, PSS_LIMBS * sizeof(u32));
+        return PSS_OK;
+    }
+    // fused route: sieve -> block sums -> truncating scan to the n-th prime; no u64 prime buffer (8 GB at n = 1e9) is written
+    const u64 bound = pss_nth_prime_upper(n) + 1;
+    if (bound > kMaxValue) return fail(h, PSS_EINVAL, "n = %llu needs primes beyond 2^%d", (unsigned long long)n, PSS_MAX_PRIME_BITS);
+    pss_search_args a;
+    memset(&a, 0, sizeof a);
+    a.n_min = n; a.n_max = n; a.power_max = power; a.cmp = 2;   // S < 0: never true; only S_k(n_max) is wanted
+    pss_search_result res;
+    memset(&res, 0, sizeof res);
+    PSS_TRY(sieve_range(h, 0, bound, true));
+    PSS_TRY(bitmap_reduce(h, power, false, true));
+    PSS_TRY(bitmap_compare(h, 1, nullptr, &a, &res));
+    memcpy(limbs_out, res.powers[0].final_sum, PSS_LIMBS * sizeof(u32));
     return PSS_OK;
 }
 

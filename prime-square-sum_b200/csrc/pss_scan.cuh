@@ -11,12 +11,10 @@
 // p^(e+1) = p^e * p as IMAD.WIDE.U32 + carry chains, no tensor cores (integer work, not a contraction).
 // With MULTI the powers 1..K share one chain (config "--max p:5").
 //
-// Scan: every thread owns ITEMS consecutive primes (blocked order, staged through padded shared memory
-// from coalesced loads).  pass 1: thread-local sums -> warp shuffle scan (carry-propagating adds) ->
-// warp totals in shared memory -> tile aggregate -> single-pass decoupled look-back across tiles
-// (status flag + aggregate / inclusive limb records; tiles are handed out by an atomic ticket so every
-// predecessor is resident) seeded with the slice's carry-in.  pass 2: every thread re-walks its primes
-// from its exact exclusive prefix, forming each S_k(n) and comparing it with the target limbs.
+// Scan (warp -> block -> grid): pass A k_power_tiles forms every tile's exact sums (streaming, registers only),
+// k_scan_columns (pss_bscan.cuh) scans them across tiles, pass B k_power_walk gives every thread its exact exclusive
+// prefix (carry-in + tile prefix + block scan + warp scan) and forms / compares every S_k(n) of the tiles that can
+// matter.  See the kernels below.
 #pragma once
 #include "pss_common.cuh"
 #include "../../include/pss_b200.h"
@@ -24,7 +22,6 @@
 namespace pss {
 
 constexpr int kScanThreads = 256;
-constexpr u32 kSpinLimit = 1u << 22;   // look-back watchdog (polls); sets error_flag instead of hanging
 
 enum ScanMode { kModeReduce = 0, kModeCompare = 1, kModePrefix = 2, kModeTri = 3 };
 
@@ -54,10 +51,10 @@ struct ScanParams {
     u32 n_tiles;
     u32 target[PSS_LIMBS];
     const u32* carry_in;   // NP * PSS_LIMBS limbs (device)
-    u32* tile_status;      // n_tiles, zeroed before launch
-    u32* tile_agg;         // n_tiles * TOTAL
-    u32* tile_incl;        // n_tiles * TOTAL
-    u32* ticket;           // zeroed before launch
+    u64* cols;             // pass A output: deferred-carry tile sums, column major (limb column c of tile t at cols[c * col_stride + t])
+    const u64* col_prefix; // their exclusive prefixes over tiles (k_scan_columns), n_tiles + 1 entries per column
+    u64 col_stride;
+    u32 exhaustive;        // compare mode: 1 = walk every tile, 0 = skip tiles whose sum interval cannot contain the target
     pss_power_result* results;  // NP records (device)
     u32* prefix_out;       // kModePrefix: count * PSS_LIMBS limbs
     u32* error_flag;
@@ -296,11 +293,74 @@ struct Pass2Fn {
     }
 };
 
-__device__ __forceinline__ u32 ld_volatile_u32(const u32* p) { return *reinterpret_cast<const volatile u32*>(p); }
-__device__ __forceinline__ void st_volatile_u32(u32* p, u32 v) { *reinterpret_cast<volatile u32*>(p) = v; }
+// ---- K2/K3 over materialised u64 primes: three launches, no CTA ever waits for another --------------------------------
+//   k_power_tiles     pass A: every CTA streams tiles of T * ITEMS primes (coalesced 16-byte loads straight into
+//                     registers: the order inside a tile is irrelevant for a sum), forms the tile's exact sums of p^k and
+//                     stores them as deferred-carry u64 columns (col c of tile t at cols[c * col_stride + t]).  Pure
+//                     streaming: 8 B per prime read once — the HBM-bound form of power_sum / slice sums.
+//   k_scan_columns    (pss_bscan.cuh) exclusive u64 prefix of every column = the grid level of the scan; entry n_tiles of
+//                     a column is the slice total.
+//   k_power_walk      pass B (compare / prefix modes): tile prefix = carry-in + normalised column prefix; the tile is
+//                     staged in blocked order, thread sums -> warp scan -> block scan give every thread its exact
+//                     exclusive prefix, then every S_k(n) is formed and compared / written.  With interval pruning
+//                     (default) a tile whose sum interval (S_before, S_after] cannot contain the target, that lies
+//                     entirely inside or outside the window and does not hold n_max, compares like its prefix and is not
+//                     even loaded (S_k is strictly increasing) — same argument and same results as the fused path.
+// This replaces the single-pass decoupled look-back of round 1 (6.1 ms per 1e9 primes: one warp per CTA chased
+// predecessor records while seven waited at a barrier).
+template <int K, bool MULTI, int ITEMS>
+__global__ void __launch_bounds__(kScanThreads) k_power_tiles(const __grid_constant__ ScanParams P) {
+    using Lay = Layout<K, MULTI>;
+    constexpr int TOTAL = Lay::TOTAL, T = kScanThreads, NWARP = T / 32, TILE = T * ITEMS;
+    static_assert(ITEMS % 2 == 0, "16-byte loads");
+    __shared__ u32 s_part[NWARP][TOTAL];
+    const u32 tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+    for (u32 tile = blockIdx.x; tile < P.n_tiles; tile += gridDim.x) {
+        const u64 base = (u64)tile * TILE;
+        u32 acc[TOTAL];
+#pragma unroll
+        for (int i = 0; i < TOTAL; ++i) acc[i] = 0;
+        AccFn<K, MULTI> fn{acc};
+        const bool full = base + TILE <= P.count;
+        if (full && ((reinterpret_cast<size_t>(P.primes + base) & 15u) == 0)) {
+            const ulonglong2* src = reinterpret_cast<const ulonglong2*>(P.primes + base);
+            ulonglong2 v[ITEMS / 2];
+#pragma unroll
+            for (int r = 0; r < ITEMS / 2; ++r) v[r] = __ldg(src + r * T + tid);     // all loads in flight, then the arithmetic
+#pragma unroll
+            for (int r = 0; r < ITEMS / 2; ++r) {
+                power_chain<K, MULTI>(v[r].x, fn);
+                power_chain<K, MULTI>(v[r].y, fn);
+            }
+        } else {
+#pragma unroll 4
+            for (int r = 0; r < ITEMS; ++r) {
+                const u64 g = base + (u64)r * T + tid;
+                if (g < P.count) power_chain<K, MULTI>(__ldg(P.primes + g), fn);
+            }
+        }
+#pragma unroll
+        for (int d = 16; d >= 1; d >>= 1) {
+            OpShflXorAdd op{acc, d};
+            for_each_power<0, Lay>(op);
+        }
+        if (lane == 0) {
+#pragma unroll
+            for (int i = 0; i < TOTAL; ++i) s_part[warp][i] = acc[i];
+        }
+        __syncthreads();
+        if (tid < (u32)TOTAL) {
+            u64 sum = 0;
+#pragma unroll
+            for (int w = 0; w < NWARP; ++w) sum += s_part[w][tid];
+            P.cols[(u64)tid * P.col_stride + tile] = sum;
+        }
+        __syncthreads();
+    }
+}
 
 template <int K, bool MULTI, int MODE, int ITEMS>
-__global__ void __launch_bounds__(kScanThreads) k_power_scan(const __grid_constant__ ScanParams P) {
+__global__ void __launch_bounds__(kScanThreads) k_power_walk(const __grid_constant__ ScanParams P) {
     using Lay = Layout<K, MULTI>;
     constexpr int TOTAL = Lay::TOTAL, NP = Lay::NP, T = kScanThreads, NWARP = T / 32, TILE = T * ITEMS;
     static_assert(NWARP <= 32 && (NWARP & (NWARP - 1)) == 0, "warp count must be a power of two");
@@ -308,16 +368,65 @@ __global__ void __launch_bounds__(kScanThreads) k_power_scan(const __grid_consta
     __shared__ u64 s_p[TILE + T];          // element e lives at e + e / ITEMS (bank-conflict padding)
     __shared__ u32 s_warp[NWARP][TOTAL];   // inclusive warp totals, then exclusive warp offsets
     __shared__ u32 s_excl[TOTAL];          // tile exclusive prefix (includes carry-in)
-    __shared__ u32 s_tile;
+    __shared__ u32 s_end[TOTAL];           // tile inclusive prefix
+    __shared__ int s_c0[NP], s_c1[NP];     // three-way compares of the two with the target
 
     const u32 tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
 
-    for (;;) {
-        if (tid == 0) s_tile = atomicAdd(P.ticket, 1u);
-        __syncthreads();
-        const u32 tile = s_tile;
-        if (tile >= P.n_tiles) break;
+    for (u32 tile = blockIdx.x; tile < P.n_tiles; tile += gridDim.x) {
         const u64 base = (u64)tile * TILE;
+        // ---- tile prefix / end from the scanned columns (thread j < NP normalises power j)
+        if (tid < (u32)NP) {
+            for (int which = 0; which < 2; ++which) {
+                u32* dst = which ? s_end : s_excl;
+                u64 c = 0;
+                const u32 off = (u32)lay_offset<K, MULTI>((int)tid), w = (u32)lay_width<K, MULTI>((int)tid);
+                for (u32 i = 0; i < w; ++i) {
+                    const u64 v = P.col_prefix[(u64)(off + i) * P.col_stride + tile + which];
+                    const u64 lo = (v & 0xFFFFFFFFull) + (c & 0xFFFFFFFFull) + P.carry_in[tid * PSS_LIMBS + i];
+                    dst[off + i] = (u32)lo;
+                    c = (v >> 32) + (c >> 32) + (lo >> 32);
+                }
+                int cmp = -1;
+                if (!((P.target_over_mask >> tid) & 1u)) {
+                    cmp = 0;
+                    for (u32 i = 0; i < w; ++i)
+                        if (dst[off + i] != P.target[i]) cmp = (dst[off + i] < P.target[i]) ? -1 : 1;
+                }
+                (which ? s_c1 : s_c0)[tid] = cmp;
+            }
+        }
+        __syncthreads();
+        const u32 tcnt = (u32)min((u64)TILE, P.count - base);
+        const u64 t_n0 = P.n_first + base;               // global index of the tile's first prime
+        if constexpr (MODE == kModeCompare) {
+            // ---- interval pruning at tile level (uniform over the CTA)
+            if (!P.exhaustive) {
+                const u64 t_last = t_n0 + tcnt - 1;
+                const bool inside = t_n0 >= P.n_min && t_last <= P.n_max, outside = t_last < P.n_min || t_n0 > P.n_max;
+                bool simple = inside || outside;
+                bool bracket = false;
+#pragma unroll
+                for (int jj = 0; jj < NP; ++jj) bracket = bracket || (s_c0[jj] < 0 && s_c1[jj] >= 0);
+                if (simple && !bracket) {
+                    if (tid == 0 && inside) {
+#pragma unroll
+                        for (int jj = 0; jj < NP; ++jj) {
+                            const bool below = s_c0[jj] < 0;      // every S of the tile compares like the tile's prefix ...
+                            const bool hit = below ? (P.cmp_mask & 1u) : (P.cmp_mask & 4u);   // ... except that "==" cannot occur
+                            if (hit) {
+                                pss_power_result* r = P.results + jj;
+                                atomicAdd(reinterpret_cast<unsigned long long*>(&r->match_count), (unsigned long long)tcnt);
+                                atomicMin(reinterpret_cast<unsigned long long*>(&r->first_match_n), (unsigned long long)t_n0);
+                                atomicMax(reinterpret_cast<unsigned long long*>(&r->last_match_n), (unsigned long long)t_last);
+                            }
+                        }
+                    }
+                    __syncthreads();      // s_excl / s_c0 are rewritten by the next tile
+                    continue;
+                }
+            }
+        }
 
         // ---- coalesced load -> padded shared memory (blocked order for the owner threads)
 #pragma unroll
@@ -354,9 +463,7 @@ __global__ void __launch_bounds__(kScanThreads) k_power_scan(const __grid_consta
             run[i] = lane ? up : 0u;
         }
         __syncthreads();
-
-        if (warp == 0) {
-            // scan of the warp totals
+        if (warp == 0) {   // scan of the warp totals -> exclusive warp offsets
             u32 wi[TOTAL];
 #pragma unroll
             for (int i = 0; i < TOTAL; ++i) wi[i] = (lane < NWARP) ? s_warp[lane][i] : 0u;
@@ -365,149 +472,59 @@ __global__ void __launch_bounds__(kScanThreads) k_power_scan(const __grid_consta
                 OpShflUpAdd op{wi, d, lane >= (u32)d};
                 for_each_power<0, Lay>(op);
             }
-            u32 agg[TOTAL];
 #pragma unroll
             for (int i = 0; i < TOTAL; ++i) {
-                agg[i] = __shfl_sync(0xFFFFFFFFu, wi[i], NWARP - 1);
                 const u32 up = __shfl_up_sync(0xFFFFFFFFu, wi[i], 1);
                 if (lane < NWARP) s_warp[lane][i] = lane ? up : 0u;
-            }
-            if (tile > 0 && lane == 0) {
-                u32* a = P.tile_agg + (u64)tile * TOTAL;
-#pragma unroll
-                for (int i = 0; i < TOTAL; ++i) a[i] = agg[i];
-                __threadfence();
-                st_volatile_u32(P.tile_status + tile, 1u);
-            }
-            // ---- decoupled look-back: 32 predecessors per window
-            u32 excl[TOTAL];
-#pragma unroll
-            for (int i = 0; i < TOTAL; ++i) excl[i] = 0;
-            long long j = (long long)tile - 1;
-            for (;;) {
-                const long long idx = j - (long long)lane;
-                u32 st = 2u;
-                if (idx >= 0) {
-                    u32 spins = 0;
-                    while ((st = ld_volatile_u32(P.tile_status + idx)) == 0u) {
-                        if (++spins > kSpinLimit) {
-                            atomicExch(P.error_flag, 1u);
-                            st = 2u;
-                            break;
-                        }
-                        if (spins > 16) __nanosleep(40);
-                    }
-                }
-                const u32 incl_mask = __ballot_sync(0xFFFFFFFFu, st == 2u);
-                const int first = incl_mask ? (__ffs(incl_mask) - 1) : 32;
-                __threadfence();
-                u32 val[TOTAL];
-#pragma unroll
-                for (int i = 0; i < TOTAL; ++i) val[i] = 0;
-                if ((int)lane < first) {
-                    const u32* a = P.tile_agg + (u64)idx * TOTAL;
-#pragma unroll
-                    for (int i = 0; i < TOTAL; ++i) val[i] = ld_volatile_u32(a + i);
-                } else if ((int)lane == first) {
-                    if (idx >= 0) {
-                        const u32* a = P.tile_incl + (u64)idx * TOTAL;
-#pragma unroll
-                        for (int i = 0; i < TOTAL; ++i) val[i] = ld_volatile_u32(a + i);
-                    } else if (idx == -1) {
-                        // carry-in of the slice = "inclusive prefix of tile -1"
-#pragma unroll
-                        for (int jj = 0; jj < NP; ++jj)
-#pragma unroll
-                            for (int i = 0; i < PSS_LIMBS; ++i)
-                                if (i < Lay::width(jj)) val[Lay::offset(jj) + i] = P.carry_in[jj * PSS_LIMBS + i];
-                    }
-                }
-#pragma unroll
-                for (int d = 16; d >= 1; d >>= 1) {
-                    OpShflXorAdd op{val, d};
-                    for_each_power<0, Lay>(op);
-                }
-                {
-                    OpAdd op{excl, val};
-                    for_each_power<0, Lay>(op);
-                }
-                if (incl_mask) break;
-                j -= 32;
-            }
-            // inclusive prefix of this tile
-            {
-                OpAdd op{agg, excl};
-                for_each_power<0, Lay>(op);
-            }
-            if (lane == 0) {
-                u32* a = P.tile_incl + (u64)tile * TOTAL;
-#pragma unroll
-                for (int i = 0; i < TOTAL; ++i) {
-                    a[i] = agg[i];
-                    s_excl[i] = excl[i];
-                }
-                __threadfence();
-                st_volatile_u32(P.tile_status + tile, 2u);
-                if (tile == P.n_tiles - 1) {
-#pragma unroll
-                    for (int jj = 0; jj < NP; ++jj)
-#pragma unroll
-                        for (int i = 0; i < PSS_LIMBS; ++i)
-                            P.results[jj].final_sum[i] = (i < Lay::width(jj)) ? agg[Lay::offset(jj) + i] : 0u;
-                }
             }
         }
         __syncthreads();
 
-        if constexpr (MODE != kModeReduce) {
-            // ---- pass 2: exact exclusive prefix of this thread, then every S_k(n) formed and compared
-            {
-                OpAdd op1{run, s_excl};
-                for_each_power<0, Lay>(op1);
-                OpAdd op2{run, s_warp[warp]};
-                for_each_power<0, Lay>(op2);
-            }
-            int prevc[NP];
-            u32 mcount[NP], mfirst[NP], mlast[NP];
+        // ---- pass 2: exact exclusive prefix of this thread, then every S_k(n) formed and compared / written
+        {
+            OpAdd op1{run, s_excl};
+            for_each_power<0, Lay>(op1);
+            OpAdd op2{run, s_warp[warp]};
+            for_each_power<0, Lay>(op2);
+        }
+        int prevc[NP];
+        u32 mcount[NP], mfirst[NP], mlast[NP];
+#pragma unroll
+        for (int jj = 0; jj < NP; ++jj) {
+            mcount[jj] = 0;
+            mfirst[jj] = 0xFFFFFFFFu;
+            mlast[jj] = 0;
+            prevc[jj] = 0;
+        }
+        if constexpr (MODE == kModeCompare) {
+            OpCmpInit op{run, P.target, P.target_over_mask, prevc};
+            for_each_power<0, Lay>(op);
+        }
+        Pass2Fn<K, MULTI, MODE> fn{run, &P, prevc, mcount, mfirst, mlast, t_n0, 0, 0, 0, false};
+#pragma unroll 2
+        for (int i = 0; i < ITEMS; ++i) {
+            const u64 p = s_p[tid * (ITEMS + 1) + i];
+            if (p == 0) continue;   // padding past the end of the range
+            const u32 li = tid * ITEMS + i;
+            fn.local_idx = li;
+            fn.elem = base + li;
+            fn.p = p;
+            const u64 n = t_n0 + li;
+            fn.in_window = (n >= P.n_min) && (n <= P.n_max);
+            power_chain<K, MULTI>(p, fn);
+        }
+        if constexpr (MODE == kModeCompare) {
 #pragma unroll
             for (int jj = 0; jj < NP; ++jj) {
-                mcount[jj] = 0;
-                mfirst[jj] = 0xFFFFFFFFu;
-                mlast[jj] = 0;
-                prevc[jj] = 0;
-            }
-            if constexpr (MODE == kModeCompare) {
-                OpCmpInit op{run, P.target, P.target_over_mask, prevc};
-                for_each_power<0, Lay>(op);
-            }
-            Pass2Fn<K, MULTI, MODE> fn{run, &P, prevc, mcount, mfirst, mlast, P.n_first + base, 0, 0, 0, false};
-#pragma unroll 2
-            for (int i = 0; i < ITEMS; ++i) {
-                const u64 p = s_p[tid * (ITEMS + 1) + i];
-                if (p == 0) continue;   // padding past the end of the range
-                const u32 li = tid * ITEMS + i;
-                fn.local_idx = li;
-                fn.elem = base + li;
-                fn.p = p;
-                const u64 n = P.n_first + base + li;
-                fn.in_window = (n >= P.n_min) && (n <= P.n_max);
-                power_chain<K, MULTI>(p, fn);
-            }
-            if constexpr (MODE == kModeCompare) {
-#pragma unroll
-                for (int jj = 0; jj < NP; ++jj) {
-                    if (__any_sync(0xFFFFFFFFu, mcount[jj] != 0)) {
-                        const u32 c = __reduce_add_sync(0xFFFFFFFFu, mcount[jj]);
-                        const u32 f = __reduce_min_sync(0xFFFFFFFFu, mfirst[jj]);
-                        const u32 l = __reduce_max_sync(0xFFFFFFFFu, mlast[jj]);
-                        if (lane == 0) {
-                            pss_power_result* r = P.results + jj;
-                            atomicAdd(reinterpret_cast<unsigned long long*>(&r->match_count), (unsigned long long)c);
-                            atomicMin(reinterpret_cast<unsigned long long*>(&r->first_match_n),
-                                      (unsigned long long)(P.n_first + base + f));
-                            atomicMax(reinterpret_cast<unsigned long long*>(&r->last_match_n),
-                                      (unsigned long long)(P.n_first + base + l - 1));
-                        }
+                if (__any_sync(0xFFFFFFFFu, mcount[jj] != 0)) {
+                    const u32 c = __reduce_add_sync(0xFFFFFFFFu, mcount[jj]);
+                    const u32 f = __reduce_min_sync(0xFFFFFFFFu, mfirst[jj]);
+                    const u32 l = __reduce_max_sync(0xFFFFFFFFu, mlast[jj]);
+                    if (lane == 0) {
+                        pss_power_result* r = P.results + jj;
+                        atomicAdd(reinterpret_cast<unsigned long long*>(&r->match_count), (unsigned long long)c);
+                        atomicMin(reinterpret_cast<unsigned long long*>(&r->first_match_n), (unsigned long long)(t_n0 + f));
+                        atomicMax(reinterpret_cast<unsigned long long*>(&r->last_match_n), (unsigned long long)(t_n0 + l - 1));
                     }
                 }
             }
