@@ -67,7 +67,7 @@ WORKLOADS = {
 }
 EXTRA = ["C5", "C4_k3", "C4_k4", "C4_k5", "C2"]
 IMAD_PER_PRIME = {1: 0, 2: 4, 3: 10, 4: 18, 5: 28}   # IMAD.WIDE of the per-prime power chain
-MISC_BYTES = 1936   # sizeof(MiscDev): ticket/flag + 8 result records + carry limbs, one H2D and one D2H per scan
+MISC_BYTES = 2016   # sizeof(MiscDev): ticket/flag + 8 result records + carry limbs + timeline stamps, one H2D and one D2H per scan
 SMS = 148
 
 
@@ -366,6 +366,8 @@ def main():
     h = _lib.default_handle()
     target = TRISUM_666
     KKEYS = ["ms_sieve", "ms_count_scan", "ms_compact", "ms_power_scan", "ms_bitmap_reduce", "ms_bitmap_compare"]
+    TKEYS = ["ms_span", "ms_sieve", "ms_bitmap_reduce", "ms_peer_pre_publish", "ms_peer_wait_totals", "ms_peer_compare_region",
+             "ms_bitmap_compare", "ms_peer_wait_results"]     # per-rank timeline of a multi-GPU query (pss_stats)
 
     def barrier():
         torch.cuda.synchronize()
@@ -395,7 +397,7 @@ def main():
 
     def timed_steps(step, n_steps):
         """K steps bracketed by barrier + synchronize; per-step device span from the library's CUDA events"""
-        dev, acc = [], dict.fromkeys(KKEYS, 0.0)
+        dev, acc = [], dict.fromkeys(KKEYS + [k for k in TKEYS if k not in KKEYS], 0.0)
         launches = 0
         barrier()
         t_start = time.perf_counter()
@@ -406,12 +408,27 @@ def main():
             # whole-query span on the launch stream (gaps and, at N > 1, the waits on the peers' publishes included);
             # paths with a host synchronisation in the middle fall back to the sum of the kernels' event times
             dev.append(s["ms_span"] if s.get("ms_span", 0.0) > 0.0 else s["ms_total_device"])
-            for k in KKEYS:
-                acc[k] += s[k]
+            for k in acc:
+                acc[k] += s.get(k, 0.0)
             launches += s["launches"]
         barrier()
         wall = time.perf_counter() - t_start
         return sum(dev), wall * 1e3, acc, launches, o
+
+    def gather_timeline(kern, wall_ms):
+        """every rank's per-step averages of the query timeline (rank order); None at N = 1"""
+        if world == 1:
+            return None
+        t = torch.tensor([kern.get(k, 0.0) / args.steps for k in TKEYS] + [wall_ms / args.steps], dtype=torch.float64, device="cuda")
+        parts = [torch.empty_like(t) for _ in range(world)]
+        dist.all_gather(parts, t)
+        rows = []
+        for r, p in enumerate(parts):
+            v = p.cpu().tolist()
+            row = {"rank": r}
+            row.update({k: round(x, 4) for k, x in zip(TKEYS + ["ms_wall_e2e"], v)})
+            rows.append(row)
+        return rows
 
     def reduce_ranks(dev_ms, wall_ms, kern, launches):
         if world == 1:
@@ -424,6 +441,9 @@ def main():
         return float(tmax[0]), float(tmax[1]), {k: float(tmax[2 + i]) for i, k in enumerate(KKEYS)}, int(tsum[2 + len(KKEYS)])
 
     def run_workload(name, sampler=None):
+        """warm-up, then the timed region (K steps; per-kernel events at the library's default level 1 = around the sieve
+        only, so the region is not stretched by instrumentation), then K more steps with events around EVERY kernel for
+        the per-kernel table and the multi-GPU timeline"""
         step = make_step(name)
         for _ in range(args.warmup):
             out = step()
@@ -433,8 +453,18 @@ def main():
         dev_ms, wall_ms, kern, launches, out = timed_steps(step, args.steps)
         clocks = sampler.stop() if sampler is not None else None
         check(name, out)
+        h.set_kernel_events(2)
+        try:
+            step()
+            _, wall_d, kern_d, _, out = timed_steps(step, args.steps)
+        finally:
+            h.set_kernel_events(1)
+        check(name, out)
+        timeline = gather_timeline(kern_d, wall_d)
+        _, _, kern_d, _ = reduce_ranks(0.0, 0.0, kern_d, 0)
         dev_ms, wall_ms, kern, launches = reduce_ranks(dev_ms, wall_ms, kern, launches)
-        return dict(dev_ms=dev_ms, wall_ms=wall_ms, kern=kern, launches=launches, clocks=clocks)
+        kern_d["ms_sieve_timed_region"] = kern["ms_sieve"]
+        return dict(dev_ms=dev_ms, wall_ms=wall_ms, kern=kern_d, launches=launches, clocks=clocks, timeline=timeline)
 
     # ---------------------------------------------------------------- N > 1: rank-boundary verification (warm-up)
     verified_multi = None
@@ -451,6 +481,7 @@ def main():
     exhaustive = None
     if not args.no_exhaustive and main_name != "C2":
         h.set_compare_mode(True)
+        h.set_kernel_events(2)
         try:
             step = make_step(main_name)
             step()
@@ -460,6 +491,7 @@ def main():
             exhaustive = (ex_dev, ex_wall, ex_kern["ms_bitmap_compare"] / args.steps)
         finally:
             h.set_compare_mode(False)
+            h.set_kernel_events(1)
 
     extras = {}
     if not args.no_extra:
@@ -492,6 +524,7 @@ def main():
         n_primes = w["n_max"]
         hi = (w["p_n"] + 1) if world > 1 else None
         per = {k: v / K for k, v in r["kern"].items()}
+        per["ms_sieve"] = per.pop("ms_sieve_timed_region", per["ms_sieve"])    # the dominant kernel: timed inside the timed region
         # sieve bound: the proven p_n upper bound the library sieves to (single GPU) / the slices (multi GPU)
         sieve_hi = h.nth_prime_upper(n_primes) + 1
         if world > 1:
@@ -524,11 +557,14 @@ def main():
             kernels["k_power_tiles+k_scan_columns+k_power_walk"] = {
                 "ms": ms_mat, "hbm_GBps_read_once": (rate(8.0 * n_primes / world, ms_mat) or 0.0) / 1e9, "hbm_peak_GBps": load_peaks()[0],
                 "note": "8 B per prime read once by pass A; pass B re-reads only the tiles that can hold the target (interval pruning)"}
-        dev_step = r["dev_ms"] / K
+        dev_ms_total = r["dev_ms"] if r["dev_ms"] > 0 else r["wall_ms"]      # PSS_KERNEL_EVENTS=0 on a multi-call path: wall clock
+        dev_step = dev_ms_total / K
         d = {
-            "value": n_primes * K / (r["dev_ms"] * 1e-3), "unit": "primes/s", "ms_per_step": dev_step,
+            "value": n_primes * K / (dev_ms_total * 1e-3), "unit": "primes/s", "ms_per_step": dev_step,
             "e2e": {"value": n_primes * K / (r["wall_ms"] * 1e-3), "unit": "primes/s", "ms_per_step": r["wall_ms"] / K},
             "gpu_launches": r["launches"], "kernels": kernels, "config": workload_config(name, world),
+            "kernel_timing": "k_sieve: CUDA events inside the timed region; the other kernels: the same steps repeated with events "
+                             "around every kernel (pss_set_kernel_events(2)), which stretches a query by ~20 us",
             "crossoffs_per_prime": x_alg * (world if world > 1 else 1) / n_primes,
             "verified": "final sums, p_n and no-match/bracket checked against tests/golden (bit-exact)" if name != "C2"
                         else "tri hits == [(m=36,n=7),(m=3169,n=86)] (reference find_matches answer)",
@@ -580,6 +616,14 @@ def main():
     }
     if verified_multi is not None:
         line["verified_multi"] = verified_multi
+    if res.get("timeline"):
+        line["timeline_per_rank"] = {
+            "rows": res["timeline"],
+            "legend": "per-step averages on each rank (ms): ms_span = first launch -> every rank's outcome gathered; "
+                      "ms_peer_pre_publish = chain start -> slice totals published (ms_sieve + ms_bitmap_reduce + launch gaps); "
+                      "ms_peer_wait_totals = spin in k_peer_gather on the lower ranks; ms_peer_compare_region = gather exit -> outcome "
+                      "published (ms_bitmap_compare + gaps); ms_peer_wait_results = spin in k_peer_gather_results on all ranks "
+                      "(= the other ranks' lateness: launch skew + slower slices); ms_wall_e2e - ms_span = host side of the call"}
     if exhaustive:
         line["exhaustive_compare"] = {
             "value": n_primes * K / (exhaustive[0] * 1e-3), "unit": "primes/s", "ms_per_step": exhaustive[0] / K,

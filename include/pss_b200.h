@@ -37,7 +37,7 @@
 extern "C" {
 #endif
 
-#define PSS_ABI_VERSION 2
+#define PSS_ABI_VERSION 3
 #define PSS_LIMBS 12        /* 32-bit limbs per big integer at the boundary (384 bit) */
 #define PSS_MAX_POWER 8     /* highest exponent k supported by the device kernels */
 #define PSS_MAX_PRIME_BITS 40 /* sieve value bound: primes < 2^40 */
@@ -79,7 +79,7 @@ typedef struct pss_stats {
     double ms_sieve;        /* K1a segmented wheel-30 sieve (CUDA events, this call) */
     double ms_count_scan;   /* K1b exclusive scan of chunk counts */
     double ms_compact;      /* K1c ballot/popc compaction into the u64 prime buffer */
-    double ms_power_scan;   /* K2+K3 power + decoupled look-back scan + compare */
+    double ms_power_scan;   /* K2+K3: tile sums + column scan + walk/compare (materialised path), or the fused bitmap passes */
     double ms_total_device; /* first kernel start -> last kernel end */
     uint64_t primes;        /* primes power-summed */
     uint64_t sieve_lo, sieve_hi; /* value range sieved */
@@ -88,6 +88,11 @@ typedef struct pss_stats {
     double ms_bitmap_compare; /* fused path: re-walk with exact prefixes + compare (part of ms_power_scan) */
     double ms_span;           /* pss_search, fused path: first launch -> last kernel end of the query on the launch stream,
                                  gaps between kernels included (0 for multi-call sequences) */
+    /* pss_peer_search: where ms_span went, from the exchange kernels' own %globaltimer stamps */
+    double ms_peer_pre_publish;    /* first launch -> this rank's slice totals published (sieve + block sums + column scan + gaps) */
+    double ms_peer_wait_totals;    /* k_peer_gather: waiting for the lower ranks' slice totals */
+    double ms_peer_compare_region; /* totals gathered -> outcome record published (compare kernel + launch gaps) */
+    double ms_peer_wait_results;   /* k_peer_gather_results: waiting for every rank's outcome record */
 } pss_stats;
 
 /* ---- fused search: replaces the O(n^2) host loop utils/grammar.py:937-999 (find_matches) over
@@ -152,6 +157,17 @@ int pss_search_targets(pss_handle* h, const pss_search_args* args, uint32_t n_ta
  * total number found.  Replaces the m x n double loop of utils/grammar.py:937-999 for this RHS. */
 int pss_search_tri(pss_handle* h, uint64_t n_min, uint64_t n_max, uint32_t power, uint64_t m_min, uint64_t m_max,
                    uint64_t* pairs_out, uint32_t cap, uint32_t* count, pss_stats* stats);
+
+/* sieve variant (the reference's --algorithm sieve:<variant>, utils/sieve.py:56-62,391-437): 0 (default) = segmented
+ * bit-packed wheel-30 sieve (k_sieve); 1 = "individual", per-candidate trial division by the primes up to sqrt(v)
+ * (utils/sieve.py:330-387 _individual_sieve) as a device kernel with the same outputs — a selectable cross-check of the
+ * sieve with the reference's O(n sqrt(n) / log n) complexity, not a fast path. */
+int pss_set_sieve_variant(pss_handle* h, int variant);
+
+/* per-kernel CUDA timing events of a query: 0 = none, 1 (default) = around the sieve only (the dominant kernel:
+ * pss_stats.ms_sieve), 2 = around every kernel (all pss_stats.ms_* fields).  pss_stats.ms_span (first launch -> end of the
+ * last kernel) is always measured.  Each event costs ~2 us of stream time and ~2 us of host time per query. */
+int pss_set_kernel_events(pss_handle* h, int level);
 
 /* search path selection: 0 (default) = fused, K2/K3 read the sieve's bit-packed output directly;
  * 1 = materialised, K1c compacts u64 primes first (the layout generate_primes / slice_* serve). */

@@ -51,12 +51,55 @@ struct MiscDev {   // small device-side block, one H2D / D2H per scan
     u32 carry[PSS_MAX_POWER * PSS_LIMBS];
     u64 last_prime;
     u64 n_first;     // peer path: global index of the slice's first prime (written by k_peer_gather)
+    u64 tl[8];       // peer path: globaltimer stamps of the exchange kernels (pss_peer.cuh: stamp)
 };
 
 struct HostBack {   // pinned: asynchronous D2H targets of one query
     u64 sv_total;
     u64 col_totals[1 + PSS_MAX_POWER * PSS_LIMBS];
 };
+
+// A query chain keeps the copy engine out of its critical path: a copy between two kernels costs ~8 us of stream latency
+// (profiles/r02: per-rank timeline), a dependent kernel ~2 us.  So the MiscDev block is INITIALISED by a one-CTA kernel from
+// by-value arguments instead of an H2D copy, and the query's results (MiscDev block, column totals, peer outcome records)
+// are stored by a one-CTA kernel straight into mapped pinned host memory instead of two or three D2H copies.
+struct MiscInit {
+    u32 np;
+    u32 power[PSS_MAX_POWER];
+    u32 carry[PSS_MAX_POWER * PSS_LIMBS];
+};
+__global__ void k_init_misc(MiscDev* dm, const MiscInit in) {
+    MiscDev* d = dm + blockIdx.x;
+    u32* w = reinterpret_cast<u32*>(d);
+    for (u32 i = threadIdx.x; i < sizeof(MiscDev) / 4; i += blockDim.x) w[i] = 0u;
+    __syncthreads();
+    if (threadIdx.x < in.np) {
+        d->results[threadIdx.x].power = in.power[threadIdx.x];
+        d->results[threadIdx.x].first_match_n = ~0ull;
+    }
+    for (u32 i = threadIdx.x; i < PSS_MAX_POWER * PSS_LIMBS; i += blockDim.x) d->carry[i] = in.carry[i];
+}
+struct ExportParams {
+    const MiscDev* dm;       // device block ...
+    MiscDev* hm;             // ... -> mapped pinned host block
+    const u64* col_prefix;   // column totals at col_prefix[c * col_stride + n_tiles], c < ncols (ncols == 0: none)
+    u64 col_stride;
+    u32 n_tiles, ncols;
+    u64* totals_host;
+    const PeerResult* peer;  // peer outcome records (world == 0: none)
+    PeerResult* peer_host;
+    u32 world;
+};
+__global__ void k_export(const ExportParams P) {
+    const u32* src = reinterpret_cast<const u32*>(P.dm);
+    u32* dst = reinterpret_cast<u32*>(P.hm);
+    for (u32 i = threadIdx.x; i < sizeof(MiscDev) / 4; i += blockDim.x) dst[i] = src[i];
+    for (u32 c = threadIdx.x; c < P.ncols; c += blockDim.x) P.totals_host[c] = P.col_prefix[(u64)c * P.col_stride + P.n_tiles];
+    const u64* ps = reinterpret_cast<const u64*>(P.peer);
+    u64* pd = reinterpret_cast<u64*>(P.peer_host);
+    for (u32 i = threadIdx.x; i < P.world * (u32)(sizeof(PeerResult) / 8); i += blockDim.x) pd[i] = ps[i];
+    __threadfence_system();
+}
 
 }  // namespace
 
@@ -73,6 +116,8 @@ struct pss_handle {
     u32 sieve_threads = 1024;
     u32 n_pat = 4;
     u32 warp_wide_div = 104;    // p < tile_bytes / div -> dense (one warp per prime, skewed conflict-free lanes), else one lane per prime
+    int kernel_events = 1;     // PSS_KERNEL_EVENTS
+    int sieve_variant = 0;     // 0: segmented wheel-30 sieve (k_sieve), 1: "individual" per-candidate trial division (k_individual)
     int search_path = 0;       // 0: fused (scan straight from the bitmap), 1: materialised u64 primes
     int compare_exhaustive = 0;  // 1: the compare pass walks every prime; 0: interval pruning (PSS_COMPARE_EXHAUSTIVE / pss_set_compare_mode)
     int reduce_moments = 2;    // block sums from moments (k = 2: per-byte tables; other k <= 5: per-prime small moments);
@@ -102,6 +147,8 @@ struct pss_handle {
     u32 occ_cache_threads = 0, occ_cache_tile = 0;
     bool sv_total_from_reduce = false;   // deferred sieve: no tile-count scan, the total comes from the block sums
     bool bs_pending = false;   // reduce enqueued, column totals not read back yet (reduce_finish)
+    bool bs_totals_copied = false;   // ... and their D2H copy is enqueued (copy_totals)
+    bool misc_uploaded = false;      // the query's MiscDev block is already on its way to the device (prepare_misc)
 
     // resident primes
     DevBuf primes;
@@ -120,8 +167,11 @@ struct pss_handle {
     DevBuf status, agg, incl, misc, prefix_out, user_vals, tri_buf, misc_multi;
     MiscDev* h_misc_multi = nullptr;   // pinned, h_misc_multi_cap blocks (pss_search_targets)
     size_t h_misc_multi_cap = 0;
-    MiscDev* h_misc = nullptr;   // pinned
-    HostBack* h_back = nullptr;  // pinned
+    MiscDev* h_misc = nullptr;   // pinned + mapped (k_export stores into it)
+    HostBack* h_back = nullptr;  // pinned + mapped
+    MiscDev* h_misc_dev = nullptr;    // device-side addresses of the two
+    HostBack* h_back_dev = nullptr;
+    PeerResult* h_peer_results_dev = nullptr;
 
     // peer-memory exchange (pss_peer_*): own mailbox, mapped mailboxes of all ranks, query epoch
     PeerBox* box_local = nullptr;
@@ -134,7 +184,7 @@ struct pss_handle {
     // attribute belong to the handle's device (a process may hold handles on several GPUs)
     std::unordered_map<const void*, int> occ_map;
 
-    cudaEvent_t ev[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t ev[10] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};   // [8], [9]: first / last launch of a query chain
     u64 launches = 0;
     pss_stats acc = {};          // accumulated per-kernel device time since pss_stats_reset
 };
@@ -205,7 +255,16 @@ u64 isqrt_u64(u64 x) {
     return r;
 }
 
+// Timing events of a query.  The span events ([8] first launch, [9] end of the last kernel) are always recorded; the
+// per-kernel events ([0..7]) cost ~2 us of stream time and ~2 us of host time EACH (A/B in profiles/r02: a C3 query is
+// 19 us shorter on the device and 37 us shorter end to end without them, a C4 query 25 % shorter), so they are levelled:
+//   0  none        1 (default)  the sieve only ([0], [1]: the dominant kernel of every query)        2  every kernel
+// pss_set_kernel_events / PSS_KERNEL_EVENTS select the level; times of events that were not recorded read 0.
+bool ev_on(const pss_handle* h, int i) { return i >= 8 || h->kernel_events >= 2 || (h->kernel_events == 1 && i <= 1); }
+cudaError_t mark(pss_handle* h, int i) { return ev_on(h, i) ? cudaEventRecord(h->ev[i], h->stream) : cudaSuccess; }
+
 double ev_ms(pss_handle* h, int a, int b) {
+    if (!ev_on(h, a) || !ev_on(h, b)) return 0.0;
     float ms = 0;
     if (cudaEventElapsedTime(&ms, h->ev[a], h->ev[b]) != cudaSuccess) {
         cudaGetLastError();
@@ -456,14 +515,22 @@ int sieve_range(pss_handle* h, u64 lo, u64 hi, bool defer_sync = false) {
     sp.tile_counts = static_cast<u32*>(h->tile_counts.p);
     sp.prof = static_cast<unsigned long long*>(h->sieve_prof.p);
 
-    CU_TRY(h, cudaEventRecord(h->ev[0], h->stream));
-    switch (h->sieve_threads) {
-        case 256: PSS_TRY(launch_sieve<256>(h, sp, std::min(n_tiles, grid_max))); break;
-        case 512: PSS_TRY(launch_sieve<512>(h, sp, std::min(n_tiles, grid_max))); break;
-        case 768: PSS_TRY(launch_sieve<768>(h, sp, std::min(n_tiles, grid_max))); break;
-        default: PSS_TRY(launch_sieve<1024>(h, sp, std::min(n_tiles, grid_max))); break;
+    CU_TRY(h, mark(h, 0));
+    if (h->sieve_variant == 1) {   // per-candidate trial division (selectable cross-check; same outputs as the sieve)
+        CU_TRY(h, cudaMemsetAsync(sp.tile_counts, 0, (size_t)n_tiles * sizeof(u32), h->stream));
+        const u64 n_chunks = (u64)n_tiles * cpt;
+        k_individual<<<(u32)std::min<u64>(n_chunks, (u64)h->sm_count * 8), kChunkWords, 0, h->stream>>>(sp);
+        CU_TRY(h, cudaGetLastError());
+        h->launches++;
+    } else {
+        switch (h->sieve_threads) {
+            case 256: PSS_TRY(launch_sieve<256>(h, sp, std::min(n_tiles, grid_max))); break;
+            case 512: PSS_TRY(launch_sieve<512>(h, sp, std::min(n_tiles, grid_max))); break;
+            case 768: PSS_TRY(launch_sieve<768>(h, sp, std::min(n_tiles, grid_max))); break;
+            default: PSS_TRY(launch_sieve<1024>(h, sp, std::min(n_tiles, grid_max))); break;
+        }
     }
-    CU_TRY(h, cudaEventRecord(h->ev[1], h->stream));
+    CU_TRY(h, mark(h, 1));
 
     u64 c235 = 0;
     for (u64 q : {2ull, 3ull, 5ull})
@@ -476,7 +543,7 @@ int sieve_range(pss_handle* h, u64 lo, u64 hi, bool defer_sync = false) {
         CU_TRY(h, cudaGetLastError());
         h->launches++;
     }
-    CU_TRY(h, cudaEventRecord(h->ev[2], h->stream));
+    CU_TRY(h, mark(h, 2));
     if (!defer_sync)
         CU_TRY(h, cudaMemcpyAsync(&h->h_back->sv_total, static_cast<u64*>(h->tile_prefix.p) + n_tiles, sizeof(u64), cudaMemcpyDeviceToHost, h->stream));
     h->sv_lo = lo; h->sv_hi = hi; h->sv_B_start = B_start; h->sv_total = 0; h->sv_c235 = c235;
@@ -497,12 +564,12 @@ int compact_resident(pss_handle* h, u64 cap) {
     const u64 n_out = std::min(h->sv_total, cap);
     h->n_resident = 0;
     if (n_out == 0) {
-        CU_TRY(h, cudaEventRecord(h->ev[3], h->stream));
+        CU_TRY(h, mark(h, 3));
         return PSS_OK;
     }
     PSS_TRY(ensure(h, h->primes, (size_t)n_out * sizeof(u64)));
     u64* out = static_cast<u64*>(h->primes.p);
-    CU_TRY(h, cudaEventRecord(h->ev[2], h->stream));
+    CU_TRY(h, mark(h, 2));
     if (h->sv_c235) {
         u64 small[3];
         u32 k = 0;
@@ -547,7 +614,7 @@ int compact_resident(pss_handle* h, u64 cap) {
         CU_TRY(h, cudaGetLastError());
         h->launches++;
     }
-    CU_TRY(h, cudaEventRecord(h->ev[3], h->stream));
+    CU_TRY(h, mark(h, 3));
     u32 flag = 0;
     u64 last = 0;
     CU_TRY(h, cudaMemcpyAsync(&flag, &static_cast<MiscDev*>(h->misc.p)->error_flag, sizeof(u32), cudaMemcpyDeviceToHost, h->stream));
@@ -679,7 +746,7 @@ int run_scan(pss_handle* h, const u64* d_vals, u64 count, u64 n_first, const u32
     sp.prefix_out = d_prefix_out;
     sp.exhaustive = h->compare_exhaustive ? 1u : 0u;
 
-    CU_TRY(h, cudaEventRecord(h->ev[4], h->stream));
+    CU_TRY(h, mark(h, 4));
     if (count > 0) {
         CU_TRY(h, cudaMemcpyAsync(dm, hm, sizeof(MiscDev), cudaMemcpyHostToDevice, h->stream));
         switch (mode) {
@@ -687,7 +754,7 @@ int run_scan(pss_handle* h, const u64* d_vals, u64 count, u64 n_first, const u32
             case kModeCompare: PSS_TRY(launch_scan<kModeCompare>(h, sp, K, multi)); break;
             default: PSS_TRY(launch_scan<kModePrefix>(h, sp, K, multi)); break;
         }
-        CU_TRY(h, cudaEventRecord(h->ev[5], h->stream));
+        CU_TRY(h, mark(h, 5));
         CU_TRY(h, cudaMemcpyAsync(hm, dm, sizeof(MiscDev), cudaMemcpyDeviceToHost, h->stream));
         CU_TRY(h, cudaStreamSynchronize(h->stream));
         if (hm->error_flag) return fail(h, PSS_EINTERNAL, "scan kernel reported error flag %u", hm->error_flag);
@@ -706,7 +773,7 @@ int run_scan(pss_handle* h, const u64* d_vals, u64 count, u64 n_first, const u32
             col += w;
         }
     } else {
-        CU_TRY(h, cudaEventRecord(h->ev[5], h->stream));
+        CU_TRY(h, mark(h, 5));
         CU_TRY(h, cudaStreamSynchronize(h->stream));
     }
     for (u32 j = 0; j < np; ++j) {
@@ -831,6 +898,15 @@ void fill_bscan_common(pss_handle* h, BScanParams& bp) {
     bp.warp_rec = static_cast<u32*>(h->warp_rec.p);
 }
 
+// enqueue the D2H of the column totals of the last bitmap_reduce (once per reduce)
+int copy_totals(pss_handle* h) {
+    if (!h->bs_pending || h->bs_totals_copied || h->bs_n_tiles == 0) return PSS_OK;
+    CU_TRY(h, cudaMemcpy2DAsync(h->h_back->col_totals, sizeof(u64), static_cast<const u64*>(h->col_prefix.p) + h->bs_n_tiles,
+                                h->bs_col_stride * sizeof(u64), sizeof(u64), h->bs_total_cols, cudaMemcpyDeviceToHost, h->stream));
+    h->bs_totals_copied = true;
+    return PSS_OK;
+}
+
 // completes an asynchronous bitmap_reduce after the stream has been synchronised
 int reduce_finish(pss_handle* h) {
     if (!h->bs_pending) return PSS_OK;
@@ -895,7 +971,7 @@ int bitmap_reduce(pss_handle* h, u32 K, bool multi, bool defer_sync = false) {
     PSS_TRY(ensure(h, h->col_prefix, (size_t)ncols * bp.col_stride * sizeof(u64)));
     bp.cols = static_cast<u64*>(h->cols.p);
     bp.col_prefix = static_cast<const u64*>(h->col_prefix.p);
-    CU_TRY(h, cudaEventRecord(h->ev[4], h->stream));
+    CU_TRY(h, mark(h, 4));
     CU_TRY(h, cudaMemsetAsync(bp.cols, 0, (size_t)ncols * bp.col_stride * sizeof(u64), h->stream));
     if (K == 2 && !multi && h->reduce_moments) {
         int occ = 1;
@@ -913,13 +989,15 @@ int bitmap_reduce(pss_handle* h, u32 K, bool multi, bool defer_sync = false) {
     launch_scan_columns(h, ncols, bp.cols, static_cast<u64*>(h->col_prefix.p), bp.n_tiles, bp.col_stride);
     CU_TRY(h, cudaGetLastError());
     h->launches++;
-    CU_TRY(h, cudaEventRecord(h->ev[5], h->stream));
-    CU_TRY(h, cudaMemcpy2DAsync(h->h_back->col_totals, sizeof(u64), static_cast<const u64*>(h->col_prefix.p) + bp.n_tiles, bp.col_stride * sizeof(u64),
-                                sizeof(u64), ncols, cudaMemcpyDeviceToHost, h->stream));
+    CU_TRY(h, mark(h, 5));
     h->bs_n_tiles = bp.n_tiles;
     h->bs_col_stride = bp.col_stride;
     h->bs_pending = true;
+    h->bs_totals_copied = false;
+    // A copy-engine operation between two kernels costs ~8 us of stream latency (measured: profiles/r02 timeline), so in a
+    // query chain the read-back of the column totals is enqueued after the LAST kernel (copy_totals), not here.
     if (!defer_sync) {
+        PSS_TRY(copy_totals(h));
         CU_TRY(h, cudaStreamSynchronize(h->stream));
         sieve_finish(h);
         PSS_TRY(reduce_finish(h));
@@ -936,6 +1014,59 @@ void limbs_add(u32* a, const u32* b) {
     }
 }
 
+// Host part of a compare launch that does not depend on the sieve: the MiscDev block (result records, carry-in limbs) is
+// filled and its H2D copy enqueued.  A query chain calls this BEFORE the sieve so that the copy engine works under the
+// sieve kernel instead of sitting between the column scan and the compare kernel.
+int prepare_misc(pss_handle* h, const pss_search_args* a, const u32* carry_in) {
+    const bool multi = a->all_powers && a->power_max > 1;
+    const u32 K = a->power_max, np = n_powers_of(K, multi);
+    MiscInit in;
+    memset(&in, 0, sizeof in);
+    in.np = np;
+    for (u32 j = 0; j < np; ++j) {
+        in.power[j] = expo_of(K, multi, j);
+        if (carry_in) {
+            memcpy(&in.carry[j * PSS_LIMBS], carry_in + j * PSS_LIMBS, PSS_LIMBS * sizeof(u32));
+            const int w = sum_limbs((int)expo_of(K, multi, j));
+            for (int i = w; i < PSS_LIMBS; ++i)
+                if (in.carry[j * PSS_LIMBS + i]) return fail(h, PSS_EINVAL, "carry-in of power %u exceeds %d limbs", in.power[j], w);
+        }
+    }
+    CU_TRY(h, cudaEventRecord(h->ev[8], h->stream));     // a query chain starts here
+    k_init_misc<<<1, 128, 0, h->stream>>>(static_cast<MiscDev*>(h->misc.p), in);
+    CU_TRY(h, cudaGetLastError());
+    h->launches++;
+    h->misc_uploaded = true;
+    return PSS_OK;
+}
+
+// last launch of a query chain: MiscDev block, pending column totals and (peer path) all ranks' outcome records -> mapped
+// pinned host memory; the caller synchronises the stream afterwards
+int export_results(pss_handle* h, u32 peer_world, u64 peer_parity) {
+    ExportParams ep;
+    memset(&ep, 0, sizeof ep);
+    ep.dm = static_cast<const MiscDev*>(h->misc.p);
+    ep.hm = h->h_misc_dev;
+    if (h->bs_pending && !h->bs_totals_copied && h->bs_n_tiles > 0) {
+        ep.col_prefix = static_cast<const u64*>(h->col_prefix.p);
+        ep.col_stride = h->bs_col_stride;
+        ep.n_tiles = h->bs_n_tiles;
+        ep.ncols = h->bs_total_cols;
+        ep.totals_host = h->h_back_dev->col_totals;
+        h->bs_totals_copied = true;
+    }
+    if (peer_world) {
+        ep.peer = &h->box_local->r[peer_parity][0];
+        ep.peer_host = h->h_peer_results_dev;
+        ep.world = peer_world;
+    }
+    k_export<<<1, 256, 0, h->stream>>>(ep);
+    CU_TRY(h, cudaGetLastError());
+    CU_TRY(h, cudaEventRecord(h->ev[9], h->stream));     // ... and ends here
+    h->launches++;
+    return PSS_OK;
+}
+
 // phase B of the fused path: compare every partial sum, seeded with carry_in (host limbs or NULL)
 int bitmap_compare(pss_handle* h, u64 n_first, const u32* carry_in, const pss_search_args* a, pss_search_result* res) {
     const bool multi = a->all_powers && a->power_max > 1;
@@ -946,22 +1077,13 @@ int bitmap_compare(pss_handle* h, u64 n_first, const u32* carry_in, const pss_se
     const u32 np = n_powers_of(K, multi);
     static const u32 kMasks[6] = {2u, 5u, 1u, 3u, 4u, 6u};
     MiscDev* hm = h->h_misc;
-    memset(hm, 0, sizeof(MiscDev));
-    for (u32 j = 0; j < np; ++j) {
-        hm->results[j].power = expo_of(K, multi, j);
-        hm->results[j].first_match_n = ~0ull;
-        if (carry_in) {
-            memcpy(&hm->carry[j * PSS_LIMBS], carry_in + j * PSS_LIMBS, PSS_LIMBS * sizeof(u32));
-            const int w = sum_limbs((int)expo_of(K, multi, j));
-            for (int i = w; i < PSS_LIMBS; ++i)
-                if (hm->carry[j * PSS_LIMBS + i]) return fail(h, PSS_EINVAL, "carry-in of power %u exceeds %d limbs", hm->results[j].power, w);
-        }
-    }
+    if (!h->misc_uploaded) PSS_TRY(prepare_misc(h, a, carry_in));
+    h->misc_uploaded = false;
     // with a pending reduce the slice count is not known yet: the caller (pss_search) guarantees by a proven bound
     // that the slice holds n_max, and checks it after the synchronisation
     u64 scanned = (a->n_max >= n_first) ? (pending ? a->n_max - n_first + 1 : std::min<u64>(h->bs_count, a->n_max - n_first + 1)) : 0;
     if (h->bs_n_tiles == 0) scanned = 0;
-    CU_TRY(h, cudaEventRecord(h->ev[6], h->stream));
+    CU_TRY(h, mark(h, 6));
     if (scanned > 0) {
         BScanParams bp;
         fill_bscan_common(h, bp);
@@ -983,15 +1105,13 @@ int bitmap_compare(pss_handle* h, u64 n_first, const u32* carry_in, const pss_se
         bp.results = dm->results;
         bp.last_prime_out = &dm->last_prime;
         bp.error_flag = &dm->error_flag;
-        CU_TRY(h, cudaMemcpyAsync(dm, hm, sizeof(MiscDev), cudaMemcpyHostToDevice, h->stream));
         PSS_TRY(launch_bscan<kBsCompare>(h, bp, K, multi));
-        CU_TRY(h, cudaEventRecord(h->ev[7], h->stream));
-        CU_TRY(h, cudaMemcpyAsync(hm, dm, sizeof(MiscDev), cudaMemcpyDeviceToHost, h->stream));
-        CU_TRY(h, cudaStreamSynchronize(h->stream));
+        CU_TRY(h, mark(h, 7));
     } else {
-        CU_TRY(h, cudaEventRecord(h->ev[7], h->stream));
-        CU_TRY(h, cudaStreamSynchronize(h->stream));
+        CU_TRY(h, mark(h, 7));
     }
+    PSS_TRY(export_results(h, 0, 0));
+    CU_TRY(h, cudaStreamSynchronize(h->stream));
     if (pending) {
         sieve_finish(h);
         PSS_TRY(reduce_finish(h));
@@ -1001,7 +1121,7 @@ int bitmap_compare(pss_handle* h, u64 n_first, const u32* carry_in, const pss_se
     }
     h->acc.ms_power_scan += ev_ms(h, 6, 7);
     h->acc.ms_bitmap_compare += ev_ms(h, 6, 7);
-    if (pending) h->acc.ms_span += ev_ms(h, 0, 7);   // sieve start -> compare end: the whole query on the stream
+    if (pending) h->acc.ms_span += ev_ms(h, 8, 9);   // first launch (k_init_misc) -> end of the last kernel (k_export): the whole query
     h->acc.primes += scanned;
     const bool reached_n_max = scanned > 0 && (n_first + scanned - 1 == a->n_max);
     for (u32 j = 0; j < np; ++j) {
@@ -1048,6 +1168,7 @@ void fill_compare_params(pss_handle* h, BScanParams& bp, const pss_search_args* 
 
 int check_handle(pss_handle* h) {
     if (!h) return fail(nullptr, PSS_EINVAL, "null handle");
+    h->misc_uploaded = false;   // every API call starts without a staged MiscDev block
     cudaError_t e = cudaSetDevice(h->device);
     if (e != cudaSuccess) return fail(h, PSS_ENODEV, "cudaSetDevice(%d): %s", h->device, cudaGetErrorString(e));
     return PSS_OK;
@@ -1104,6 +1225,7 @@ int pss_open(int device, pss_handle** out) {
     h->warp_wide_div = env_u32("PSS_WARP_WIDE_DIV", h->warp_wide_div);
     h->reduce_moments = (int)env_u32("PSS_REDUCE_MOMENTS", (u32)h->reduce_moments);
     h->compare_exhaustive = (int)env_u32("PSS_COMPARE_EXHAUSTIVE", (u32)h->compare_exhaustive);
+    h->kernel_events = (int)std::min<u32>(env_u32("PSS_KERNEL_EVENTS", 1), 2);
     h->tile_bytes = std::max<u32>(8192, std::min<u32>((h->tile_bytes / kChunkBytes) * kChunkBytes, kMaxTileBytes));
     if (env_u32("PSS_SIEVE_PROF", 0) && cudaMalloc(&h->sieve_prof.p, 64) == cudaSuccess) {
         h->sieve_prof.cap = 64;
@@ -1117,8 +1239,13 @@ int pss_open(int device, pss_handle** out) {
     if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) return cleanup(fail(nullptr, PSS_EINTERNAL, "stream create failed"));
     for (auto& ev : h->ev)
         if (cudaEventCreate(&ev) != cudaSuccess) return cleanup(fail(nullptr, PSS_EINTERNAL, "event create failed"));
-    if (cudaMallocHost(&h->h_misc, sizeof(MiscDev)) != cudaSuccess) return cleanup(fail(nullptr, PSS_EINTERNAL, "pinned alloc failed"));
-    if (cudaMallocHost(&h->h_back, sizeof(HostBack)) != cudaSuccess) return cleanup(fail(nullptr, PSS_EINTERNAL, "pinned alloc failed"));
+    if (cudaHostAlloc(reinterpret_cast<void**>(&h->h_misc), sizeof(MiscDev), cudaHostAllocMapped) != cudaSuccess ||
+        cudaHostAlloc(reinterpret_cast<void**>(&h->h_back), sizeof(HostBack), cudaHostAllocMapped) != cudaSuccess ||
+        cudaHostGetDevicePointer(reinterpret_cast<void**>(&h->h_misc_dev), h->h_misc, 0) != cudaSuccess ||
+        cudaHostGetDevicePointer(reinterpret_cast<void**>(&h->h_back_dev), h->h_back, 0) != cudaSuccess)
+        return cleanup(fail(nullptr, PSS_EINTERNAL, "pinned alloc failed"));
+    memset(h->h_misc, 0, sizeof(MiscDev));
+    memset(h->h_back, 0, sizeof(HostBack));
     int rc = ensure(h, h->misc, sizeof(MiscDev));
     if (rc == PSS_OK) rc = set_kernel_attributes(h);
     if (rc == PSS_OK) rc = build_patterns(h);
@@ -1302,6 +1429,7 @@ int pss_primesum(pss_handle* h, uint64_t n, uint32_t power, uint32_t* limbs_out)
     a.n_min = n; a.n_max = n; a.power_max = power; a.cmp = 2;   // S < 0: never true; only S_k(n_max) is wanted
     pss_search_result res;
     memset(&res, 0, sizeof res);
+    PSS_TRY(prepare_misc(h, &a, nullptr));
     PSS_TRY(sieve_range(h, 0, bound, true));
     PSS_TRY(bitmap_reduce(h, power, false, true));
     PSS_TRY(bitmap_compare(h, 1, nullptr, &a, &res));
@@ -1324,6 +1452,10 @@ static void fill_stats(pss_handle* h, pss_stats* s, const pss_stats& before) {
     s->ms_bitmap_reduce = now.ms_bitmap_reduce - before.ms_bitmap_reduce;
     s->ms_bitmap_compare = now.ms_bitmap_compare - before.ms_bitmap_compare;
     s->ms_span = now.ms_span - before.ms_span;
+    s->ms_peer_wait_totals = now.ms_peer_wait_totals - before.ms_peer_wait_totals;
+    s->ms_peer_wait_results = now.ms_peer_wait_results - before.ms_peer_wait_results;
+    s->ms_peer_compare_region = now.ms_peer_compare_region - before.ms_peer_compare_region;
+    s->ms_peer_pre_publish = now.ms_peer_pre_publish - before.ms_peer_pre_publish;
     s->ms_total_device = s->ms_sieve + s->ms_count_scan + s->ms_compact + s->ms_power_scan;
     s->primes = now.primes - before.primes;
     s->sieve_lo = now.sieve_lo;
@@ -1359,6 +1491,8 @@ int pss_search(pss_handle* h, const pss_search_args* a, pss_search_result* res) 
         const u64 bound = pss_nth_prime_upper(a->n_max) + 1;
         if (bound > kMaxValue) return fail(h, PSS_EINVAL, "n = %llu needs primes beyond 2^%d", (unsigned long long)a->n_max, PSS_MAX_PRIME_BITS);
         // sieve -> reduce -> column scan -> compare are enqueued back to back; one synchronisation at the end
+        // (the small H2D goes first and the D2H copies last: no copy-engine operation sits between two kernels)
+        PSS_TRY(prepare_misc(h, a, nullptr));
         PSS_TRY(sieve_range(h, 0, bound, true));
         PSS_TRY(bitmap_reduce(h, a->power_max, multi, true));
         PSS_TRY(bitmap_compare(h, 1, nullptr, a, res));
@@ -1396,8 +1530,6 @@ int pss_search_targets(pss_handle* h, const pss_search_args* args, uint32_t n_ta
     MiscDev* dmv = static_cast<MiscDev*>(h->misc_multi.p);
     MiscDev* hmv = h->h_misc_multi;
     // one sieve + one block-sum pass, then one (pruned) compare launch per target on the resident records
-    PSS_TRY(sieve_range(h, 0, bound, true));
-    PSS_TRY(bitmap_reduce(h, K, multi, true));
     memset(hmv, 0, sizeof(MiscDev) * n_targets);
     for (u32 t = 0; t < n_targets; ++t)
         for (u32 j = 0; j < np; ++j) {
@@ -1405,14 +1537,17 @@ int pss_search_targets(pss_handle* h, const pss_search_args* args, uint32_t n_ta
             hmv[t].results[j].first_match_n = ~0ull;
         }
     CU_TRY(h, cudaMemcpyAsync(dmv, hmv, sizeof(MiscDev) * n_targets, cudaMemcpyHostToDevice, h->stream));
-    CU_TRY(h, cudaEventRecord(h->ev[6], h->stream));
+    PSS_TRY(sieve_range(h, 0, bound, true));
+    PSS_TRY(bitmap_reduce(h, K, multi, true));
+    CU_TRY(h, mark(h, 6));
     if (h->bs_n_tiles > 0)
         for (u32 t = 0; t < n_targets; ++t) {
             BScanParams bp;
             fill_compare_params(h, bp, &args[t], 1, dmv + t);
             PSS_TRY(launch_bscan<kBsCompare>(h, bp, K, multi));
         }
-    CU_TRY(h, cudaEventRecord(h->ev[7], h->stream));
+    CU_TRY(h, mark(h, 7));
+    PSS_TRY(copy_totals(h));
     CU_TRY(h, cudaMemcpyAsync(hmv, dmv, sizeof(MiscDev) * n_targets, cudaMemcpyDeviceToHost, h->stream));
     CU_TRY(h, cudaStreamSynchronize(h->stream));
     sieve_finish(h);
@@ -1479,10 +1614,10 @@ int pss_search_tri(pss_handle* h, uint64_t n_min, uint64_t n_max, uint32_t power
         bp.tri_out = static_cast<u64*>(h->tri_buf.p);
         bp.tri_count = &dm->ticket;   // reused as the match counter
         bp.tri_cap = cap;
-        CU_TRY(h, cudaEventRecord(h->ev[4], h->stream));
+        CU_TRY(h, mark(h, 4));
         CU_TRY(h, cudaMemcpyAsync(dm, hm, sizeof(MiscDev), cudaMemcpyHostToDevice, h->stream));
         PSS_TRY(launch_bscan_tri(h, bp, power));
-        CU_TRY(h, cudaEventRecord(h->ev[5], h->stream));
+        CU_TRY(h, mark(h, 5));
         CU_TRY(h, cudaMemcpyAsync(hm, dm, sizeof(MiscDev), cudaMemcpyDeviceToHost, h->stream));
         CU_TRY(h, cudaStreamSynchronize(h->stream));
         h->acc.ms_power_scan += ev_ms(h, 4, 5);
@@ -1499,6 +1634,20 @@ int pss_search_tri(pss_handle* h, uint64_t n_min, uint64_t n_max, uint32_t power
 int pss_set_compare_mode(pss_handle* h, int exhaustive) {
     PSS_TRY(check_handle(h));
     h->compare_exhaustive = exhaustive ? 1 : 0;
+    return PSS_OK;
+}
+
+int pss_set_kernel_events(pss_handle* h, int level) {
+    PSS_TRY(check_handle(h));
+    if (level < 0 || level > 2) return fail(h, PSS_EINVAL, "kernel event level must be 0, 1 or 2");
+    h->kernel_events = level;
+    return PSS_OK;
+}
+
+int pss_set_sieve_variant(pss_handle* h, int variant) {
+    PSS_TRY(check_handle(h));
+    if (variant != 0 && variant != 1) return fail(h, PSS_EINVAL, "sieve variant must be 0 (segmented) or 1 (individual)");
+    h->sieve_variant = variant;
     return PSS_OK;
 }
 
@@ -1538,7 +1687,8 @@ int pss_peer_export(pss_handle* h, void* ipc_handle_out) {
     if (!h->box_local) {
         CU_TRY(h, cudaMalloc(reinterpret_cast<void**>(&h->box_local), sizeof(PeerBox)));
         CU_TRY(h, cudaMemset(h->box_local, 0, sizeof(PeerBox)));
-        CU_TRY(h, cudaMallocHost(reinterpret_cast<void**>(&h->h_peer_results), sizeof(PeerResult) * kMaxPeers));
+        CU_TRY(h, cudaHostAlloc(reinterpret_cast<void**>(&h->h_peer_results), sizeof(PeerResult) * kMaxPeers, cudaHostAllocMapped));
+        CU_TRY(h, cudaHostGetDevicePointer(reinterpret_cast<void**>(&h->h_peer_results_dev), h->h_peer_results, 0));
     }
     cudaIpcMemHandle_t hd;
     CU_TRY(h, cudaIpcGetMemHandle(&hd, h->box_local));
@@ -1597,21 +1747,17 @@ int pss_peer_search(pss_handle* h, uint64_t lo, uint64_t hi_excl, const pss_sear
     // publishes must still release the peers (k_peer_publish_failure), or they would spin until the watchdog fires.
     int stage = 0;           // publishes done: 1 = slice totals, 2 = outcome record
     auto run = [&]() -> int {
+        // the MiscDev block goes up first: its copy runs under the sieve instead of between two kernels of the chain
+        MiscDev* hm = h->h_misc;
+        MiscDev* dm = static_cast<MiscDev*>(h->misc.p);
+        PSS_TRY(prepare_misc(h, a, nullptr));
+        h->misc_uploaded = false;
         // ---- phase A: sieve + block sums + column scan of this rank's slice (enqueued, not synchronised)
         PSS_TRY(sieve_range(h, lo, hi_excl, true));
         const bool sv_was_pending = h->sv_pending;
         PSS_TRY(bitmap_reduce(h, K, multi, true));
         const bool has_tiles = h->bs_n_tiles > 0;
-        if (!sv_was_pending) CU_TRY(h, cudaEventRecord(h->ev[0], h->stream));   // empty slice: the chain starts here
-
-        MiscDev* hm = h->h_misc;
-        MiscDev* dm = static_cast<MiscDev*>(h->misc.p);
-        memset(hm, 0, sizeof(MiscDev));
-        for (u32 j = 0; j < np; ++j) {
-            hm->results[j].power = expo_of(K, multi, j);
-            hm->results[j].first_match_n = ~0ull;
-        }
-        CU_TRY(h, cudaMemcpyAsync(dm, hm, sizeof(MiscDev), cudaMemcpyHostToDevice, h->stream));
+        if (!sv_was_pending) CU_TRY(h, mark(h, 0));   // empty slice: the chain starts here
 
         // ---- the exchange: publish the slice totals into every rank's mailbox, gather the lower ranks' totals
         PeerPublishParams pp;
@@ -1625,6 +1771,7 @@ int pss_peer_search(pss_handle* h, uint64_t lo, uint64_t hi_excl, const pss_sear
         pp.world = world;
         pp.rank = rank;
         pp.epoch = epoch;
+        pp.tl = dm->tl;
         PeerGatherParams pg;
         memset(&pg, 0, sizeof pg);
         pg.box = h->box_local;
@@ -1634,6 +1781,7 @@ int pss_peer_search(pss_handle* h, uint64_t lo, uint64_t hi_excl, const pss_sear
         pg.n_first_out = &dm->n_first;
         pg.carry_out = dm->carry;
         pg.error_flag = &dm->error_flag;
+        pg.tl = dm->tl;
         static const bool peer_split = env_u32("PSS_PEER_MERGE", 0) == 0;   // default: the two halves as separate launches (8-GPU A/B)
         if (peer_split) {
             k_peer_publish<<<1, 32, 0, h->stream>>>(pp);
@@ -1647,14 +1795,14 @@ int pss_peer_search(pss_handle* h, uint64_t lo, uint64_t hi_excl, const pss_sear
         stage = 1;
 
         // ---- phase B: compare, seeded from device memory (n_first, carry)
-        CU_TRY(h, cudaEventRecord(h->ev[6], h->stream));
+        CU_TRY(h, mark(h, 6));
         if (has_tiles) {
             BScanParams bp;
             fill_compare_params(h, bp, a, 0);
             bp.n_first_dev = &dm->n_first;
             PSS_TRY(launch_bscan<kBsCompare>(h, bp, K, multi));
         }
-        CU_TRY(h, cudaEventRecord(h->ev[7], h->stream));
+        CU_TRY(h, mark(h, 7));
 
         // ---- outcome records: publish to every rank, wait for every rank's
         PeerResultParams pr;
@@ -1672,27 +1820,33 @@ int pss_peer_search(pss_handle* h, uint64_t lo, uint64_t hi_excl, const pss_sear
         pr.col_stride = pp.col_stride;
         pr.n_tiles = pp.n_tiles;
         for (u32 j = 0; j < np; ++j) pr.width[j] = pp.width[j];
+        pr.tl = dm->tl;
         if (peer_split) {
             k_peer_publish_result<<<1, 256, 0, h->stream>>>(pr);
-            k_peer_gather_results<<<1, 32, 0, h->stream>>>(h->box_local, world, epoch, watchdog, &dm->error_flag);
+            k_peer_gather_results<<<1, 32, 0, h->stream>>>(h->box_local, world, epoch, watchdog, &dm->error_flag, dm->tl);
             h->launches += 2;
         } else {
-            k_peer_exchange_results<<<1, 256, 0, h->stream>>>(pr, h->box_local, world, epoch, watchdog, &dm->error_flag);
+            k_peer_exchange_results<<<1, 256, 0, h->stream>>>(pr, h->box_local, world, epoch, watchdog, &dm->error_flag, dm->tl);
             h->launches += 1;
         }
         CU_TRY(h, cudaGetLastError());
         stage = 2;
-        CU_TRY(h, cudaMemcpyAsync(h->h_peer_results, &h->box_local->r[epoch & 1ull][0], sizeof(PeerResult) * world, cudaMemcpyDeviceToHost, h->stream));
-        CU_TRY(h, cudaMemcpyAsync(hm, dm, sizeof(MiscDev), cudaMemcpyDeviceToHost, h->stream));
-        cudaEvent_t ev_end = h->ev[3];   // compaction event, unused on this path
-        CU_TRY(h, cudaEventRecord(ev_end, h->stream));
+        PSS_TRY(export_results(h, world, epoch & 1ull));
         CU_TRY(h, cudaStreamSynchronize(h->stream));
 
         sieve_finish(h);
         PSS_TRY(reduce_finish(h));
         h->acc.ms_power_scan += ev_ms(h, 6, 7);
         h->acc.ms_bitmap_compare += ev_ms(h, 6, 7);
-        h->acc.ms_span += ev_ms(h, 0, 3);     // first launch -> all ranks' outcomes gathered (waits on peers included)
+        h->acc.ms_span += ev_ms(h, 8, 9);     // first launch -> all ranks' outcomes gathered and stored to the host (waits on peers included)
+        {   // where the span went, from the exchange kernels' own globaltimer stamps
+            const u64* tl = hm->tl;
+            auto ms = [](u64 a, u64 b) { return b > a ? (double)(b - a) * 1e-6 : 0.0; };
+            h->acc.ms_peer_wait_totals += ms(tl[1], tl[2]);
+            h->acc.ms_peer_wait_results += ms(tl[4], tl[5]);
+            h->acc.ms_peer_compare_region += ms(tl[2], tl[3]);
+            h->acc.ms_peer_pre_publish += std::max(0.0, ev_ms(h, 8, 9) - ms(tl[0], tl[5]));
+        }
         if (hm->error_flag) return fail(h, PSS_EINTERNAL, "peer exchange failed on the device (flags 0x%x): a rank did not publish in time", hm->error_flag);
         u64 scanned_here = 0;
         for (u32 r = 0; r < world; ++r) {

@@ -57,6 +57,17 @@ __device__ __forceinline__ void st_release_sys(u64* p, u64 v) {
     asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
 
+__device__ __forceinline__ u64 global_ns() {
+    u64 t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+// timeline of the exchange (this rank's own globaltimer, ns): [0] publish entry, [1] gather entry, [2] gather exit,
+// [3] publish_result entry, [4] gather_results entry, [5] gather_results exit
+__device__ __forceinline__ void stamp(u64* tl, int i) {
+    if (tl && threadIdx.x == 0) tl[i] = global_ns();
+}
+
 // spin until *flag == epoch; false after `limit` clock cycles (the watchdog: a rank that died must not hang the box)
 __device__ __forceinline__ bool wait_flag(const u64* flag, u64 epoch, long long limit) {
     const long long t0 = clock64();
@@ -76,11 +87,13 @@ struct PeerPublishParams {
     PeerBox* box[kMaxPeers];
     u32 world, rank;
     u64 epoch;
+    u64* tl;                 // timeline stamps (device, 8 entries) or NULL
 };
 
 // one CTA of 32 * ceil(world / 32) threads: thread t stores this rank's record into rank t's mailbox
 __device__ __forceinline__ void peer_publish_body(const PeerPublishParams& P) {
     __shared__ u64 s_count;
+    stamp(P.tl, 0);
     __shared__ u32 s_sums[PSS_MAX_POWER * PSS_LIMBS];
     if (threadIdx.x == 0) {
         for (u32 i = 0; i < PSS_MAX_POWER * PSS_LIMBS; ++i) s_sums[i] = 0;
@@ -119,10 +132,12 @@ struct PeerGatherParams {
     u64* n_first_out;        // device: 1 + primes of all lower ranks
     u32* carry_out;          // device: np * PSS_LIMBS limbs = sums of all lower ranks
     u32* error_flag;
+    u64* tl;
 };
 
 __device__ __forceinline__ void peer_gather_body(const PeerGatherParams& P) {
     __shared__ u32 s_bad;
+    stamp(P.tl, 1);
     if (threadIdx.x == 0) s_bad = 0;
     __syncthreads();
     const u32 t = threadIdx.x;
@@ -150,6 +165,7 @@ __device__ __forceinline__ void peer_gather_body(const PeerGatherParams& P) {
         for (u32 r = 0; r < P.rank; ++r) n += P.box->a[P.epoch & 1ull][r].count;
         *P.n_first_out = n;
     }
+    stamp(P.tl, 2);
 }
 
 struct PeerResultParams {
@@ -166,11 +182,13 @@ struct PeerResultParams {
     u64 col_stride;
     u32 n_tiles;
     u32 width[PSS_MAX_POWER];
+    u64* tl;
 };
 
 // one CTA: builds this rank's outcome record and stores it into every rank's mailbox
 __device__ __forceinline__ void peer_publish_result_body(const PeerResultParams& P) {
     __shared__ PeerResult s_rec;
+    stamp(P.tl, 3);
     if (threadIdx.x == 0) {
         const u64 n_first = *P.n_first;
         const u64 count = P.col_prefix ? P.col_prefix[P.n_tiles] : 0;
@@ -221,10 +239,13 @@ __device__ __forceinline__ void peer_publish_result_body(const PeerResultParams&
     if (threadIdx.x < P.world) st_release_sys(&P.box[threadIdx.x]->r[P.epoch & 1ull][P.rank].flag, P.epoch);
 }
 
-__device__ __forceinline__ void peer_gather_results_body(PeerBox* box, u32 world, u64 epoch, long long watchdog, u32* error_flag) {
+__device__ __forceinline__ void peer_gather_results_body(PeerBox* box, u32 world, u64 epoch, long long watchdog, u32* error_flag, u64* tl) {
+    stamp(tl, 4);
     if (threadIdx.x < world) {
         if (!wait_flag(&box->r[epoch & 1ull][threadIdx.x].flag, epoch, watchdog)) atomicOr(error_flag, 0x200u);
     }
+    __syncthreads();
+    stamp(tl, 5);
 }
 
 // The two halves of an exchange step run in ONE launch: publish first (remote stores + release of the epoch flag), then wait
@@ -233,8 +254,8 @@ __device__ __forceinline__ void peer_gather_results_body(PeerBox* box, u32 world
 __global__ void k_peer_publish(const PeerPublishParams P) { peer_publish_body(P); }
 __global__ void k_peer_gather(const PeerGatherParams P) { peer_gather_body(P); }
 __global__ void k_peer_publish_result(const PeerResultParams P) { peer_publish_result_body(P); }
-__global__ void k_peer_gather_results(PeerBox* box, u32 world, u64 epoch, long long watchdog, u32* error_flag) {
-    peer_gather_results_body(box, world, epoch, watchdog, error_flag);
+__global__ void k_peer_gather_results(PeerBox* box, u32 world, u64 epoch, long long watchdog, u32* error_flag, u64* tl) {
+    peer_gather_results_body(box, world, epoch, watchdog, error_flag, tl);
 }
 // A rank whose host side failed after the query's epoch was opened (allocation, launch error) still has to release its
 // peers: it publishes empty slice totals (stage 0) and an outcome record whose error field carries `code` (stages 0, 1), so
@@ -269,10 +290,10 @@ __global__ void k_peer_exchange(const PeerPublishParams PP, const PeerGatherPara
     __syncthreads();
     peer_gather_body(PG);
 }
-__global__ void k_peer_exchange_results(const PeerResultParams PR, PeerBox* box, u32 world, u64 epoch, long long watchdog, u32* error_flag) {
+__global__ void k_peer_exchange_results(const PeerResultParams PR, PeerBox* box, u32 world, u64 epoch, long long watchdog, u32* error_flag, u64* tl) {
     peer_publish_result_body(PR);
     __syncthreads();
-    peer_gather_results_body(box, world, epoch, watchdog, error_flag);
+    peer_gather_results_body(box, world, epoch, watchdog, error_flag, tl);
 }
 
 }  // namespace pss

@@ -344,6 +344,53 @@ __global__ void __launch_bounds__(THREADS, (THREADS <= 768) ? 2 : 1) k_sieve(con
     }
 }
 
+// ---- K1 variant "individual": per-candidate trial division (reference: utils/sieve.py:330-387 _individual_sieve) --------
+// The reference's minimal-memory variant tests every candidate on its own by trial division with the primes up to its
+// square root.  Here: one CTA per 1 KiB bitmap chunk, one thread per bitmap word (32 wheel-30 candidates); a candidate is
+// prime iff no prime 7 <= p <= sqrt(v) divides it (2, 3, 5 are excluded by the wheel).  Same outputs as k_sieve (bitmap,
+// chunk and tile popcounts), so counting, compaction and the fused scan run unchanged on top of it.  O(n sqrt(n) / log n)
+// like the reference's: a selectable cross-check of the sieve, not a fast path.
+__global__ void __launch_bounds__(kChunkWords) k_individual(const SieveParams P) {
+    __shared__ u32 s_cnt[kChunkWords / 32];
+    const u32 chunks_per_tile = P.tile_bytes / kChunkBytes;
+    const u64 n_chunks = (u64)P.n_tiles * chunks_per_tile;
+    const u32 tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+    const u32 kSmall[14] = {7, 11, 13, 17, 19, 23, 29, 31, 37, 41, 43, 47, 53, 59};
+    for (u64 ch = blockIdx.x; ch < n_chunks; ch += gridDim.x) {
+        const u64 Bw = P.B_start + ch * (u64)kChunkBytes + 4ull * tid;
+        u32 word = 0;
+        for (u32 bit = 0; bit < 32; ++bit) {
+            const u64 v = word_bit_value(Bw, bit);
+            if (v < 7 || v < P.lo || v >= P.hi) continue;
+            bool prime = true;
+            for (u32 i = 0; i < 14 && prime; ++i) {
+                const u64 q = kSmall[i];
+                if (q * q > v) break;
+                if (v % q == 0) prime = false;
+            }
+            // base_p holds the primes from the first one not covered by a pre-sieve pattern (>= 61 by default; the
+            // host stages them up to sqrt(hi)); entries below 61 were tested above
+            for (u32 i = 0; i < P.n_base && prime; ++i) {
+                const u64 q = __ldg(P.base_p + i);
+                if (q * q > v) break;
+                if (q > 59 && v % q == 0) prime = false;
+            }
+            if (prime) word |= 1u << bit;
+        }
+        P.bitmap[ch * kChunkWords + tid] = word;
+        u32 cnt = __reduce_add_sync(0xFFFFFFFFu, __popc(word));
+        if (lane == 0) s_cnt[warp] = cnt;
+        __syncthreads();
+        if (tid == 0) {
+            u32 total = 0;
+            for (u32 w = 0; w < kChunkWords / 32; ++w) total += s_cnt[w];
+            P.chunk_counts[ch] = total;
+            atomicAdd(P.tile_counts + (u32)(ch / chunks_per_tile), total);
+        }
+        __syncthreads();
+    }
+}
+
 // ---- K1b: exclusive scan of per-tile counts (u32 -> u64), single CTA ----------------------------
 // prefix[t] = init + sum_{i<t} counts[i];  prefix[n] = grand total.
 __global__ void __launch_bounds__(1024) k_scan_tile_counts(const u32* counts, u32 n, u64 init, u64* prefix) {

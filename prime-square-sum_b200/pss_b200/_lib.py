@@ -15,7 +15,7 @@ import numpy as np
 
 PSS_LIMBS = 12
 PSS_MAX_POWER = 8
-ABI_VERSION = 2   # PSS_ABI_VERSION of include/pss_b200.h this binding was written against
+ABI_VERSION = 3   # PSS_ABI_VERSION of include/pss_b200.h this binding was written against
 PSS_MAX_PRIME_BITS = 40
 PSS_OK, PSS_EINVAL, PSS_ENODEV, PSS_ENOMEM, PSS_EINTERNAL = 0, 1, 2, 3, 4
 
@@ -43,6 +43,8 @@ class Stats(ctypes.Structure):
         ("ms_power_scan", ctypes.c_double), ("ms_total_device", ctypes.c_double),
         ("primes", u64), ("sieve_lo", u64), ("sieve_hi", u64), ("launches", u64),
         ("ms_bitmap_reduce", ctypes.c_double), ("ms_bitmap_compare", ctypes.c_double), ("ms_span", ctypes.c_double),
+        ("ms_peer_pre_publish", ctypes.c_double), ("ms_peer_wait_totals", ctypes.c_double),
+        ("ms_peer_compare_region", ctypes.c_double), ("ms_peer_wait_results", ctypes.c_double),
     ]
 
 
@@ -80,6 +82,7 @@ EXPORTS = [
     "pss_slice_device_buffer", "pss_nth_prime_upper", "pss_stats_reset", "pss_stats_get",
     "pss_set_search_path", "pss_slice_sieve_sums", "pss_slice_scan_bitmap", "pss_search_tri",
     "pss_set_compare_mode", "pss_peer_export", "pss_peer_connect", "pss_peer_search", "pss_search_targets",
+    "pss_set_sieve_variant", "pss_set_kernel_events",
 ]
 
 _cdll = None
@@ -121,6 +124,8 @@ def load_library() -> ctypes.CDLL:
     L.pss_search_tri.argtypes = [H, u64, u64, u32, u64, u64, pu64, u32, pu32, ctypes.POINTER(Stats)]
     L.pss_set_search_path.argtypes = [H, ctypes.c_int]
     L.pss_set_compare_mode.argtypes = [H, ctypes.c_int]
+    L.pss_set_sieve_variant.argtypes = [H, ctypes.c_int]
+    L.pss_set_kernel_events.argtypes = [H, ctypes.c_int]
     L.pss_search_targets.argtypes = [H, ctypes.POINTER(SearchArgs), u32, ctypes.POINTER(SearchResult)]
     L.pss_peer_export.argtypes = [H, ctypes.c_void_p]
     L.pss_peer_connect.argtypes = [H, ctypes.c_int, ctypes.c_int, ctypes.c_void_p]
@@ -144,7 +149,9 @@ def stats_to_dict(s: "Stats") -> dict:
     return {"ms_sieve": s.ms_sieve, "ms_count_scan": s.ms_count_scan, "ms_compact": s.ms_compact,
             "ms_power_scan": s.ms_power_scan, "ms_bitmap_reduce": s.ms_bitmap_reduce,
             "ms_bitmap_compare": s.ms_bitmap_compare, "ms_total_device": s.ms_total_device, "ms_span": s.ms_span, "primes": int(s.primes),
-            "sieve_lo": int(s.sieve_lo), "sieve_hi": int(s.sieve_hi), "launches": int(s.launches)}
+            "sieve_lo": int(s.sieve_lo), "sieve_hi": int(s.sieve_hi), "launches": int(s.launches),
+            "ms_peer_pre_publish": s.ms_peer_pre_publish, "ms_peer_wait_totals": s.ms_peer_wait_totals,
+            "ms_peer_compare_region": s.ms_peer_compare_region, "ms_peer_wait_results": s.ms_peer_wait_results}
 
 
 def int_to_limbs(x: int, n: Optional[int] = None) -> np.ndarray:
@@ -160,6 +167,8 @@ def int_to_limbs(x: int, n: Optional[int] = None) -> np.ndarray:
 
 
 def limbs_to_int(a) -> int:
+    if isinstance(a, ctypes.Array):          # a limb field of a result struct: no numpy round trip on the query path
+        return int.from_bytes(bytes(a), "little")
     return int.from_bytes(np.asarray(a, dtype=np.uint32).tobytes(), "little")
 
 
@@ -354,6 +363,14 @@ class Handle:
 
     def set_search_path(self, materialised: bool):
         self._check(self._L.pss_set_search_path(self._h, 1 if materialised else 0))
+
+    def set_kernel_events(self, level: int):
+        """per-kernel CUDA timing events: 0 none, 1 (default) the sieve only, 2 every kernel (see pss_b200.h)"""
+        self._check(self._L.pss_set_kernel_events(self._h, int(level)))
+
+    def set_sieve_variant(self, individual: bool):
+        """False (default): the segmented wheel-30 sieve; True: per-candidate trial division (reference 'individual')"""
+        self._check(self._L.pss_set_sieve_variant(self._h, 1 if individual else 0))
 
     def set_compare_mode(self, exhaustive: bool):
         """fused compare pass: False (default) = interval pruning, True = walk every prime / form every S_k(n)"""

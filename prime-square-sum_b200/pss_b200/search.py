@@ -478,24 +478,26 @@ def _peer_search(h, group, rank, world, lo_g, hi_g, target, n_max, power, n_min,
     recs, stats = h.peer_search(lo_g, hi_g, n_min, n_max, power, target, op, all_powers)
     if sum(int(r.count) for r in recs) < n_max:
         raise RuntimeError("prime count bound violated")
-    outs = []
-    for g, r in enumerate(recs):
-        if not r.valid:
-            outs.append(None)
-            continue
-        powers = []
-        for j in range(np_):
-            q = r.powers[j]
-            powers.append(PowerOutcome(
-                power=int(q.power), match_count=int(q.match_count), first_match_n=int(q.first_match_n),
-                last_match_n=int(q.last_match_n), cross_n=int(q.cross_n), cross_prime=int(q.cross_prime),
-                sum_at_cross=_lib.limbs_to_int(q.sum_at_cross), sum_before_cross=_lib.limbs_to_int(q.sum_before_cross),
-                final_sum=_lib.limbs_to_int(q.final_sum)))
-        outs.append(SearchOutcome(n_min, n_max, op, target, int(r.last_prime), powers, dict(stats) if g == rank else {}))
-    merged = merge_outcomes(outs, n_min, n_max, op, target)
-    merged.stats = dict(stats)
-    merged.stats["exchange"] = "peer memory (NVLink, device-side)"
-    return merged
+    # merge the ranks' records field by field (ranks are in value order); big integers are converted only where the merged
+    # outcome needs them: the crossing rank's two sums and the last scanning rank's final sum
+    valid = [r for r in recs if r.valid]
+    if not valid:
+        raise ValueError("no slice scanned anything")
+    powers = []
+    for j in range(np_):
+        qs = [r.powers[j] for r in valid]
+        cross = next((q for q in qs if q.cross_n), None)
+        matched = [q for q in qs if q.match_count]
+        powers.append(PowerOutcome(
+            power=int(qs[0].power), match_count=sum(int(q.match_count) for q in matched),
+            first_match_n=min((int(q.first_match_n) for q in matched), default=0),
+            last_match_n=max((int(q.last_match_n) for q in matched), default=0),
+            cross_n=int(cross.cross_n) if cross else 0, cross_prime=int(cross.cross_prime) if cross else 0,
+            sum_at_cross=_lib.limbs_to_int(cross.sum_at_cross) if cross else 0,
+            sum_before_cross=_lib.limbs_to_int(cross.sum_before_cross) if cross else 0,
+            final_sum=_lib.limbs_to_int(qs[-1].final_sum)))
+    stats["exchange"] = "peer memory (NVLink, device-side)"
+    return SearchOutcome(n_min, n_max, op, target, int(valid[-1].last_prime), powers, stats)
 
 
 _STAT_KEYS = ("ms_sieve", "ms_count_scan", "ms_compact", "ms_power_scan", "ms_bitmap_reduce", "ms_bitmap_compare",

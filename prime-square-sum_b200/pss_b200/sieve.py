@@ -1,7 +1,8 @@
 """
 sieve.py — host-side mirror of the reference's sieve facade (utils/sieve.py:440-693) for the new
 `b200` variant.  Same names, argument meaning and error behaviour; every prime comes from the sm_100a
-segmented wheel-30 sieve (csrc/pss_sieve.cuh) through the C ABI.  No CPU fallback.
+segmented wheel-30 sieve (csrc/pss_sieve.cuh) — or, for `individual`, the per-candidate trial-division kernel — through
+the C ABI.  No CPU fallback.
 
 Reference semantics kept:
   generate_primes(limit)        exclusive bound, int64 array, limit < 2 -> empty      (utils/sieve.py:444,473-474)
@@ -22,9 +23,19 @@ from . import _lib
 
 ALGORITHM_AUTO = "auto"
 ALGORITHM_B200 = "b200"
-# the reference's CPU variants: recognised names, not provided by this package
-_REFERENCE_CPU_VARIANTS = ["primesieve", "basic", "segmented", "individual"]
-VALID_ALGORITHMS = [ALGORITHM_AUTO, ALGORITHM_B200] + _REFERENCE_CPU_VARIANTS
+ALGORITHM_PRIMESIEVE = "primesieve"
+ALGORITHM_BASIC = "basic"
+ALGORITHM_SEGMENTED = "segmented"
+ALGORITHM_INDIVIDUAL = "individual"
+# What each of the reference's names runs HERE (every variant computes on the device; there is no CPU path):
+#   auto, b200, segmented, basic -> the segmented bit-packed wheel-30 sieve (the only sieve in this build is segmented;
+#                                   "basic" — one segment spanning the range — is served by the same kernel)
+#   individual                   -> per-candidate trial division on the device (k_individual), the reference's
+#                                   _individual_sieve (utils/sieve.py:330-387): same results, O(n sqrt(n) / log n)
+#   primesieve                   -> not installed (third-party CPU library): ValueError like utils/sieve.py:492-498
+VALID_ALGORITHMS = [ALGORITHM_AUTO, ALGORITHM_B200, ALGORITHM_PRIMESIEVE, ALGORITHM_BASIC, ALGORITHM_SEGMENTED, ALGORITHM_INDIVIDUAL]
+_DEVICE_VARIANT = {ALGORITHM_AUTO: False, ALGORITHM_B200: False, ALGORITHM_BASIC: False, ALGORITHM_SEGMENTED: False,
+                   ALGORITHM_INDIVIDUAL: True}
 
 _config = {"algorithm": ALGORITHM_AUTO, "max_memory_mb": None, "prefer": None}
 
@@ -45,16 +56,25 @@ def get_config() -> dict:
     return _config.copy()
 
 
-def _resolve(algorithm: Optional[str]) -> str:
-    if algorithm is None:
+def _resolve(algorithm: Optional[str]) -> bool:
+    """-> True when the 'individual' device variant is selected, False for the segmented sieve"""
+    if algorithm is None or algorithm == ALGORITHM_AUTO:
         algorithm = _config.get("algorithm", ALGORITHM_AUTO)
     if algorithm not in VALID_ALGORITHMS:
         raise ValueError(f"Unknown algorithm: {algorithm}. Valid options: {', '.join(VALID_ALGORITHMS)}")
-    if algorithm in _REFERENCE_CPU_VARIANTS:
-        # mirrors "primesieve requested but not installed" (utils/sieve.py:492-498): a recognised variant
-        # this build does not carry.  pss_b200 has no CPU path by design.
-        raise ValueError(f"{algorithm} requested but not provided by pss_b200 (GPU-only build; use 'b200' or 'auto')")
-    return ALGORITHM_B200
+    if algorithm == ALGORITHM_PRIMESIEVE:
+        raise ValueError("primesieve requested but not installed (pss_b200 computes on the GPU: use 'b200', 'segmented', "
+                         "'individual' or 'auto')")
+    return _DEVICE_VARIANT[algorithm]
+
+
+def _handle(algorithm: Optional[str]) -> "_lib.Handle":
+    individual = _resolve(algorithm)
+    h = _lib.default_handle()
+    if getattr(h, "_individual", False) != individual:
+        h.set_sieve_variant(individual)
+        h._individual = individual
+    return h
 
 
 def _as_int(x, what: str) -> int:
@@ -73,8 +93,7 @@ def generate_primes(limit: int, algorithm: str = None, max_memory_mb: Optional[i
     limit = _as_int(limit, "limit")
     if limit < 2:
         return np.array([], dtype=np.int64)
-    _resolve(algorithm)
-    return _lib.default_handle().generate_primes(0, limit)
+    return _handle(algorithm).generate_primes(0, limit)
 
 
 def generate_primes_range(start: int, stop: int, algorithm: str = ALGORITHM_AUTO,
@@ -84,23 +103,21 @@ def generate_primes_range(start: int, stop: int, algorithm: str = ALGORITHM_AUTO
     _resolve(algorithm)
     if stop < 2 or start >= stop:
         return np.array([], dtype=np.int64)
-    return _lib.default_handle().generate_primes(max(start, 0), stop)
+    return _handle(algorithm).generate_primes(max(start, 0), stop)
 
 
 def generate_n_primes(n: int, algorithm: str = ALGORITHM_AUTO, max_memory_mb: Optional[int] = None) -> np.ndarray:
     n = _as_int(n, "n")
     if n <= 0:
         return np.array([], dtype=np.int64)
-    _resolve(algorithm)
-    return _lib.default_handle().generate_n_primes(n)
+    return _handle(algorithm).generate_n_primes(n)
 
 
 def nth_prime(n: int, algorithm: str = ALGORITHM_AUTO) -> int:
     n = _as_int(n, "n")
     if n <= 0:
         raise ValueError("n must be positive (1-indexed)")
-    _resolve(algorithm)
-    return _lib.default_handle().nth_prime(n)
+    return _handle(algorithm).nth_prime(n)
 
 
 def prime_count(limit: int, algorithm: str = ALGORITHM_AUTO) -> int:
@@ -109,24 +126,23 @@ def prime_count(limit: int, algorithm: str = ALGORITHM_AUTO) -> int:
     _resolve(algorithm)
     if limit < 2:
         return 0
-    return _lib.default_handle().count_primes(0, limit + 1)
+    return _handle(algorithm).count_primes(0, limit + 1)
 
 
 def get_available_algorithms() -> List[str]:
-    return [ALGORITHM_AUTO, ALGORITHM_B200]
+    return [ALGORITHM_AUTO, ALGORITHM_B200, ALGORITHM_BASIC, ALGORITHM_SEGMENTED, ALGORITHM_INDIVIDUAL]
 
 
 def get_algorithm_info() -> dict:
     """Same shape as utils/sieve.py:657-693 so `--list algorithms` (utils/list_commands.py:60-97) can print it."""
-    info = {
+    seg = {"available": True, "complexity_time": "O(n log log n)",
+           "complexity_space": "O(sqrt(n)) base primes + n/30 bytes bitmap in HBM"}
+    return {
         ALGORITHM_AUTO: {"description": "Auto-select best available algorithm", "available": True},
-        ALGORITHM_B200: {
-            "description": "B200 (sm_100a) segmented bit-packed wheel-30 sieve, shared-memory tiles",
-            "available": True,
-            "complexity_time": "O(n log log n)",
-            "complexity_space": "O(sqrt(n)) base primes + n/30 bytes bitmap in HBM",
-        },
+        ALGORITHM_B200: dict(seg, description="B200 (sm_100a) segmented bit-packed wheel-30 sieve, shared-memory tiles"),
+        ALGORITHM_PRIMESIEVE: {"description": "C++ primesieve library (third-party CPU code, not part of pss_b200)", "available": False},
+        ALGORITHM_BASIC: dict(seg, description="served by the B200 segmented sieve (one kernel for every range)"),
+        ALGORITHM_SEGMENTED: dict(seg, description="B200 segmented sieve (same kernel as 'b200')"),
+        ALGORITHM_INDIVIDUAL: {"description": "Individual testing on the device (trial division per candidate)", "available": True,
+                               "complexity_time": "O(n * sqrt(n) / log(n))", "complexity_space": "n/30 bytes bitmap in HBM"},
     }
-    for name in _REFERENCE_CPU_VARIANTS:
-        info[name] = {"description": f"reference CPU variant '{name}' (not part of pss_b200)", "available": False}
-    return info

@@ -28,7 +28,7 @@ def test_library_exports_every_declared_symbol():
     L = ctypes.CDLL(_lib.LIB_PATH)
     for name in declared_functions():
         assert hasattr(L, name), f"{name} declared in include/pss_b200.h but not exported"
-    assert L.pss_abi_version() == _lib.ABI_VERSION == 2
+    assert L.pss_abi_version() == _lib.ABI_VERSION == 3
     # the ctypes binding covers the whole header too
     assert sorted(set(_lib.EXPORTS)) == declared_functions()
 
@@ -37,7 +37,7 @@ def test_struct_layouts_match_the_header():
     from pss_b200 import _lib
     # pss_power_result: 2*u32 + 5*u64 + 3*12*u32
     assert ctypes.sizeof(_lib.PowerResult) == 8 + 40 + 144
-    assert ctypes.sizeof(_lib.Stats) == 5 * 8 + 4 * 8 + 3 * 8
+    assert ctypes.sizeof(_lib.Stats) == 5 * 8 + 4 * 8 + 3 * 8 + 4 * 8
     assert ctypes.sizeof(_lib.SearchArgs) == 8 + 8 + 4 * 4 + 8
     assert ctypes.sizeof(_lib.SearchResult) == 8 + 8 + 8 + 8 * ctypes.sizeof(_lib.PowerResult) + ctypes.sizeof(_lib.Stats)
 

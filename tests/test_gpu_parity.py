@@ -99,6 +99,30 @@ def test_compaction_kernels_vs_oracle(orc, env):
             del os.environ[env]
 
 
+def test_individual_variant_matches_the_sieve(handle, orc):
+    """--algorithm sieve:individual (reference utils/sieve.py:330-387): per-candidate trial division on the device gives
+    the same primes, counts and sums as the segmented sieve and the oracle (the reference's own cross-check of its
+    variants, tests/test_sieve.py:80-120)"""
+    from pss_b200 import sieve
+    try:
+        for limit in (2, 3, 8, 100, 10007, 300_000):
+            got = sieve.generate_primes(limit, algorithm="individual")
+            assert np.array_equal(got.astype(np.uint64), orc.c_primes_range(0, limit)), limit
+        got = sieve.generate_primes_range(10 ** 9, 10 ** 9 + 20_000, algorithm="individual")
+        assert np.array_equal(got.astype(np.uint64), orc.c_primes_range(10 ** 9, 10 ** 9 + 20_000))
+        assert [int(x) for x in sieve.generate_n_primes(25, algorithm="individual")] == [int(x) for x in orc.c_first_n_primes(25)]
+        assert sieve.nth_prime(1000, algorithm="individual") == 7919 and sieve.prime_count(10 ** 5, algorithm="individual") == 9592
+        sieve.configure(algorithm="individual")
+        assert sieve.prime_count(10 ** 4) == 1229
+        cnt, sums = handle.slice_sieve_sums(0, 200_000, 3, True)          # the fused passes run on its bitmap unchanged
+        assert (cnt, sums) == (17984, orc.c_power_sums(orc.c_primes_range(0, 200_000), [1, 2, 3]))
+    finally:
+        sieve.configure(algorithm="auto")
+        assert sieve.prime_count(10 ** 6) == 78498                         # back on the segmented sieve
+    for name in ("segmented", "basic", "b200"):
+        assert sieve.prime_count(10 ** 5, algorithm=name) == 9592
+
+
 def test_sieve_medium_vs_oracle(handle, orc):
     exp = orc.c_primes_range(0, 2 * 10 ** 8)
     got = handle.generate_primes(0, 2 * 10 ** 8).astype(np.uint64)

@@ -27,14 +27,15 @@ def test_sieve_facade_semantics_without_device():
         sieve.configure(algorithm="nope")
     with pytest.raises(ValueError, match="Unknown algorithm"):
         sieve.generate_primes(100, algorithm="nope")
-    with pytest.raises(ValueError, match="not provided"):
+    with pytest.raises(ValueError, match="primesieve requested but not installed"):   # utils/sieve.py:492-498 wording
         sieve.generate_primes(100, algorithm="primesieve")
     sieve.configure(algorithm="b200", max_memory_mb=123, prefer="gpu")
     assert sieve.get_config() == {"algorithm": "b200", "max_memory_mb": 123, "prefer": "gpu"}
     sieve.configure(algorithm="auto")
     info = sieve.get_algorithm_info()
-    assert info["b200"]["available"] and info["auto"]["available"] and not info["basic"]["available"]
-    assert sieve.get_available_algorithms() == ["auto", "b200"]
+    assert info["b200"]["available"] and info["auto"]["available"] and info["individual"]["available"]
+    assert not info["primesieve"]["available"] and set(info) == set(sieve.VALID_ALGORITHMS)
+    assert sieve.get_available_algorithms() == ["auto", "b200", "basic", "segmented", "individual"]
 
 
 def test_primesum_argument_errors_without_device():
