@@ -1587,14 +1587,20 @@ int pss_search_tri(pss_handle* h, uint64_t n_min, uint64_t n_max, uint32_t power
     const pss_stats before = stats_snapshot(h);
     const u64 bound = pss_nth_prime_upper(n_max) + 1;
     if (bound > kMaxValue) return fail(h, PSS_EINVAL, "n = %llu needs primes beyond 2^%d", (unsigned long long)n_max, PSS_MAX_PRIME_BITS);
-    PSS_TRY(sieve_range(h, 0, bound));
-    if (h->sv_total < n_max) return fail(h, PSS_EINTERNAL, "prime count bound failed");
-    PSS_TRY(bitmap_reduce(h, power, false));
-    if (m_max >= m_min && m_max >= 1) {
+    // one launch chain like pss_search: init -> sieve -> block sums -> column scan -> predicate walk -> export, one sync
+    pss_search_args ia;
+    memset(&ia, 0, sizeof ia);
+    ia.power_max = power;
+    PSS_TRY(prepare_misc(h, &ia, nullptr));
+    h->misc_uploaded = false;
+    PSS_TRY(sieve_range(h, 0, bound, true));
+    PSS_TRY(bitmap_reduce(h, power, false, true));
+    MiscDev* hm = h->h_misc;
+    const bool want = m_max >= m_min && m_max >= 1 && h->bs_n_tiles > 0;
+    CU_TRY(h, mark(h, 6));
+    if (want) {
         const u32 dev_cap = std::max<u32>(cap, 1);
         PSS_TRY(ensure(h, h->tri_buf, (size_t)dev_cap * 2 * sizeof(u64) + 16));
-        MiscDev* hm = h->h_misc;
-        memset(hm, 0, sizeof(MiscDev));
         MiscDev* dm = static_cast<MiscDev*>(h->misc.p);
         BScanParams bp;
         fill_bscan_common(h, bp);
@@ -1612,17 +1618,21 @@ int pss_search_tri(pss_handle* h, uint64_t n_min, uint64_t n_max, uint32_t power
         bp.tri_m_max = m_max;
         bp.tri_max_value = m_max * (m_max + 1) / 2;
         bp.tri_out = static_cast<u64*>(h->tri_buf.p);
-        bp.tri_count = &dm->ticket;   // reused as the match counter
+        bp.tri_count = &dm->ticket;   // reused as the match counter (zeroed by k_init_misc)
         bp.tri_cap = cap;
-        CU_TRY(h, mark(h, 4));
-        CU_TRY(h, cudaMemcpyAsync(dm, hm, sizeof(MiscDev), cudaMemcpyHostToDevice, h->stream));
         PSS_TRY(launch_bscan_tri(h, bp, power));
-        CU_TRY(h, mark(h, 5));
-        CU_TRY(h, cudaMemcpyAsync(hm, dm, sizeof(MiscDev), cudaMemcpyDeviceToHost, h->stream));
-        CU_TRY(h, cudaStreamSynchronize(h->stream));
-        h->acc.ms_power_scan += ev_ms(h, 4, 5);
-        h->acc.ms_bitmap_compare += ev_ms(h, 4, 5);
-        h->acc.primes += n_max;
+    }
+    CU_TRY(h, mark(h, 7));
+    PSS_TRY(export_results(h, 0, 0));
+    CU_TRY(h, cudaStreamSynchronize(h->stream));
+    sieve_finish(h);
+    PSS_TRY(reduce_finish(h));
+    if (h->sv_total < n_max) return fail(h, PSS_EINTERNAL, "prime count bound failed");
+    h->acc.ms_power_scan += ev_ms(h, 6, 7);
+    h->acc.ms_bitmap_compare += ev_ms(h, 6, 7);
+    h->acc.ms_span += ev_ms(h, 8, 9);
+    h->acc.primes += n_max;
+    if (want) {
         *count = hm->ticket;
         const u32 n_copy = std::min<u32>(hm->ticket, cap);
         if (n_copy) CU_TRY(h, cudaMemcpy(pairs_out, h->tri_buf.p, (size_t)n_copy * 2 * sizeof(u64), cudaMemcpyDeviceToHost));

@@ -443,7 +443,8 @@ __global__ void __launch_bounds__(kBsThreads, bs_min_blocks<K, MULTI>()) k_bitma
                 const u32 tquota = min(tcnt, t_lmax + 1u);
                 const u32 tskip = min(t_lmin, tquota);
                 const bool t_nmax = tquota > 0 && (t_n0 + tquota - 1 == P.n_max);
-                bool simple = !t_nmax && (tskip == 0 || tskip == tquota);
+                // (a window edge inside the tile does not matter: the in-window primes [tskip, tquota) are one contiguous run)
+                bool simple = !t_nmax;
                 if (simple) {
                     u32 tpre[TOTAL];
                     tile_prefix(tile, tpre);
@@ -578,7 +579,7 @@ __global__ void __launch_bounds__(kBsThreads, bs_min_blocks<K, MULTI>()) k_bitma
                 const u32 wquota = (wli0 > lmax) ? 0u : min(wcnt, lmax - wli0 + 1u);
                 const u32 wskip = (lmin > wli0) ? min(lmin - wli0, wquota) : 0u;
                 const bool holds_nmax = wquota > 0 && (tile_n0 + wli0 + wquota - 1 == P.n_max);
-                bool simple = !holds_nmax && (wskip == 0 || wskip == wquota);
+                bool simple = !holds_nmax;
                 if constexpr (MODE == kBsCompare) {
                     if (simple) {
                         u32 wend[TOTAL];
@@ -655,7 +656,8 @@ __global__ void __launch_bounds__(kBsThreads, bs_min_blocks<K, MULTI>()) k_bitma
                 }
                 // ---- interval pruning, thread level (same argument on the thread's 2880 integers)
                 bool walk = quota > 0;
-                if (!P.exhaustive && walk && !owns_nmax && (skip0 == 0 || skip0 == quota)) {
+                bool coop = false;     // this thread holds n_max and nothing else forces a per-prime walk: the warp finishes it together
+                if (!P.exhaustive && walk) {
                     if constexpr (MODE == kBsCompare) {
                         u32 end[TOTAL];
 #pragma unroll
@@ -668,7 +670,12 @@ __global__ void __launch_bounds__(kBsThreads, bs_min_blocks<K, MULTI>()) k_bitma
                         bool bracket = false;
 #pragma unroll
                         for (int jj = 0; jj < NP; ++jj) bracket = bracket || (c0[jj] < 0 && c1[jj] >= 0);
+                        // (for the thread that holds n_max the interval (S_before, S_before + whole block] is a superset of
+                        //  (S_before, S(n_max)]: no bracket there means no bracket up to n_max)
                         walk = bracket;
+                        coop = owns_nmax && !bracket;
+                    } else if (owns_nmax) {
+                        // triangular predicate: the n_max block is always walked
                     } else {
                         bool beyond = false;
 #pragma unroll
@@ -679,7 +686,74 @@ __global__ void __launch_bounds__(kBsThreads, bs_min_blocks<K, MULTI>()) k_bitma
                 }
                 a = li0 + skip0;
                 u64 last_p = 0;
-                if (__any_sync(0xFFFFFFFFu, walk)) stage();   // the bitmap is only read where a walk is needed
+                const u32 coop_mask = __ballot_sync(0xFFFFFFFFu, coop);
+                if (__any_sync(0xFFFFFFFFu, walk) || coop_mask) stage();   // the bitmap is only read where a walk is needed
+                if constexpr (MODE == kBsCompare) {
+                    if (coop_mask) {
+                        // ---- S_k(n_max) and p_(n_max) by the whole warp.  One thread of the grid holds n_max; walking its
+                        //      block alone is a serial chain of up to ~400 primes (the longest latency of a pruned query), so
+                        //      lane l takes word l of that thread: popcount prefix -> which of its primes lie at or below
+                        //      n_max -> their powers -> butterfly sum.  No per-prime compare is needed (no bracket in the block).
+                        const int owner = __ffs(coop_mask) - 1;
+                        u32 q = __shfl_sync(0xFFFFFFFFu, quota, owner);
+                        const u32 vb_lo = __shfl_sync(0xFFFFFFFFu, (u32)value_base, owner);
+                        const u32 vb_hi = __shfl_sync(0xFFFFFFFFu, (u32)(value_base >> 32), owner);
+                        const bool o_small = __shfl_sync(0xFFFFFFFFu, has_small ? 1u : 0u, owner) != 0u;
+                        u32 part[TOTAL];
+#pragma unroll
+                        for (int i = 0; i < TOTAL; ++i) part[i] = 0;
+                        BsAccFn<K, MULTI> pf{part};
+                        u64 my_last = 0;
+                        u32 ns = 0;
+                        if (o_small) {                      // 2, 3, 5 come first in that thread's sequence
+                            ns = min(P.n_small, q);
+                            if (lane == 0)
+                                for (u32 i = 0; i < ns; ++i) {
+                                    my_last = P.small_primes[i];
+                                    pf((u32)my_last, 0u);
+                                }
+                            q -= ns;
+                        }
+                        u32 w = ((int)lane < WPT) ? my_warp_words[owner * PAD + lane] : 0u;   // bit-reversed: lowest prime = top bit
+                        const u32 c = __popc(w);
+                        u32 incl = c;
+#pragma unroll
+                        for (int d = 1; d < 32; d <<= 1) {
+                            const u32 up = __shfl_up_sync(0xFFFFFFFFu, incl, d);
+                            if (lane >= (u32)d) incl += up;
+                        }
+                        const u32 pre = incl - c;
+                        const u32 take = (q > pre) ? min(c, q - pre) : 0u;
+                        const u64 vb = ((u64)vb_hi << 32) | vb_lo;
+                        for (u32 t = 0; t < take; ++t) {
+                            const u32 m = msb_index(w);
+                            w ^= (1u << m);
+                            const u64 pv = vb + 120u * lane + msb_value_offset(m);
+                            my_last = pv;
+                            pf((u32)pv, (u32)(pv >> 32));
+                        }
+#pragma unroll
+                        for (int d = 16; d >= 1; d >>= 1) {
+                            OpShflXorAdd op{part, d};
+                            for_each_power<0, Lay>(op);
+                        }
+                        // the lane whose word holds the q-th prime of the block knows p_(n_max) (lane 0 if n_max is one of 2, 3, 5)
+                        const u32 last_mask = __ballot_sync(0xFFFFFFFFu, take > 0 && pre + take == q);
+                        const int last_lane = (q > 0 && last_mask) ? (__ffs(last_mask) - 1) : 0;
+                        const u32 lp_lo = __shfl_sync(0xFFFFFFFFu, (u32)my_last, last_lane);
+                        const u32 lp_hi = __shfl_sync(0xFFFFFFFFu, (u32)(my_last >> 32), last_lane);
+                        if ((int)lane == owner) {
+                            OpAdd op{run, part};
+                            for_each_power<0, Lay>(op);
+                            *P.last_prime_out = ((u64)lp_hi << 32) | lp_lo;
+#pragma unroll
+                            for (int jj = 0; jj < NP; ++jj)
+#pragma unroll
+                                for (int i = 0; i < PSS_LIMBS; ++i)
+                                    P.results[jj].final_sum[i] = (i < Lay::width(jj)) ? run[Lay::offset(jj) + i] : 0u;
+                        }
+                    }
+                }
                 if (walk) {
                     // ---- every S_k(n) of this thread formed and compared
                     auto run_walk = [&](auto& fn) {
