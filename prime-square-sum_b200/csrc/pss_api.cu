@@ -1479,10 +1479,14 @@ int pss_search(pss_handle* h, const pss_search_args* a, pss_search_result* res) 
     memset(res, 0, sizeof *res);
     const bool multi = a->all_powers && a->power_max > 1;
     if (h->search_path == 1) {
-        // materialised path: K1c compaction into u64 primes, K2/K3 with decoupled look-back
+        // materialised path: K1c compaction into u64 primes, then tile sums + column scan + (pruned) walk over them
+        CU_TRY(h, cudaEventRecord(h->ev[8], h->stream));
         PSS_TRY(sieve_first_n(h, a->n_max));
         PSS_TRY(run_scan(h, static_cast<const u64*>(h->primes.p), a->n_max, 1, nullptr, a->power_max, multi, kModeCompare, a->n_min, a->n_max,
                          a->cmp, a->target, a->target_nlimbs, nullptr, res->powers));
+        CU_TRY(h, cudaEventRecord(h->ev[9], h->stream));
+        CU_TRY(h, cudaEventSynchronize(h->ev[9]));
+        h->acc.ms_span += ev_ms(h, 8, 9);     // includes the host synchronisations between the three stages of this path
         res->n_powers = n_powers_of(a->power_max, multi);
         res->primes_scanned = a->n_max;
         res->last_prime = h->resident_last;

@@ -364,71 +364,42 @@ __global__ void __launch_bounds__(kScanThreads) k_power_walk(const __grid_consta
     using Lay = Layout<K, MULTI>;
     constexpr int TOTAL = Lay::TOTAL, NP = Lay::NP, T = kScanThreads, NWARP = T / 32, TILE = T * ITEMS;
     static_assert(NWARP <= 32 && (NWARP & (NWARP - 1)) == 0, "warp count must be a power of two");
+    constexpr int kListCap = 64;           // tiles of one batch that need a walk (a query has a handful in total)
 
     __shared__ u64 s_p[TILE + T];          // element e lives at e + e / ITEMS (bank-conflict padding)
     __shared__ u32 s_warp[NWARP][TOTAL];   // inclusive warp totals, then exclusive warp offsets
     __shared__ u32 s_excl[TOTAL];          // tile exclusive prefix (includes carry-in)
-    __shared__ u32 s_end[TOTAL];           // tile inclusive prefix
-    __shared__ int s_c0[NP], s_c1[NP];     // three-way compares of the two with the target
+    __shared__ u32 s_list[kListCap];
+    __shared__ u32 s_nlist;
 
     const u32 tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
 
-    for (u32 tile = blockIdx.x; tile < P.n_tiles; tile += gridDim.x) {
-        const u64 base = (u64)tile * TILE;
-        // ---- tile prefix / end from the scanned columns (thread j < NP normalises power j)
-        if (tid < (u32)NP) {
-            for (int which = 0; which < 2; ++which) {
-                u32* dst = which ? s_end : s_excl;
-                u64 c = 0;
-                const u32 off = (u32)lay_offset<K, MULTI>((int)tid), w = (u32)lay_width<K, MULTI>((int)tid);
-                for (u32 i = 0; i < w; ++i) {
-                    const u64 v = P.col_prefix[(u64)(off + i) * P.col_stride + tile + which];
-                    const u64 lo = (v & 0xFFFFFFFFull) + (c & 0xFFFFFFFFull) + P.carry_in[tid * PSS_LIMBS + i];
-                    dst[off + i] = (u32)lo;
-                    c = (v >> 32) + (c >> 32) + (lo >> 32);
-                }
-                int cmp = -1;
-                if (!((P.target_over_mask >> tid) & 1u)) {
-                    cmp = 0;
-                    for (u32 i = 0; i < w; ++i)
-                        if (dst[off + i] != P.target[i]) cmp = (dst[off + i] < P.target[i]) ? -1 : 1;
-                }
-                (which ? s_c1 : s_c0)[tid] = cmp;
-            }
+    // normalised prefix (carry-in + deferred-carry column prefix) of power jj before tile `idx` (idx = n_tiles: slice end)
+    auto prefix_of = [&](u32 idx, int jj, u32* out) {
+        u64 c = 0;
+        const int off = lay_offset<K, MULTI>(jj), w = lay_width<K, MULTI>(jj);
+        for (int i = 0; i < w; ++i) {
+            const u64 v = P.col_prefix[(u64)(off + i) * P.col_stride + idx];
+            const u64 lo = (v & 0xFFFFFFFFull) + (c & 0xFFFFFFFFull) + P.carry_in[jj * PSS_LIMBS + i];
+            out[i] = (u32)lo;
+            c = (v >> 32) + (c >> 32) + (lo >> 32);
         }
-        __syncthreads();
-        const u32 tcnt = (u32)min((u64)TILE, P.count - base);
-        const u64 t_n0 = P.n_first + base;               // global index of the tile's first prime
-        if constexpr (MODE == kModeCompare) {
-            // ---- interval pruning at tile level (uniform over the CTA)
-            if (!P.exhaustive) {
-                const u64 t_last = t_n0 + tcnt - 1;
-                const bool inside = t_n0 >= P.n_min && t_last <= P.n_max, outside = t_last < P.n_min || t_n0 > P.n_max;
-                bool simple = inside || outside;
-                bool bracket = false;
-#pragma unroll
-                for (int jj = 0; jj < NP; ++jj) bracket = bracket || (s_c0[jj] < 0 && s_c1[jj] >= 0);
-                if (simple && !bracket) {
-                    if (tid == 0 && inside) {
-#pragma unroll
-                        for (int jj = 0; jj < NP; ++jj) {
-                            const bool below = s_c0[jj] < 0;      // every S of the tile compares like the tile's prefix ...
-                            const bool hit = below ? (P.cmp_mask & 1u) : (P.cmp_mask & 4u);   // ... except that "==" cannot occur
-                            if (hit) {
-                                pss_power_result* r = P.results + jj;
-                                atomicAdd(reinterpret_cast<unsigned long long*>(&r->match_count), (unsigned long long)tcnt);
-                                atomicMin(reinterpret_cast<unsigned long long*>(&r->first_match_n), (unsigned long long)t_n0);
-                                atomicMax(reinterpret_cast<unsigned long long*>(&r->last_match_n), (unsigned long long)t_last);
-                            }
-                        }
-                    }
-                    __syncthreads();      // s_excl / s_c0 are rewritten by the next tile
-                    continue;
-                }
-            }
-        }
+    };
+    auto cmp_target = [&](const u32* a, int jj) -> int {
+        if ((P.target_over_mask >> jj) & 1u) return -1;
+        int r = 0;
+        const int w = lay_width<K, MULTI>(jj);
+        for (int i = 0; i < w; ++i)
+            if (a[i] != P.target[i]) r = (a[i] < P.target[i]) ? -1 : 1;
+        return r;
+    };
 
-        // ---- coalesced load -> padded shared memory (blocked order for the owner threads)
+    // ---- the full walk of one tile by the whole CTA
+    auto walk_tile = [&](u32 tile) {
+        const u64 base = (u64)tile * TILE;
+        const u64 t_n0 = P.n_first + base;               // global index of the tile's first prime
+        if (tid < (u32)NP) prefix_of(tile, (int)tid, s_excl + lay_offset<K, MULTI>((int)tid));
+        // coalesced load -> padded shared memory (blocked order for the owner threads)
 #pragma unroll
         for (int r = 0; r < ITEMS; ++r) {
             const u32 e = r * T + tid;
@@ -437,7 +408,7 @@ __global__ void __launch_bounds__(kScanThreads) k_power_walk(const __grid_consta
         }
         __syncthreads();
 
-        // ---- pass 1: thread-local sums of p^k
+        // pass 1: thread-local sums of p^k
         u32 acc[TOTAL];
 #pragma unroll
         for (int i = 0; i < TOTAL; ++i) acc[i] = 0;
@@ -446,7 +417,7 @@ __global__ void __launch_bounds__(kScanThreads) k_power_walk(const __grid_consta
 #pragma unroll 2
             for (int i = 0; i < ITEMS; ++i) power_chain<K, MULTI>(s_p[tid * (ITEMS + 1) + i], fn);
         }
-        // ---- warp inclusive scan (multi-limb adds with carry), exclusive value for this lane
+        // warp inclusive scan (multi-limb adds with carry), exclusive value for this lane
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) {
             OpShflUpAdd op{acc, d, lane >= (u32)d};
@@ -480,7 +451,7 @@ __global__ void __launch_bounds__(kScanThreads) k_power_walk(const __grid_consta
         }
         __syncthreads();
 
-        // ---- pass 2: exact exclusive prefix of this thread, then every S_k(n) formed and compared / written
+        // pass 2: exact exclusive prefix of this thread, then every S_k(n) formed and compared / written
         {
             OpAdd op1{run, s_excl};
             for_each_power<0, Lay>(op1);
@@ -530,6 +501,78 @@ __global__ void __launch_bounds__(kScanThreads) k_power_walk(const __grid_consta
             }
         }
         __syncthreads();   // shared memory is reused by the next tile
+    };
+
+    if (MODE != kModeCompare || P.exhaustive) {
+        for (u32 tile = blockIdx.x; tile < P.n_tiles; tile += gridDim.x) walk_tile(tile);
+        return;
+    }
+
+    // ---- compare mode with interval pruning.  S_k is strictly increasing, so a tile whose sum interval (S_before, S_after]
+    // does not contain the target for any power, and that lies entirely inside (or outside) the window, compares like its
+    // prefix: its matches are known without loading a prime.  The test needs only the scanned columns, so EVERY THREAD
+    // tests one tile (256 tiles per CTA step, all loads independent); the few tiles that do need a walk — the one bracketing
+    // the target, the ones cut by the window — are listed in shared memory and walked by the whole CTA afterwards.
+    for (u32 batch = blockIdx.x * T; batch < P.n_tiles; batch += gridDim.x * T) {
+        if (tid == 0) s_nlist = 0;
+        __syncthreads();
+        const u32 tile = batch + tid;
+        u64 mc[NP], mf[NP], ml[NP];
+#pragma unroll
+        for (int jj = 0; jj < NP; ++jj) mc[jj] = 0, mf[jj] = ~0ull, ml[jj] = 0;
+        if (tile < P.n_tiles) {
+            const u64 base = (u64)tile * TILE;
+            const u32 tcnt = (u32)min((u64)TILE, P.count - base);
+            const u64 t_n0 = P.n_first + base, t_last = t_n0 + tcnt - 1;
+            const bool inside = t_n0 >= P.n_min && t_last <= P.n_max, outside = t_last < P.n_min || t_n0 > P.n_max;
+            bool need_walk = !(inside || outside);
+            int c0[NP];
+#pragma unroll
+            for (int jj = 0; jj < NP; ++jj) {
+                u32 a[PSS_LIMBS];
+                prefix_of(tile, jj, a);
+                c0[jj] = cmp_target(a, jj);
+                prefix_of(tile + 1, jj, a);
+                need_walk = need_walk || (c0[jj] < 0 && cmp_target(a, jj) >= 0);
+            }
+            if (need_walk) {
+                const u32 slot = atomicAdd(&s_nlist, 1u);
+                if (slot < (u32)kListCap) s_list[slot] = tile;
+            } else if (inside) {
+#pragma unroll
+                for (int jj = 0; jj < NP; ++jj) {
+                    // every S of the tile compares like the tile's prefix ("==" cannot occur inside it)
+                    const bool hit = (c0[jj] < 0) ? (P.cmp_mask & 1u) : (P.cmp_mask & 4u);
+                    if (hit) mc[jj] = tcnt, mf[jj] = t_n0, ml[jj] = t_last;
+                }
+            }
+        }
+#pragma unroll
+        for (int jj = 0; jj < NP; ++jj) {
+            if (__any_sync(0xFFFFFFFFu, mc[jj] != 0)) {
+                u64 c = mc[jj], f = mf[jj], l = ml[jj];
+#pragma unroll
+                for (int d = 16; d >= 1; d >>= 1) {
+                    c += __shfl_xor_sync(0xFFFFFFFFu, c, d);
+                    f = min(f, __shfl_xor_sync(0xFFFFFFFFu, f, d));
+                    l = max(l, __shfl_xor_sync(0xFFFFFFFFu, l, d));
+                }
+                if (lane == 0) {
+                    pss_power_result* r = P.results + jj;
+                    atomicAdd(reinterpret_cast<unsigned long long*>(&r->match_count), (unsigned long long)c);
+                    atomicMin(reinterpret_cast<unsigned long long*>(&r->first_match_n), (unsigned long long)f);
+                    atomicMax(reinterpret_cast<unsigned long long*>(&r->last_match_n), (unsigned long long)l);
+                }
+            }
+        }
+        __syncthreads();
+        const u32 n_list = s_nlist;
+        if (n_list > (u32)kListCap) {      // cannot happen for a monotone S (at most 2 + NP tiles of a query need a walk): fail loudly
+            if (tid == 0) atomicExch(P.error_flag, 4u);
+        } else {
+            for (u32 i = 0; i < n_list; ++i) walk_tile(s_list[i]);
+        }
+        __syncthreads();
     }
 }
 

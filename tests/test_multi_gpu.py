@@ -28,3 +28,9 @@ def test_peer_and_nccl_exchange_match_single_gpu(world):
     p = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     assert p.returncode == 0, p.stdout[-3000:] + p.stderr[-3000:]
     assert "mismatches=0" in p.stdout
+    summary = [line for line in p.stdout.splitlines() if line.startswith("PEER_WORKER")]
+    print("\n".join(summary))
+    out_dir = os.path.join(ROOT, "gpurun_out")          # kept next to the other GPU-run artefacts (copied to profiles/)
+    if os.path.isdir(out_dir):
+        with open(os.path.join(out_dir, f"peer_worker_{world}.log"), "w") as f:
+            f.write(f"world={world}\n" + "\n".join(summary) + "\n")

@@ -84,7 +84,8 @@ def main():
     pairs = {"k_sieve": ["k_sieve"], "k_bitmap_moments2+k_scan_columns": ["k_bitmap_moments2", "k_scan_columns"],
              "k_bitmap_scan<compare>": ["k_bitmap_scan<2, 0, 1>"], "k_bitmap_scan<reduce>+k_scan_columns": ["k_bitmap_scan<2, 0, 0>", "k_scan_columns"],
              "k_bitmap_moments_tab+k_scan_columns": ["k_bitmap_moments_tab<5, 1>", "k_scan_columns"],
-             "k_compact": ["k_compact"]}
+             "k_compact": ["k_compact"], "k_compact_lut": ["k_compact_lut"],
+             "k_power_tiles+k_scan_columns+k_power_walk": ["k_power_tiles<2, 0, 16>", "k_scan_columns", "k_power_walk<2, 0, 1, 16>"]}
     for label, names in pairs.items():
         ks = [tot(n) for n in names]
         if any(k is None for k in ks):
@@ -92,6 +93,18 @@ def main():
         rd = sum(k.get("dram_read_bytes", 0) for k in ks)
         wr = sum(k.get("dram_write_bytes", 0) for k in ks)
         traffic[label] = {"dram_bytes_per_launch": int(rd + wr), "dram_read": int(rd), "dram_write": int(wr)}
+    sv = tot("k_sieve")
+    if sv and sv.get("shared_atomic_instructions"):
+        traffic["k_sieve_counters"] = {
+            "shared_atomic_warp_instructions": int(sv["shared_atomic_instructions"]),
+            "shared_atomic_wavefronts": int(sv.get("shared_atomic_wavefronts", 0)),
+            "wavefronts_per_atomic": round(sv.get("shared_atomic_wavefronts", 0) / sv["shared_atomic_instructions"], 3),
+            "shared_wavefronts_total": int(sv.get("shared_wavefronts", 0)),
+            "bank_conflict_wavefronts": int(sv.get("shared_bank_conflicts", 0)),
+            "bank_conflict_share_of_shared_wavefronts": round(sv.get("shared_bank_conflicts", 0) / max(sv.get("shared_wavefronts", 1), 1), 3),
+            "l1tex_throughput_pct": sv.get("l1tex_throughput_pct"), "issue_active_pct": sv.get("issue_active_pct"),
+            "warp_instructions": int(sv.get("warp_instructions", 0)),
+            "source": os.path.relpath(out, root) + " (one C3 launch, ncu --set full)"}
     tp = os.path.join(root, "profiles", "ncu_traffic.json")
     old = {}
     if os.path.exists(tp):

