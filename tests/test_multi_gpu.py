@@ -34,3 +34,26 @@ def test_peer_and_nccl_exchange_match_single_gpu(world):
     if os.path.isdir(out_dir):
         with open(os.path.join(out_dir, f"peer_worker_{world}.log"), "w") as f:
             f.write(f"world={world}\n" + "\n".join(summary) + "\n")
+
+
+def test_two_handles_on_two_devices_in_one_process():
+    """kernel attributes (opt-in shared memory) and occupancy are per device; a second handle on another GPU of
+    the same process must sieve, compact and search like the first"""
+    if _gpu_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    sys.path.insert(0, os.path.join(ROOT, "prime-square-sum_b200"))
+    from pss_b200 import _lib, search
+    h0, h1 = _lib.Handle(0), _lib.Handle(1)
+    try:
+        assert "sm_10" in h0.device_info() and "sm_10" in h1.device_info()
+        for h in (h1, h0, h1):
+            assert h.count_primes(0, 10 ** 8) == 5761455
+            assert int(h.generate_n_primes(100000)[-1]) == 1299709
+            o = search.search(666, 10 ** 6, power=2, handle=h)
+            assert o.first() == (7, 2) and o.last_prime == 15485863
+        h0.set_search_path(True)
+        assert search.search(8944, 10 ** 5, power=3, handle=h0).first() == (7, 3)
+        assert search.search(8944, 10 ** 5, power=3, handle=h1).first() == (7, 3)
+    finally:
+        h0.close()
+        h1.close()
