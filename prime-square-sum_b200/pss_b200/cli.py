@@ -8,7 +8,8 @@ copied into this package), installs a handful of run-time hooks, and then hands 
   --algorithm sieve:b200       "b200" is appended to utils.sieve.VALID_ALGORITHMS (:56-62), so the CLI accepts it
                                (prime-square-sum.py:562-573) and config.json `algorithms.sieve: "b200"` (:546-550) works
   --prefer gpu                 with the algorithm left on "auto", selects the b200 variant (the reference stores the
-                               preference and never reads it: SURVEY §0.3)
+                               preference and never reads it: SURVEY §0.3); with --algorithm sieve:individual it selects
+                               the trial-division variant as a device kernel
   generate_primes / generate_primes_range / generate_n_primes / nth_prime / prime_count   (utils/sieve.py:440-641)
                                dispatch to pss_b200.sieve when the b200 variant is selected — also through the names
                                other reference modules imported (`from utils.sieve import generate_n_primes`)
@@ -66,12 +67,18 @@ class Hooks:
         self.rs = sys.modules["utils.sieve"]
         self.fast_queries = 0            # expressions answered by the fused device search (for tests / -v output)
 
-    def selected(self, algorithm: Optional[str] = None) -> bool:
+    def selected(self, algorithm: Optional[str] = None) -> Optional[str]:
+        """the pss_b200.sieve variant in force ("b200" / "individual"), or None when the call belongs to the reference"""
         if self.no_gpu:
-            return False
+            return None
         cfg = self.rs.get_config()
         algo = algorithm if algorithm not in (None, "auto") else cfg.get("algorithm", "auto")
-        return algo == ALGORITHM_B200 or (algo == "auto" and cfg.get("prefer") == "gpu")
+        gpu = cfg.get("prefer") == "gpu"
+        if algo == ALGORITHM_B200 or (algo == "auto" and gpu):
+            return ALGORITHM_B200
+        if algo == "individual" and gpu:
+            return "individual"          # --algorithm sieve:individual --prefer gpu: the trial-division variant as a device kernel
+        return None
 
     # ---- rebinding: a reference module that did `from utils.sieve import f` holds its own reference to f
     @staticmethod
@@ -94,8 +101,9 @@ class Hooks:
             ref_fn, dev_fn = getattr(rs, name), getattr(b_sieve, name)
 
             def dispatch(*args, **kwargs):
-                if self.selected(pick_algorithm(args, kwargs)):
-                    return dev_fn(*args[:pick_algorithm.n_positional], **{k: v for k, v in kwargs.items() if k in pick_algorithm.keep})
+                variant = self.selected(pick_algorithm(args, kwargs))
+                if variant:
+                    return dev_fn(*args[:pick_algorithm.n_positional], algorithm=variant)
                 return ref_fn(*args, **kwargs)
 
             dispatch.__name__, dispatch.__doc__ = ref_fn.__name__, ref_fn.__doc__
