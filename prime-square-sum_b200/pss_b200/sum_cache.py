@@ -86,36 +86,40 @@ def _host_add(cache, prime: int) -> None:
     cache._checkpoint_counter = getattr(cache, "_checkpoint_counter", 0) + 1
 
 
+def _pass_groups(powers: Sequence[int]):
+    """device passes that cover `powers`: [(power_max, all_powers, [k carried by the pass])].  Several powers <= 6 share one
+    all-powers pass (which carries every k in 1..max); a single one, and every k in 7..8, gets a single-power pass."""
+    pos = sorted({int(k) for k in powers if k > 0})
+    low = [k for k in pos if k <= 6]
+    groups = []
+    if len(low) == 1:
+        groups.append((low[0], False, low))
+    elif low:
+        groups.append((low[-1], True, list(range(1, low[-1] + 1))))
+    groups += [(k, False, [k]) for k in pos if k > 6]
+    return groups
+
+
 def _device_sums_to(h: "_lib.Handle", have: int, last_prime: Optional[int], n: int, powers: Sequence[int],
                     carry: Dict[int, int]):
-    """S_k(n) for every k in `powers` and p_n, continuing from (have, last_prime, carry): one sieve of
-    (last_prime, bound) + one block-sum pass + one truncating scan per group of powers"""
+    """S_k(n) for every k in `powers` and p_n, continuing from (have, last_prime, carry): per group of powers one sieve of
+    (last_prime, bound) + one block-sum pass + one truncating scan"""
     lo = (int(last_prime) + 1) if have else 0
     hi = h.nth_prime_upper(n) + 1
     out: Dict[int, int] = {}
     p_n = None
-    pos = sorted({int(k) for k in powers if k > 0})
-    groups = []
-    if pos:
-        multi_top = max((k for k in pos if k <= 6), default=0)
-        if multi_top:
-            groups.append((multi_top, True, [k for k in pos if k <= multi_top]))
-        groups += [(k, False, [k]) for k in pos if k > 6]
-    for top, allp, wanted in groups:
+    for top, allp, ks in _pass_groups(powers):
         cnt, _ = h.slice_sieve_sums(lo, hi, top, allp)
         if cnt < n - have:
             raise RuntimeError("prime count bound violated")
-        ks = list(range(1, top + 1)) if (allp and top > 1) else [top]
-        res = h.slice_scan_bitmap(have + 1, [carry.get(k, 0) for k in ks], have + 1, n, top, 0, "<", allp)
+        res = h.slice_scan_bitmap(have + 1, [carry[k] if have else 0 for k in ks], have + 1, n, top, 0, "<", allp)
         p_n = int(res.last_prime)
         for j, k in enumerate(ks):
-            if k in wanted:
-                out[k] = _lib.limbs_to_int(res.powers[j].final_sum)
+            out[k] = _lib.limbs_to_int(res.powers[j].final_sum)
     if p_n is None:                      # only power 0 tracked: p_n is still needed for the state
         p_n = h.nth_prime(n)
-    for k in powers:
-        if k == 0:
-            out[0] = carry.get(0, 0) + (n - have)
+    if 0 in powers:
+        out[0] = carry.get(0, 0) + (n - have)
     return out, p_n
 
 
@@ -137,16 +141,13 @@ def advance(cache, n: int, handle: Optional["_lib.Handle"] = None):
     if n <= have:
         return cache
     h = handle or _lib.default_handle()
-    missing = [k for k in md.powers if k > 0 and k - 1 not in md.powers]     # S_(k) of lower powers the carry lacks
-    carry = {int(k): int(cache.sums[k]) for k in md.powers}
     want = sorted({int(k) for k in md.powers})
-    if missing and any(0 < k <= 6 for k in want):
-        # the all-powers pass scans 1..top together: lower powers that are not tracked need their own carry
-        top = max(k for k in want if k <= 6)
-        lacking = [k for k in range(1, top + 1) if k not in carry]
-        if lacking and have:
-            prev, _ = _device_sums_to(h, 0, None, have, lacking, {})
-            carry.update(prev)
+    carry = {int(k): int(cache.sums[k]) for k in md.powers}
+    # an all-powers pass scans 1..max together: lower powers the cache does not track need their own carry S_k(have)
+    lacking = sorted({k for _, _, ks in _pass_groups(want) for k in ks} - set(carry))
+    if lacking:
+        prev, _ = _device_sums_to(h, 0, None, have, lacking, dict.fromkeys(lacking, 0))
+        carry.update(prev)
     sums, p_n = _device_sums_to(h, have, md.last_prime, n, want, carry)
     # diagnostics tail: the last rows the per-prime path would have left (needs the last few primes)
     tail_primes = [int(x) for x in h.generate_primes(max(0, p_n - 4096), p_n + 1)[-_TAIL_ROWS:]]
