@@ -293,11 +293,22 @@ def li(x: float) -> float:
     return x / lx * (1.0 + s)
 
 
-# Cost model behind the slice cuts (measured on B200, profiles/r01): the block-sum and compare passes cost is proportional to
-# the slice's prime count, the sieve's to its width times a slowly growing per-integer factor (more base
-# primes are active in higher tiles: ~ (x/N)^0.12); for the whole C3 range sieve : scans = 3.7 : 1 (2.13 ms : 0.57 ms).
-SIEVE_WEIGHT = 3.7
-SIEVE_EXPONENT = 0.12
+# Cost model behind the slice cuts (measured on B200, profiles/r01 and profiles/r02): the sieve's time is proportional to the
+# slice's width times a slowly growing per-integer factor (more base primes are active in higher tiles: ~ (x/N)^0.12).  The
+# block-sum pass works per bitmap WORD (byte-table moments), so it is proportional to the width too — not to the prime count:
+# the 8-GPU timeline of round 2 showed rank 0 (the densest primes, hence the widest slice under a prime-count model) with the
+# longest block-sum pass.  Fit to that timeline (profiles/r02/bench_c3_v18_n8_timeline.json): sieve time per unit width
+# = 2.565 (x/N)^0.0925 ms, block sums (k = 2) 0.51 ms per unit width, i.e. cost(f) = f + 4.6 f^1.0925 up to a constant factor;
+# the all-powers block sums cost 1.28 / 0.36 times the k = 2 ones.
+SIEVE_WEIGHT = 4.6
+SIEVE_EXPONENT = 0.0925
+
+
+def sieve_weight_for(power: int, all_powers: bool) -> float:
+    """sieve : block-sum cost ratio of a query configuration (see the fit above)"""
+    if all_powers and power > 1:
+        return SIEVE_WEIGHT * 0.36 / (0.36 + (1.28 - 0.36) * (power - 1) / 4.0)
+    return SIEVE_WEIGHT if power == 2 else 2.7
 
 
 def partition_range(hi_excl: int, parts: int, lo: int = 0, sieve_weight: float = SIEVE_WEIGHT,
@@ -307,15 +318,18 @@ def partition_range(hi_excl: int, parts: int, lo: int = 0, sieve_weight: float =
 
 @functools.lru_cache(maxsize=64)
 def _partition_range(hi_excl: int, parts: int, lo: int, sieve_weight: float, sieve_exponent: float) -> Tuple[Tuple[int, int], ...]:
-    """Cut [lo, hi_excl) into `parts` contiguous slices of ~equal estimated device time
-    (sieve_weight = 0: equal prime counts); interior cuts are multiples of 480 (16 bitmap bytes) so every
-    slice starts on a 16-byte aligned bitmap byte."""
+    """Cut [lo, hi_excl) into `parts` contiguous slices of ~equal estimated device time; sieve_weight = 0 gives equal
+    (li(x)-estimated) prime counts instead.  Interior cuts are multiples of 480 (16 bitmap bytes) so every slice starts
+    on a 16-byte aligned bitmap byte."""
     if parts <= 1 or hi_excl - lo < 480 * parts * 4:
         return tuple([(lo, hi_excl)] + [(hi_excl, hi_excl)] * (parts - 1))
-    pi_est = li(hi_excl)
 
-    def cost(x: float) -> float:
-        return li(x) + sieve_weight * pi_est * (max(x, 0.0) / hi_excl) ** (1.0 + sieve_exponent)
+    if sieve_weight == 0.0:
+        cost = li
+    else:
+        def cost(x: float) -> float:
+            f = max(x, 0.0) / hi_excl
+            return f + sieve_weight * f ** (1.0 + sieve_exponent)
 
     total = cost(hi_excl) - cost(lo)
     cuts = [lo]
@@ -391,7 +405,7 @@ def distributed_search(target: int, n_max: int, power: int = 2, n_min: int = 1, 
         return search(target, n_max, power, n_min, op, all_powers, handle=h)
 
     hi = h.nth_prime_upper(n_max) + 1
-    lo_g, hi_g = partition_range(hi, world)[rank]
+    lo_g, hi_g = partition_range(hi, world, sieve_weight=sieve_weight_for(power, all_powers))[rank]
     np_ = _np(power, all_powers)
     if gather is None and _peer_exchange_enabled(group):
         return _peer_search(h, group, rank, world, lo_g, hi_g, target, n_max, power, n_min, op, all_powers, np_)
