@@ -494,7 +494,7 @@ int sieve_range(pss_handle* h, u64 lo, u64 hi, bool defer_sync = false) {
         // per tile: how many base primes satisfy p*p < tile end (tiny device kernel, no host work)
         // (the table only depends on the geometry; PSS_NACT_CACHE=1 reuses it for a repeated query instead of launching again)
         const u64 nact_key[6] = {B_start, tile_bytes, hi, n_tiles, sp.n_base, h->base_first_prime};
-        static const bool nact_cache = env_u32("PSS_NACT_CACHE", 0) != 0;   // off: see the 8-GPU A/B in DESIGN.md section 5
+        static const bool nact_cache = env_u32("PSS_NACT_CACHE", 1) != 0;   // a repeated geometry reuses the table (one launch less per query)
         if (!nact_cache || memcmp(nact_key, h->nact_key, sizeof nact_key) != 0 || !h->tile_nact.p) {
             PSS_TRY(ensure(h, h->tile_nact, (size_t)n_tiles * sizeof(u32)));
             k_tile_nact<<<(n_tiles + 255) / 256, 256, 0, h->stream>>>(sp.base_p, sp.n_base, B_start, tile_bytes, hi, n_tiles,
