@@ -68,6 +68,8 @@ WORKLOADS = {
 EXTRA = ["C5", "C4_k3", "C4_k4", "C4_k5", "C2"]
 IMAD_PER_PRIME = {1: 0, 2: 4, 3: 10, 4: 18, 5: 28}   # IMAD.WIDE of the per-prime power chain
 MISC_BYTES = 2016   # sizeof(MiscDev): ticket/flag + 8 result records + carry limbs + timeline stamps, one H2D and one D2H per scan
+MISC_INIT_BYTES = 424   # sizeof(MiscInit): by-value argument of k_init_misc
+PEER_RESULT_BYTES = 1792   # sizeof(PeerResult): one rank's outcome record
 SMS = 148
 
 
@@ -607,8 +609,12 @@ def main():
         "config": workload_config(main_name, world),
         "clocks": clocks,
         "e2e": {"value": main_d["e2e"]["value"], "unit": "primes/s", "ms_per_step": main_d["e2e"]["ms_per_step"],
-                "h2d_bytes_per_step": (MISC_BYTES + 4 * 11) * (2 if world > 1 else 1),
-                "d2h_bytes_per_step": (MISC_BYTES + 8 + 8 + 4) * (2 if world > 1 else 1),
+                # host -> device: the query travels as by-value kernel arguments (result-record init + carry limbs of k_init_misc,
+                # target limbs / window / operator of the compare kernel); device -> host: the result block, the column totals
+                # and (N > 1) every rank's outcome record, stored by k_export into mapped pinned host memory
+                "h2d_bytes_per_step": MISC_INIT_BYTES + 4 * 12 + 40,
+                "d2h_bytes_per_step": MISC_BYTES + 8 * (1 + 4) + (PEER_RESULT_BYTES * world if world > 1 else 0),
+                "transport": "kernel arguments in, zero-copy stores into mapped pinned memory out (no copy-engine operation in the chain)",
                 "api": "pss_b200.search.search -> ctypes -> pss_search (host args, host results)"},
         "gpu_launches": main_d["gpu_launches"],
         "roofline": roofline,
