@@ -315,6 +315,33 @@ def test_synthetic_hits_and_brackets(handle, orc, k, multi, search_path):
         assert got == exp, op
 
 
+def test_window_edges_at_every_level(handle, orc, search_path):
+    """[n_min, n_max] windows whose edges fall inside scan tiles, warp tiles and thread blocks (several tiles deep): with
+    interval pruning a window edge does not force a walk, so the match counts come from the emission arithmetic of all
+    three levels; checked in closed form ('<' of a huge target / '>' of 0 match the whole window) and against the oracle's
+    prefix sums for a crossing inside the window"""
+    from pss_b200 import search
+    n_top = 420_000                      # ~6.1e6 integers: 8 scan tiles of the fused path, 100+ tiles of the materialised one
+    primes = orc.c_first_n_primes(n_top)
+    for k, multi in ((2, False), (3, True)):
+        sums = orc.c_prefix_sums(primes, k)
+        for n_min, n_max in [(1, n_top), (2, 3), (4, 4), (777, 100_003), (61_234, 61_235), (59_999, 300_001), (200_000, n_top - 1),
+                             (n_top, n_top), (123_456, 123_456 + 4096), (4097, 8 * 4096)]:
+            w = n_max - n_min + 1
+            for op, target in (("<", 10 ** 80), (">", 0), ("!=", 1)):
+                o = search.search(target, n_max, power=k, n_min=n_min, op=op, all_powers=multi)
+                for po in o.powers:
+                    assert (po.match_count, po.first_match_n, po.last_match_n) == (w, n_min, n_max), (k, multi, n_min, n_max, op, po.power)
+                assert o.last_prime == int(primes[n_max - 1]) and o.powers[-1].final_sum == sums[n_max - 1]
+            hit = (n_min + n_max) // 2
+            o = search.search(sums[hit - 1], n_max, power=k, n_min=n_min, op=">=", all_powers=multi)
+            po = o.powers[-1]
+            assert (po.match_count, po.first_match_n, po.last_match_n, po.cross_n) == (n_max - hit + 1, hit, n_max, hit)
+            o = search.search(sums[hit - 1], n_max, power=k, n_min=n_min, op="<", all_powers=multi)
+            po = o.powers[-1]
+            assert po.match_count == hit - n_min and (po.match_count == 0 or (po.first_match_n, po.last_match_n) == (n_min, hit - 1))
+
+
 def test_trisum666_configs_small(handle, orc, search_path):
     """config C1 and the C3/C4 shape at a size the oracle finishes in seconds: no match, bracket = n_max"""
     from pss_b200 import search
