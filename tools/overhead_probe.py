@@ -1,5 +1,8 @@
+#!/usr/bin/env python
+"""Host-side overhead of a query: wall clock per call through pss_b200.search.search and through the raw ctypes call against the
+device span (first launch -> end of the last kernel) and the kernels' own time, for tiny and small ranges (run on the GPU box)."""
 import os, sys, time
-sys.path.insert(0, "/root/repo/prime-square-sum_b200")
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "prime-square-sum_b200"))
 from pss_b200 import _lib, search
 h = _lib.default_handle()
 T = 37005443752611483714216385166550857181329086284892731078593232926279977894581784762614450464857290
