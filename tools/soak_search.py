@@ -32,7 +32,8 @@ def run(mode, *a, **kw):
 
 t0, n_cases, bad = time.time(), 0, 0
 while time.time() - t0 < budget:
-    n_max = rng.choice([rng.randint(1, 40), rng.randint(1, 5000), rng.randint(1, 10 ** 6), rng.randint(1, 2 * 10 ** 7)])
+    n_max = rng.choice([rng.randint(1, 40), rng.randint(1, 5000), rng.randint(1, 10 ** 6), rng.randint(1, 2 * 10 ** 7)] +
+                       ([rng.randint(10 ** 8, 10 ** 9)] if rng.random() < 0.02 else []))
     power = rng.randint(1, 8)
     allp = power <= 6 and power > 1 and rng.random() < 0.4
     op = rng.choice(["==", "==", ">=", "<", "!=", "<=", ">"])
