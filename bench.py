@@ -7,8 +7,8 @@ A "step" is one complete pass of the hot path over one workload.  The headline w
     C3:  does_exist primesum(n,2) == trisum(666), n in [1, 1e9]        (BASELINE.json configs[2])
 i.e. sieve [0, 2.28e10) into the wheel-30 bitmap -> exact sums of p^2 per 2880-integer block, warp tile and scan
 tile -> grid-level prefix scan -> compare against the 325-bit target (the block whose exact sum interval brackets
-the target and the block holding n_max are walked prime by prime; every other block compares like its prefix
-because S(n) is strictly increasing) -> match / bracket record.  Inputs are only the query parameters: nothing
+the target is walked prime by prime, the block holding n_max is summed by its warp; every other block compares like
+its prefix because S(n) is strictly increasing) -> match / bracket record.  Inputs are only the query parameters: nothing
 is pre-computed or cached between steps (bitmap and block records are rewritten every step; both are far larger
 than L2).  The same JSON line carries, timed with the same --steps / --warmup:
     extra_workloads   C5 (all powers 1..5, n <= 1e9, window n >= 5e7), C4_k3 / C4_k4 / C4_k5 (the wide-limb ranges),
