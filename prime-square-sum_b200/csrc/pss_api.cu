@@ -184,6 +184,23 @@ struct pss_handle {
     // attribute belong to the handle's device (a process may hold handles on several GPUs)
     std::unordered_map<const void*, int> occ_map;
 
+    // CUDA graph of the single-GPU query chain (pss_search, fused path).  Keyed by the chain's GEOMETRY (range, power
+    // configuration, tuning, buffer generation): a query with the same geometry replays the instantiated graph with the
+    // compare kernel's argument (target, window, operator) updated in place -- one driver call instead of ten.
+    int use_graph = 1;                   // PSS_GRAPH=0: always launch kernel by kernel
+    bool dry = false;                    // bookkeeping pass of a replay: launches, memsets and event records are skipped
+    bool capturing = false;              // the stream is being captured: timing events become external event nodes
+    cudaGraph_t g_graph = nullptr;       // kept alive: node handles of the template graph address the nodes of g_exec
+    cudaGraphExec_t g_exec = nullptr;
+    cudaGraphNode_t g_cmp_node = nullptr;
+    bool dry_miss = false;               // the dry pass met a launch that is not part of the captured chain
+    cudaKernelNodeParams g_cmp_params = {};   // the compare node as captured (function, grid, block, shared memory)
+    std::vector<u64> g_key, g_seen_key;  // geometry of the instantiated graph / of the previous kernel-by-kernel query
+    u64 g_kernels = 0;                   // kernel nodes in the graph (launch counter)
+    u64 alloc_generation = 0;            // bumped whenever a device buffer or a staged table changes
+    BScanParams g_cmp_args;              // argument of the current query's compare launch
+    const void* g_cmp_func = nullptr;
+
     cudaEvent_t ev[10] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};   // [8], [9]: first / last launch of a query chain
     u64 launches = 0;
     pss_stats acc = {};          // accumulated per-kernel device time since pss_stats_reset
@@ -220,6 +237,7 @@ int fail(pss_handle* h, int code, const char* fmt, ...) {
 
 int ensure(pss_handle* h, DevBuf& b, size_t bytes) {
     if (bytes <= b.cap) return PSS_OK;
+    h->alloc_generation++;
     if (b.p) {
         CU_TRY(h, cudaStreamSynchronize(h->stream));
         CU_TRY(h, cudaFree(b.p));
@@ -261,7 +279,11 @@ u64 isqrt_u64(u64 x) {
 //   0  none        1 (default)  the sieve only ([0], [1]: the dominant kernel of every query)        2  every kernel
 // pss_set_kernel_events / PSS_KERNEL_EVENTS select the level; times of events that were not recorded read 0.
 bool ev_on(const pss_handle* h, int i) { return i >= 8 || h->kernel_events >= 2 || (h->kernel_events == 1 && i <= 1); }
-cudaError_t mark(pss_handle* h, int i) { return ev_on(h, i) ? cudaEventRecord(h->ev[i], h->stream) : cudaSuccess; }
+cudaError_t mark(pss_handle* h, int i) {
+    if (h->dry || !ev_on(h, i)) return cudaSuccess;
+    if (h->capturing) return i >= 8 ? cudaSuccess : cudaEventRecordWithFlags(h->ev[i], h->stream, cudaEventRecordExternal);
+    return cudaEventRecord(h->ev[i], h->stream);
+}
 
 double ev_ms(pss_handle* h, int a, int b) {
     if (!ev_on(h, a) || !ev_on(h, b)) return 0.0;
@@ -290,6 +312,7 @@ int ensure_base_primes(pss_handle* h, u64 hi) {
             if (!comp[i]) h->h_base.push_back((u32)i);
         h->base_limit = limit;
         h->base_first_prime = 0;   // force re-upload
+        h->alloc_generation++;
     }
     if (h->base_first_prime != first) {
         auto it = std::lower_bound(h->h_base.begin(), h->h_base.end(), first);
@@ -385,6 +408,7 @@ int sieve_occupancy(pss_handle* h, u32 threads, u32 tile_bytes, int* occ) {
 
 template <int THREADS>
 int launch_sieve(pss_handle* h, const SieveParams& sp, u32 grid) {
+    if (h->dry) return PSS_OK;
     if (sp.prof && THREADS == 1024) {
         k_sieve<1024, true><<<grid, 1024, (size_t)sp.tile_bytes + kSieveScratchBytes, h->stream>>>(sp);
     } else {
@@ -488,6 +512,7 @@ int sieve_range(pss_handle* h, u64 lo, u64 hi, bool defer_sync = false) {
                 CU_TRY(h, cudaStreamSynchronize(h->stream));   // the previous table may still be in use
                 CU_TRY(h, cudaMemcpy(h->d_batch_geo.p, geo.data(), geo.size() * sizeof(u32), cudaMemcpyHostToDevice));
                 h->h_batch_geo.swap(geo);
+                h->alloc_generation++;
             }
             sp.batch_geo = static_cast<const u32*>(h->d_batch_geo.p);
         }
@@ -497,8 +522,11 @@ int sieve_range(pss_handle* h, u64 lo, u64 hi, bool defer_sync = false) {
         static const bool nact_cache = env_u32("PSS_NACT_CACHE", 1) != 0;   // a repeated geometry reuses the table (one launch less per query)
         if (!nact_cache || memcmp(nact_key, h->nact_key, sizeof nact_key) != 0 || !h->tile_nact.p) {
             PSS_TRY(ensure(h, h->tile_nact, (size_t)n_tiles * sizeof(u32)));
-            k_tile_nact<<<(n_tiles + 255) / 256, 256, 0, h->stream>>>(sp.base_p, sp.n_base, B_start, tile_bytes, hi, n_tiles,
-                                                                      static_cast<u32*>(h->tile_nact.p));
+            if (h->dry)
+                h->dry_miss = true;      // the captured chain relied on the cached table: this query cannot be a replay
+            else
+                k_tile_nact<<<(n_tiles + 255) / 256, 256, 0, h->stream>>>(sp.base_p, sp.n_base, B_start, tile_bytes, hi, n_tiles,
+                                                                          static_cast<u32*>(h->tile_nact.p));
             CU_TRY(h, cudaGetLastError());
             h->launches++;
             memcpy(h->nact_key, nact_key, sizeof nact_key);
@@ -631,6 +659,7 @@ int compact_resident(pss_handle* h, u64 cap) {
 // column scan: one CTA per column; up to 8192 scan tiles the register-resident kernel (rows loaded once)
 void launch_scan_columns(pss_handle* h, u32 ncols, const u64* in, u64* out, u32 n, u64 stride) {
     const u32 rows = (n + 31u) / 32u;
+    if (h->dry) return;
     if ((rows + 15u) / 16u <= 16u) k_scan_columns_small<<<ncols, 512, 0, h->stream>>>(in, out, n, stride);
     else k_scan_columns<<<ncols, 1024, 0, h->stream>>>(in, out, n, stride);
 }
@@ -792,6 +821,11 @@ int launch_bscan_t(pss_handle* h, const BScanParams& bp) {
     int occ = 1;
     PSS_TRY(occ_of(h, k_bitmap_scan<K, MULTI, MODE>, kBsThreads, 0, &occ));
     const u32 grid = std::min<u32>(bp.n_tiles, (u32)(h->sm_count * occ));
+    if constexpr (MODE == kBsCompare) {     // the one launch of a query chain whose argument changes from query to query
+        h->g_cmp_args = bp;
+        h->g_cmp_func = reinterpret_cast<const void*>(k_bitmap_scan<K, MULTI, MODE>);
+    }
+    if (h->dry) return PSS_OK;
     k_bitmap_scan<K, MULTI, MODE><<<grid, kBsThreads, 0, h->stream>>>(bp);
     CU_TRY(h, cudaGetLastError());
     h->launches++;
@@ -804,6 +838,7 @@ int launch_moments_t(pss_handle* h, const BScanParams& bp) {
         int occ_t = 1;
         PSS_TRY(occ_of(h, k_bitmap_moments_tab<K, MULTI>, kBsThreads, 0, &occ_t));
         const u32 grid_t = std::min<u32>(bp.n_tiles, (u32)(h->sm_count * occ_t));
+        if (h->dry) return PSS_OK;
         k_bitmap_moments_tab<K, MULTI><<<grid_t, kBsThreads, 0, h->stream>>>(bp);
         CU_TRY(h, cudaGetLastError());
         h->launches++;
@@ -812,6 +847,7 @@ int launch_moments_t(pss_handle* h, const BScanParams& bp) {
     int occ = 1;
     PSS_TRY(occ_of(h, k_bitmap_moments<K, MULTI>, kBsThreads, 0, &occ));
     const u32 grid = std::min<u32>(bp.n_tiles, (u32)(h->sm_count * occ));
+    if (h->dry) return PSS_OK;
     k_bitmap_moments<K, MULTI><<<grid, kBsThreads, 0, h->stream>>>(bp);
     CU_TRY(h, cudaGetLastError());
     h->launches++;
@@ -972,12 +1008,12 @@ int bitmap_reduce(pss_handle* h, u32 K, bool multi, bool defer_sync = false) {
     bp.cols = static_cast<u64*>(h->cols.p);
     bp.col_prefix = static_cast<const u64*>(h->col_prefix.p);
     CU_TRY(h, mark(h, 4));
-    CU_TRY(h, cudaMemsetAsync(bp.cols, 0, (size_t)ncols * bp.col_stride * sizeof(u64), h->stream));
+    if (!h->dry) CU_TRY(h, cudaMemsetAsync(bp.cols, 0, (size_t)ncols * bp.col_stride * sizeof(u64), h->stream));
     if (K == 2 && !multi && h->reduce_moments) {
         int occ = 1;
         PSS_TRY(occ_of(h, k_bitmap_moments2, kBsThreads, 0, &occ));
         const u32 grid = std::min<u32>(bp.n_tiles, (u32)(h->sm_count * occ));
-        k_bitmap_moments2<<<grid, kBsThreads, 0, h->stream>>>(bp);
+        if (!h->dry) k_bitmap_moments2<<<grid, kBsThreads, 0, h->stream>>>(bp);
         CU_TRY(h, cudaGetLastError());
         h->launches++;
     } else if (K <= 5 && h->reduce_moments) {
@@ -1032,8 +1068,8 @@ int prepare_misc(pss_handle* h, const pss_search_args* a, const u32* carry_in) {
                 if (in.carry[j * PSS_LIMBS + i]) return fail(h, PSS_EINVAL, "carry-in of power %u exceeds %d limbs", in.power[j], w);
         }
     }
-    CU_TRY(h, cudaEventRecord(h->ev[8], h->stream));     // a query chain starts here
-    k_init_misc<<<1, 128, 0, h->stream>>>(static_cast<MiscDev*>(h->misc.p), in);
+    CU_TRY(h, mark(h, 8));     // a query chain starts here (recorded around the graph launch when the chain is a graph)
+    if (!h->dry) k_init_misc<<<1, 128, 0, h->stream>>>(static_cast<MiscDev*>(h->misc.p), in);
     CU_TRY(h, cudaGetLastError());
     h->launches++;
     h->misc_uploaded = true;
@@ -1060,15 +1096,17 @@ int export_results(pss_handle* h, u32 peer_world, u64 peer_parity) {
         ep.peer_host = h->h_peer_results_dev;
         ep.world = peer_world;
     }
-    k_export<<<1, 256, 0, h->stream>>>(ep);
+    if (!h->dry) k_export<<<1, 256, 0, h->stream>>>(ep);
     CU_TRY(h, cudaGetLastError());
-    CU_TRY(h, cudaEventRecord(h->ev[9], h->stream));     // ... and ends here
+    CU_TRY(h, mark(h, 9));     // ... and ends here
     h->launches++;
     return PSS_OK;
 }
 
-// phase B of the fused path: compare every partial sum, seeded with carry_in (host limbs or NULL)
-int bitmap_compare(pss_handle* h, u64 n_first, const u32* carry_in, const pss_search_args* a, pss_search_result* res) {
+// phase B of the fused path: compare every partial sum, seeded with carry_in (host limbs or NULL).  Two halves so that a
+// query chain can be captured into / replayed from a CUDA graph: the enqueue half only launches, the finish half runs after
+// the stream has been synchronised.
+int bitmap_compare_enqueue(pss_handle* h, u64 n_first, const u32* carry_in, const pss_search_args* a, u64* scanned_out, bool* pending_out) {
     const bool multi = a->all_powers && a->power_max > 1;
     const u32 K = a->power_max;
     const bool pending = h->bs_pending;   // single-query chain: the sieve and the reduce are enqueued, not read back yet
@@ -1076,7 +1114,6 @@ int bitmap_compare(pss_handle* h, u64 n_first, const u32* carry_in, const pss_se
         return fail(h, PSS_EINVAL, "pss_slice_sieve_sums must be called first with the same power configuration");
     const u32 np = n_powers_of(K, multi);
     static const u32 kMasks[6] = {2u, 5u, 1u, 3u, 4u, 6u};
-    MiscDev* hm = h->h_misc;
     if (!h->misc_uploaded) PSS_TRY(prepare_misc(h, a, carry_in));
     h->misc_uploaded = false;
     // with a pending reduce the slice count is not known yet: the caller (pss_search) guarantees by a proven bound
@@ -1106,12 +1143,18 @@ int bitmap_compare(pss_handle* h, u64 n_first, const u32* carry_in, const pss_se
         bp.last_prime_out = &dm->last_prime;
         bp.error_flag = &dm->error_flag;
         PSS_TRY(launch_bscan<kBsCompare>(h, bp, K, multi));
-        CU_TRY(h, mark(h, 7));
-    } else {
-        CU_TRY(h, mark(h, 7));
     }
+    CU_TRY(h, mark(h, 7));
     PSS_TRY(export_results(h, 0, 0));
-    CU_TRY(h, cudaStreamSynchronize(h->stream));
+    *scanned_out = scanned;
+    *pending_out = pending;
+    return PSS_OK;
+}
+
+int bitmap_compare_finish(pss_handle* h, u64 n_first, const pss_search_args* a, pss_search_result* res, u64 scanned, bool pending) {
+    const bool multi = a->all_powers && a->power_max > 1;
+    const u32 K = a->power_max, np = n_powers_of(K, multi);
+    MiscDev* hm = h->h_misc;
     if (pending) {
         sieve_finish(h);
         PSS_TRY(reduce_finish(h));
@@ -1140,6 +1183,14 @@ int bitmap_compare(pss_handle* h, u64 n_first, const u32* carry_in, const pss_se
     return PSS_OK;
 }
 
+int bitmap_compare(pss_handle* h, u64 n_first, const u32* carry_in, const pss_search_args* a, pss_search_result* res) {
+    u64 scanned = 0;
+    bool pending = false;
+    PSS_TRY(bitmap_compare_enqueue(h, n_first, carry_in, a, &scanned, &pending));
+    CU_TRY(h, cudaStreamSynchronize(h->stream));
+    return bitmap_compare_finish(h, n_first, a, res, scanned, pending);
+}
+
 // BScanParams of a compare launch over the bitmap left by sieve_range / bitmap_reduce
 void fill_compare_params(pss_handle* h, BScanParams& bp, const pss_search_args* a, u64 n_first, MiscDev* dm = nullptr) {
     static const u32 kMasks[6] = {2u, 5u, 1u, 3u, 4u, 6u};
@@ -1164,6 +1215,132 @@ void fill_compare_params(pss_handle* h, BScanParams& bp, const pss_search_args* 
     bp.results = dm->results;
     bp.last_prime_out = &dm->last_prime;
     bp.error_flag = &dm->error_flag;
+}
+
+// The launch chain of a single-GPU query: init -> sieve -> block sums -> column scan -> compare -> export, enqueued back to back
+// (no copy-engine operation inside, the small H2D / D2H traffic travels as kernel arguments / mapped pinned stores).
+int enqueue_query_chain(pss_handle* h, const pss_search_args* a, u64 bound, u64* scanned, bool* pending) {
+    const bool multi = a->all_powers && a->power_max > 1;
+    PSS_TRY(prepare_misc(h, a, nullptr));
+    PSS_TRY(sieve_range(h, 0, bound, true));
+    PSS_TRY(bitmap_reduce(h, a->power_max, multi, true));
+    return bitmap_compare_enqueue(h, 1, nullptr, a, scanned, pending);
+}
+
+void drop_query_graph(pss_handle* h) {
+    if (h->g_exec) cudaGraphExecDestroy(h->g_exec);
+    if (h->g_graph) cudaGraphDestroy(h->g_graph);
+    h->g_graph = nullptr;
+    h->g_exec = nullptr;
+    h->g_cmp_node = nullptr;
+    h->g_key.clear();
+}
+
+// Runs the chain kernel by kernel, or — from the second consecutive query with the same geometry on — as a CUDA graph: the
+// first repeat captures the chain (stream capture of the very same enqueue code) and instantiates it; later queries with that
+// geometry run the enqueue code "dry" (host bookkeeping only), point the compare node at the new argument (target, window,
+// operator) and launch the graph: one driver call instead of ten.  Any failure on the graph route drops the graph, switches
+// the feature off for the handle and runs the query kernel by kernel.
+int run_query_chain(pss_handle* h, const pss_search_args* a, pss_search_result* res, u64 bound) {
+    const bool multi = a->all_powers && a->power_max > 1;
+    std::vector<u64> key = {bound, a->power_max, (u64)multi, (u64)h->kernel_events, h->tile_bytes, h->sieve_threads, h->n_pat,
+                            h->warp_wide_div, (u64)h->reduce_moments, (u64)h->sieve_variant, h->alloc_generation,
+                            (u64)(h->sieve_prof.p != nullptr)};
+    u64 scanned = 0;
+    bool pending = false;
+    if (h->use_graph && h->g_exec && key == h->g_key) {
+        // ---- replay
+        const u64 launches_before = h->launches;
+        h->dry = true;
+        h->dry_miss = false;
+        const int rc = enqueue_query_chain(h, a, bound, &scanned, &pending);
+        h->dry = false;
+        h->launches = launches_before;
+        PSS_TRY(rc);
+        if (h->dry_miss || key[10] != h->alloc_generation) {
+            // a staged table or buffer changed since the capture (another geometry ran in between): this query runs kernel
+            // by kernel and the graph is rebuilt on the next repeat
+            drop_query_graph(h);
+            h->sv_pending = h->bs_pending = false;
+            key[10] = h->alloc_generation;
+            h->g_seen_key = key;
+            PSS_TRY(enqueue_query_chain(h, a, bound, &scanned, &pending));
+            CU_TRY(h, cudaStreamSynchronize(h->stream));
+            return bitmap_compare_finish(h, 1, a, res, scanned, pending);
+        }
+        bool ok = h->g_cmp_node != nullptr && h->g_cmp_func == h->g_cmp_params.func;
+        if (ok) {
+            cudaKernelNodeParams np = h->g_cmp_params;
+            void* args[1] = {&h->g_cmp_args};
+            np.kernelParams = args;
+            np.extra = nullptr;
+            ok = cudaGraphExecKernelNodeSetParams(h->g_exec, h->g_cmp_node, &np) == cudaSuccess &&
+                 cudaEventRecord(h->ev[8], h->stream) == cudaSuccess && cudaGraphLaunch(h->g_exec, h->stream) == cudaSuccess &&
+                 cudaEventRecord(h->ev[9], h->stream) == cudaSuccess;
+        }
+        if (ok) {
+            h->launches += h->g_kernels;
+            CU_TRY(h, cudaStreamSynchronize(h->stream));
+            return bitmap_compare_finish(h, 1, a, res, scanned, pending);
+        }
+        cudaGetLastError();
+        drop_query_graph(h);
+        h->use_graph = 0;          // and fall through: kernel by kernel
+    } else if (h->use_graph && key == h->g_seen_key) {
+        // ---- second query in a row with this geometry: capture, instantiate, launch
+        drop_query_graph(h);
+        cudaGraph_t graph = nullptr;
+        bool ok = cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeRelaxed) == cudaSuccess;
+        int rc = PSS_OK;
+        if (ok) {
+            const u64 launches_before = h->launches;
+            h->capturing = true;
+            rc = enqueue_query_chain(h, a, bound, &scanned, &pending);
+            h->capturing = false;
+            h->g_kernels = h->launches - launches_before;
+            h->launches = launches_before;
+            ok = cudaStreamEndCapture(h->stream, &graph) == cudaSuccess && graph != nullptr && rc == PSS_OK &&
+                 key[10] == h->alloc_generation;     // a buffer that grew during the capture invalidates it
+        }
+        if (ok) ok = cudaGraphInstantiate(&h->g_exec, graph, 0) == cudaSuccess;
+        if (ok) {   // find the compare node (the only kernel node running g_cmp_func)
+            size_t n = 0;
+            ok = cudaGraphGetNodes(graph, nullptr, &n) == cudaSuccess && n > 0;
+            std::vector<cudaGraphNode_t> nodes(n);
+            if (ok) ok = cudaGraphGetNodes(graph, nodes.data(), &n) == cudaSuccess;
+            h->g_cmp_node = nullptr;
+            for (size_t i = 0; ok && i < n; ++i) {
+                cudaGraphNodeType ty;
+                if (cudaGraphNodeGetType(nodes[i], &ty) != cudaSuccess || ty != cudaGraphNodeTypeKernel) continue;
+                cudaKernelNodeParams kp;
+                if (cudaGraphKernelNodeGetParams(nodes[i], &kp) != cudaSuccess) continue;
+                if (kp.func == h->g_cmp_func) {
+                    h->g_cmp_node = nodes[i];
+                    h->g_cmp_params = kp;
+                }
+            }
+            ok = ok && (h->g_cmp_node != nullptr || scanned == 0);
+        }
+        h->g_graph = graph;          // destroyed with the executable graph (drop_query_graph)
+        if (ok) ok = cudaEventRecord(h->ev[8], h->stream) == cudaSuccess && cudaGraphLaunch(h->g_exec, h->stream) == cudaSuccess &&
+                     cudaEventRecord(h->ev[9], h->stream) == cudaSuccess;
+        if (ok) {
+            h->g_key = key;
+            h->launches += h->g_kernels;
+            CU_TRY(h, cudaStreamSynchronize(h->stream));
+            return bitmap_compare_finish(h, 1, a, res, scanned, pending);
+        }
+        cudaGetLastError();
+        drop_query_graph(h);
+        h->use_graph = 0;
+        h->sv_pending = h->bs_pending = false;
+        if (rc != PSS_OK) return rc;
+        // fall through: kernel by kernel
+    }
+    h->g_seen_key = key;
+    PSS_TRY(enqueue_query_chain(h, a, bound, &scanned, &pending));
+    CU_TRY(h, cudaStreamSynchronize(h->stream));
+    return bitmap_compare_finish(h, 1, a, res, scanned, pending);
 }
 
 int check_handle(pss_handle* h) {
@@ -1226,6 +1403,7 @@ int pss_open(int device, pss_handle** out) {
     h->reduce_moments = (int)env_u32("PSS_REDUCE_MOMENTS", (u32)h->reduce_moments);
     h->compare_exhaustive = (int)env_u32("PSS_COMPARE_EXHAUSTIVE", (u32)h->compare_exhaustive);
     h->kernel_events = (int)std::min<u32>(env_u32("PSS_KERNEL_EVENTS", 1), 2);
+    h->use_graph = (int)env_u32("PSS_GRAPH", 1);
     h->tile_bytes = std::max<u32>(8192, std::min<u32>((h->tile_bytes / kChunkBytes) * kChunkBytes, kMaxTileBytes));
     if (env_u32("PSS_SIEVE_PROF", 0) && cudaMalloc(&h->sieve_prof.p, 64) == cudaSuccess) {
         h->sieve_prof.cap = 64;
@@ -1262,6 +1440,7 @@ int pss_close(pss_handle* h) {
     if (!h) return PSS_OK;
     cudaSetDevice(h->device);
     if (h->stream) cudaStreamSynchronize(h->stream);
+    drop_query_graph(h);
     if (h->sieve_prof.p) {   // instrumented sieve (PSS_SIEVE_PROF=1): where a tile's cycles went
         unsigned long long c[8] = {0};
         cudaMemcpy(c, h->sieve_prof.p, sizeof c, cudaMemcpyDeviceToHost);
@@ -1494,12 +1673,7 @@ int pss_search(pss_handle* h, const pss_search_args* a, pss_search_result* res) 
         // fused path: the bit-packed sieve output is scanned directly
         const u64 bound = pss_nth_prime_upper(a->n_max) + 1;
         if (bound > kMaxValue) return fail(h, PSS_EINVAL, "n = %llu needs primes beyond 2^%d", (unsigned long long)a->n_max, PSS_MAX_PRIME_BITS);
-        // sieve -> reduce -> column scan -> compare are enqueued back to back; one synchronisation at the end
-        // (the small H2D goes first and the D2H copies last: no copy-engine operation sits between two kernels)
-        PSS_TRY(prepare_misc(h, a, nullptr));
-        PSS_TRY(sieve_range(h, 0, bound, true));
-        PSS_TRY(bitmap_reduce(h, a->power_max, multi, true));
-        PSS_TRY(bitmap_compare(h, 1, nullptr, a, res));
+        PSS_TRY(run_query_chain(h, a, res, bound));
     }
     fill_stats(h, &res->stats, before);
     return PSS_OK;
