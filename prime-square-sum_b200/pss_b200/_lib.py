@@ -395,7 +395,9 @@ class Handle:
                     all_powers: bool = False):
         """this rank's part of a multi-GPU query over its value slice [lo, hi); returns (records of all ranks, stats)"""
         a, keep = self._make_args(n_min, n_max, power_max, all_powers, op, target)
-        recs = (PeerRecord * self.peer_world)()
+        recs = getattr(self, "_peer_recs", None)          # reused across queries: the caller consumes the records at once
+        if recs is None or len(recs) != self.peer_world:
+            recs = self._peer_recs = (PeerRecord * self.peer_world)()
         st = Stats()
         self._check(self._L.pss_peer_search(self._h, lo, hi_excl, ctypes.byref(a), recs, ctypes.byref(st)))
         del keep

@@ -398,16 +398,27 @@ def distributed_search(target: int, n_max: int, power: int = 2, n_min: int = 1, 
     import torch.distributed as dist
 
     t0 = time.perf_counter()
-    world = dist.get_world_size(group) if dist.is_initialized() else 1
-    rank = dist.get_rank(group) if dist.is_initialized() else 0
     h = handle or _lib.default_handle()
+    # world / rank / transport of this (handle, group) are looked up once: the query path of a 0.4 ms multi-GPU step should not
+    # pay for torch.distributed introspection every call
+    import os
+    exchange = os.environ.get("PSS_EXCHANGE", "peer")
+    ctx = getattr(h, "_dist_ctx", None)
+    if ctx is None or ctx[0] is not group or ctx[4] != exchange or gather is not None:
+        world = dist.get_world_size(group) if dist.is_initialized() else 1
+        rank = dist.get_rank(group) if dist.is_initialized() else 0
+        peer = world > 1 and gather is None and _peer_exchange_enabled(group)
+        ctx = (group, world, rank, peer, exchange)
+        if gather is None:
+            h._dist_ctx = ctx
+    _, world, rank, peer, _ = ctx
     if world == 1:
         return search(target, n_max, power, n_min, op, all_powers, handle=h)
 
     hi = h.nth_prime_upper(n_max) + 1
     lo_g, hi_g = partition_range(hi, world, sieve_weight=sieve_weight_for(power, all_powers))[rank]
     np_ = _np(power, all_powers)
-    if gather is None and _peer_exchange_enabled(group):
+    if peer:
         return _peer_search(h, group, rank, world, lo_g, hi_g, target, n_max, power, n_min, op, all_powers, np_)
     # fused phase A: sieve + per-tile sums (no u64 prime buffer); leaves the slice's bitmap resident
     count_g, sums_g = h.slice_sieve_sums(lo_g, hi_g, power, all_powers)
