@@ -41,19 +41,17 @@ _config = {"algorithm": ALGORITHM_AUTO, "max_memory_mb": None, "prefer": None}
 
 
 def configure(algorithm: str = None, max_memory_mb: int = None, prefer: str = None) -> None:
-    """Same contract as utils/sieve.py:81-100 (ValueError("Invalid algorithm: ...") for unknown names)."""
-    if algorithm is not None:
-        if algorithm not in VALID_ALGORITHMS:
-            raise ValueError(f"Invalid algorithm: {algorithm}")
-        _config["algorithm"] = algorithm
-    if max_memory_mb is not None:
-        _config["max_memory_mb"] = max_memory_mb
-    if prefer is not None:
-        _config["prefer"] = prefer
+    """Same contract as utils/sieve.py:81-100: only the arguments that are given change; an unknown algorithm name raises
+    ValueError("Invalid algorithm: ...") and changes nothing."""
+    if algorithm is not None and algorithm not in VALID_ALGORITHMS:
+        raise ValueError(f"Invalid algorithm: {algorithm}")
+    for key, value in (("algorithm", algorithm), ("max_memory_mb", max_memory_mb), ("prefer", prefer)):
+        if value is not None:
+            _config[key] = value
 
 
 def get_config() -> dict:
-    return _config.copy()
+    return dict(_config)
 
 
 def _resolve(algorithm: Optional[str]) -> bool:
