@@ -419,8 +419,11 @@ __global__ void __launch_bounds__(kBsThreads, bs_min_blocks<K, MULTI>()) k_bitma
         }
     };
 
-    // work units: reduce pass = warp tiles; compare passes = scan tiles (8 warp tiles), pruned as a whole when possible
-    const u64 n_units = (MODE == kBsReduce) ? n_warp_tiles : (u64)P.n_tiles;
+    // work units: reduce pass = warp tiles; compare pass = scan tiles (8 warp tiles), pruned as a whole when possible; the
+    // triangular predicate = warp tiles again (only the first few blocks of a range can hold a sum <= tri(m_max), and they are
+    // the densest: one warp per scan tile walked two warp tiles of ~400 primes per lane one after the other)
+    constexpr bool kUnitIsWarpTile = (MODE == kBsReduce) || (MODE == kBsTri);
+    const u64 n_units = kUnitIsWarpTile ? n_warp_tiles : (u64)P.n_tiles;
     for (u64 unit = (u64)blockIdx.x * NWARP + warp; unit < n_units; unit += warp_stride) {
         u32 tile, wit_lo, wit_hi;
         if constexpr (MODE == kBsReduce) {
@@ -428,9 +431,15 @@ __global__ void __launch_bounds__(kBsThreads, bs_min_blocks<K, MULTI>()) k_bitma
             wit_lo = (u32)(unit % NWARP);
             wit_hi = wit_lo + 1u;
         } else {
-            tile = (u32)unit;
-            wit_lo = 0u;
-            wit_hi = NWARP;
+            if constexpr (MODE == kBsTri) {
+                tile = (u32)(unit / NWARP);
+                wit_lo = (u32)(unit % NWARP);
+                wit_hi = wit_lo + 1u;
+            } else {
+                tile = (u32)unit;
+                wit_lo = 0u;
+                wit_hi = NWARP;
+            }
             if (n_first + P.col_prefix[tile] > P.n_max) break;   // prefixes are monotone in tile
             // ---- interval pruning, scan-tile level (737 280 integers): same argument as below on the tile's exact
             //      prefix / end sums; a pruned tile costs one warp ~100 instructions and touches no record
