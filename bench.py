@@ -398,24 +398,23 @@ def main():
             assert po.final_sum == w["sums"][po.power], f"{name}: S_{po.power} mismatch"
 
     def timed_steps(step, n_steps):
-        """K steps bracketed by barrier + synchronize; per-step device span from the library's CUDA events"""
-        dev, acc = [], dict.fromkeys(KKEYS + [k for k in TKEYS if k not in KKEYS], 0.0)
-        launches = 0
+        """K steps bracketed by barrier + synchronize.  The library accumulates its CUDA-event times over the K queries
+        (pss_stats since the reset), so the timed loop contains nothing but the K API calls."""
+        acc = dict.fromkeys(KKEYS + [k for k in TKEYS if k not in KKEYS], 0.0)
         barrier()
+        h.stats_reset()
         t_start = time.perf_counter()
         for _ in range(n_steps):
-            h.stats_reset()
             o = step()
-            s = h.stats()
-            # whole-query span on the launch stream (gaps and, at N > 1, the waits on the peers' publishes included);
-            # paths with a host synchronisation in the middle fall back to the sum of the kernels' event times
-            dev.append(s["ms_span"] if s.get("ms_span", 0.0) > 0.0 else s["ms_total_device"])
-            for k in acc:
-                acc[k] += s.get(k, 0.0)
-            launches += s["launches"]
         barrier()
         wall = time.perf_counter() - t_start
-        return sum(dev), wall * 1e3, acc, launches, o
+        s = h.stats()
+        # whole-query span on the launch stream (gaps and, at N > 1, the waits on the peers' publishes included), summed over
+        # the K queries; paths with a host synchronisation in the middle fall back to the sum of the kernels' event times
+        dev = s["ms_span"] if s.get("ms_span", 0.0) > 0.0 else s["ms_total_device"]
+        for k in acc:
+            acc[k] = s.get(k, 0.0)
+        return dev, wall * 1e3, acc, s["launches"], o
 
     def gather_timeline(kern, wall_ms):
         """every rank's per-step averages of the query timeline (rank order); None at N = 1"""
