@@ -342,6 +342,53 @@ def test_window_edges_at_every_level(handle, orc, search_path):
             assert po.match_count == hit - n_min and (po.match_count == 0 or (po.first_match_n, po.last_match_n) == (n_min, hit - 1))
 
 
+def test_query_graph_survives_interleaving(orc):
+    """the single-GPU query chain becomes a CUDA graph from the second query with the same geometry on:
+    replays with other targets / windows / operators, other geometries and other API calls in between (which overwrite the
+    staged tables and buffers the graph relies on), a tuning change and the exhaustive mode must all give the kernel-by-kernel
+    answers (PSS_GRAPH=0 handle)"""
+    from pss_b200 import _lib, search
+    os.environ["PSS_GRAPH"] = "0"
+    try:
+        h_ref = _lib.Handle(-1)
+    finally:
+        del os.environ["PSS_GRAPH"]
+    h = _lib.Handle(-1)
+    primes = orc.c_first_n_primes(300_000)
+    sums = {k: orc.c_prefix_sums(primes, k) for k in (1, 2, 3)}
+
+    def same(n_max, **kw):
+        a = search.search(handle=h, n_max=n_max, **kw)
+        b = search.search(handle=h_ref, n_max=n_max, **kw)
+        rec = lambda o: (o.first(), o.last_prime, [(p.power, p.match_count, p.first_match_n, p.last_match_n, p.cross_n, p.cross_prime,
+                                                     p.sum_at_cross, p.sum_before_cross, p.final_sum) for p in o.powers])
+        assert rec(a) == rec(b), (n_max, kw)
+        return a
+
+    G, G2 = 250_000, 77_777
+    for hit in (5, 123_456, G, 9, 200_000):                       # capture on the 2nd, replays with other targets after
+        assert same(G, target=sums[2][hit - 1], power=2).first() == (hit, 2)
+    assert h.count_primes(10 ** 9, 10 ** 9 + 50_000_000) == h_ref.count_primes(10 ** 9, 10 ** 9 + 50_000_000)   # other tables
+    assert same(G, target=sums[2][41], power=2, n_min=40, op=">=").powers[0].first_match_n == 42
+    assert same(G2, target=sums[2][776], power=2).first() == (777, 2)                                          # other geometry
+    assert same(G, target=sums[2][99_998], power=2).first() == (99_999, 2)                                     # back: no stale replay
+    assert same(G, target=sums[2][99_998] + 1, power=2).first() is None
+    assert int(h.generate_n_primes(1000)[-1]) == 7919                                                        # compaction in between
+    for _ in range(3):
+        assert same(G, target=sums[3][4_999], power=3, all_powers=True).first() == (5_000, 3)                 # other kernel instantiation
+    h.set_compare_mode(True); h_ref.set_compare_mode(True)
+    for hit in (17, 150_000):
+        assert same(G, target=sums[2][hit - 1], power=2).first() == (hit, 2)                                   # exhaustive through the same graph
+    h.set_compare_mode(False); h_ref.set_compare_mode(False)
+    h.set_tuning(96 * 1024, 512, 0); h_ref.set_tuning(96 * 1024, 512, 0)
+    for hit in (3, 222_222, 222_223):
+        assert same(G, target=sums[1][hit - 1], power=1).first() == (hit, 1)                                   # new tuning: new geometry key
+    h.set_kernel_events(2)
+    for hit in (1, 2):
+        assert same(G, target=sums[2][hit - 1], power=2).first() == (hit, 2)
+    h.close(); h_ref.close()
+
+
 def test_trisum666_configs_small(handle, orc, search_path):
     """config C1 and the C3/C4 shape at a size the oracle finishes in seconds: no match, bracket = n_max"""
     from pss_b200 import search
