@@ -311,7 +311,7 @@ __global__ void __launch_bounds__(THREADS, (THREADS <= 768) ? 2 : 1) k_sieve(con
                         const u64 Bw = B0 + (u64)vi * 16ull + 4ull * k;
                         u32 x = w[k];
                         if (Bw == 0) x = 0x7EEFDFFEu;   // the integers below 120: all wheel residues are prime except 1, 49, 77, 91, 119
-                                                         // (the patterns also clear their own primes, 7..83)
+                                                         // (the patterns also clear their own primes, 7..89)
                         u32 m = edge_byte_mask(Bw, P.lo, P.hi) | (edge_byte_mask(Bw + 1, P.lo, P.hi) << 8) |
                                 (edge_byte_mask(Bw + 2, P.lo, P.hi) << 16) | (edge_byte_mask(Bw + 3, P.lo, P.hi) << 24);
                         w[k] = x & m;
@@ -355,7 +355,9 @@ __global__ void __launch_bounds__(kChunkWords) k_individual(const SieveParams P)
     const u32 chunks_per_tile = P.tile_bytes / kChunkBytes;
     const u64 n_chunks = (u64)P.n_tiles * chunks_per_tile;
     const u32 tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
-    const u32 kSmall[14] = {7, 11, 13, 17, 19, 23, 29, 31, 37, 41, 43, 47, 53, 59};
+    // every prime a pre-sieve pattern group can cover (pss_api.cu: kPatGroups), so the test does not depend on where the
+    // staged base-prime table starts
+    const u32 kSmall[21] = {7, 11, 13, 17, 19, 23, 29, 31, 37, 41, 43, 47, 53, 59, 61, 67, 71, 73, 79, 83, 89};
     for (u64 ch = blockIdx.x; ch < n_chunks; ch += gridDim.x) {
         const u64 Bw = P.B_start + ch * (u64)kChunkBytes + 4ull * tid;
         u32 word = 0;
@@ -363,17 +365,17 @@ __global__ void __launch_bounds__(kChunkWords) k_individual(const SieveParams P)
             const u64 v = word_bit_value(Bw, bit);
             if (v < 7 || v < P.lo || v >= P.hi) continue;
             bool prime = true;
-            for (u32 i = 0; i < 14 && prime; ++i) {
+            for (u32 i = 0; i < 21 && prime; ++i) {
                 const u64 q = kSmall[i];
                 if (q * q > v) break;
                 if (v % q == 0) prime = false;
             }
-            // base_p holds the primes from the first one not covered by a pre-sieve pattern (>= 61 by default; the
-            // host stages them up to sqrt(hi)); entries below 61 were tested above
+            // base_p holds the primes from the first one not covered by a pre-sieve pattern (the host stages them up to
+            // sqrt(hi)); entries up to 89 were tested above
             for (u32 i = 0; i < P.n_base && prime; ++i) {
                 const u64 q = __ldg(P.base_p + i);
                 if (q * q > v) break;
-                if (q > 59 && v % q == 0) prime = false;
+                if (q > 89 && v % q == 0) prime = false;
             }
             if (prime) word |= 1u << bit;
         }
