@@ -115,6 +115,7 @@ struct pss_handle {
     u32 tile_bytes = 224 * 1024;   // one 1024-thread CTA per SM (tools/tune_sieve.py, profiles/r01/tune_sieve_*.json)
     u32 sieve_threads = 1024;
     u32 n_pat = 4;
+    u32 sparse_lead = 0xFFFFFFFFu;   // sparse batches queued ahead of the dense primes (PSS_SPARSE_LEAD; all of them by default)
     u32 warp_wide_div = 104;    // p < tile_bytes / div -> dense (one warp per prime, skewed conflict-free lanes), else one lane per prime
     int kernel_events = 1;     // PSS_KERNEL_EVENTS
     int sieve_variant = 0;     // 0: segmented wheel-30 sieve (k_sieve), 1: "individual" per-candidate trial division (k_individual)
@@ -515,6 +516,7 @@ int sieve_range(pss_handle* h, u64 lo, u64 hi, bool defer_sync = false) {
                 h->alloc_generation++;
             }
             sp.batch_geo = static_cast<const u32*>(h->d_batch_geo.p);
+            sp.sparse_lead = h->sparse_lead;
         }
         // per tile: how many base primes satisfy p*p < tile end (tiny device kernel, no host work)
         // (the table only depends on the geometry; PSS_NACT_CACHE=1 reuses it for a repeated query instead of launching again)
@@ -1400,6 +1402,7 @@ int pss_open(int device, pss_handle** out) {
     h->n_pat = std::min<u32>(env_u32("PSS_NPAT", h->n_pat), kMaxPatterns);
     if (const char* sp_ = getenv("PSS_SEARCH_PATH")) h->search_path = (strcmp(sp_, "materialised") == 0 || strcmp(sp_, "materialized") == 0) ? 1 : 0;
     h->warp_wide_div = env_u32("PSS_WARP_WIDE_DIV", h->warp_wide_div);
+    h->sparse_lead = env_u32("PSS_SPARSE_LEAD", h->sparse_lead);
     h->reduce_moments = (int)env_u32("PSS_REDUCE_MOMENTS", (u32)h->reduce_moments);
     h->compare_exhaustive = (int)env_u32("PSS_COMPARE_EXHAUSTIVE", (u32)h->compare_exhaustive);
     h->kernel_events = (int)std::min<u32>(env_u32("PSS_KERNEL_EVENTS", 1), 2);

@@ -43,6 +43,9 @@ struct SieveParams {
                               // trip counts per strand (n_uni = tile/p_hi - 1 unguarded, n_rag = (tile-1)/p_lo + 1 - n_uni guarded)
     const u32* tile_nact;     // per tile: number of base primes with p*p < tile end (the only ones that can
                               // still cross something off there)
+    u32 sparse_lead;     // the first sparse_lead batches are queued BEFORE the dense primes: a batch near the dense limit
+                         // is ~800 conflicted atomics per lane, the longest item of the tile by far (a dense prime is
+                         // 26 .. 940 conflict-free ones), so it has to start first or it becomes the tail of phase B
     u32 wide_index;      // 1: tile byte indices may exceed 2^32 -> 64-bit modulo path
     u32 n_pat;
     const uint4* pat[kMaxPatterns];
@@ -151,17 +154,25 @@ __global__ void __launch_bounds__(THREADS, (THREADS <= 768) ? 2 : 1) k_sieve(con
         __syncthreads();
         if (prof) pc1 = clock64();
 
-        // ---- phase B: cross-offs.  Warps pull work items from a shared-memory queue (largest items first):
-        //        items [0, n_dense)   one dense prime each (p < tile/128), whole warp, bank-conflict free
-        //        items [n_dense, ..)  batches of 32 consecutive sparse primes, one prime per lane
+        // ---- phase B: cross-offs.  Warps pull work items from a shared-memory queue, longest items first:
+        //        slots [0, lead)              the first `lead` batches of 32 consecutive sparse primes, one prime per lane
+        //        slots [lead, lead + n_dense) one dense prime each (p < tile/104), whole warp, bank-conflict free
+        //        slots [lead + n_dense, ..)   the remaining sparse batches (few hits per lane)
         const u32 nact = __ldg(P.tile_nact + t);
         const u32 n_dense = min(P.n_warp_wide, nact);
-        const u32 n_items = n_dense + ((nact - n_dense + 31u) >> 5);
+        const u32 n_batches = (nact - n_dense + 31u) >> 5;
+        const u32 n_items = n_dense + n_batches;
+        const u32 lead = min(P.sparse_lead, n_batches);
+        // the queue counter lives in the pipe the cross-offs saturate: a pull takes several hundred cycles to come back, so
+        // each warp asks for its next slot before it starts on the current one
+        u32 pulled = 0;
+        if (lane == 0) pulled = atomicAdd(&s_next, 1u);
         for (;;) {
-            u32 item = 0;
-            if (lane == 0) item = atomicAdd(&s_next, 1u);
-            item = __shfl_sync(0xFFFFFFFFu, item, 0);
-            if (item >= n_items) break;
+            const u32 slot = __shfl_sync(0xFFFFFFFFu, pulled, 0);
+            if (slot >= n_items) break;
+            if (lane == 0) pulled = atomicAdd(&s_next, 1u);
+            // item < n_dense: dense prime `item`; else sparse batch item - n_dense
+            const u32 item = (slot < lead) ? slot + n_dense : (slot < lead + n_dense) ? slot - lead : slot;
             long long pi0 = 0;
             u32 pcls = 0;
             if (prof) pi0 = clock64();
