@@ -1408,9 +1408,9 @@ int pss_open(int device, pss_handle** out) {
     h->kernel_events = (int)std::min<u32>(env_u32("PSS_KERNEL_EVENTS", 1), 2);
     h->use_graph = (int)env_u32("PSS_GRAPH", 1);
     h->tile_bytes = std::max<u32>(8192, std::min<u32>((h->tile_bytes / kChunkBytes) * kChunkBytes, kMaxTileBytes));
-    if (env_u32("PSS_SIEVE_PROF", 0) && cudaMalloc(&h->sieve_prof.p, 64) == cudaSuccess) {
-        h->sieve_prof.cap = 64;
-        cudaMemset(h->sieve_prof.p, 0, 64);
+    if (env_u32("PSS_SIEVE_PROF", 0) && cudaMalloc(&h->sieve_prof.p, 128) == cudaSuccess) {
+        h->sieve_prof.cap = 128;
+        cudaMemset(h->sieve_prof.p, 0, 128);
     }
     if (h->sieve_threads != 256 && h->sieve_threads != 512 && h->sieve_threads != 768) h->sieve_threads = 1024;
     auto cleanup = [&](int rc) {
@@ -1445,11 +1445,11 @@ int pss_close(pss_handle* h) {
     if (h->stream) cudaStreamSynchronize(h->stream);
     drop_query_graph(h);
     if (h->sieve_prof.p) {   // instrumented sieve (PSS_SIEVE_PROF=1): where a tile's cycles went
-        unsigned long long c[8] = {0};
+        unsigned long long c[16] = {0};
         cudaMemcpy(c, h->sieve_prof.p, sizeof c, cudaMemcpyDeviceToHost);
         const double n = c[3] ? (double)c[3] : 1.0;
-        fprintf(stderr, "[pss sieve prof] tiles=%llu cycles/tile: A=%.0f B=%.0f C=%.0f | warp-cycles/tile in B: dense32=%.0f dense16=%.0f sparse=%.0f large=%.0f\n", c[3],
-                c[0] / n, c[1] / n, c[2] / n, c[4] / n, c[5] / n, c[6] / n, c[7] / n);
+        fprintf(stderr, "[pss sieve prof] tiles=%llu cycles/tile: A=%.0f B=%.0f C=%.0f | warp-cycles/tile in B: dense32=%.0f dense16=%.0f sparse=%.0f large=%.0f, waiting at the end of B=%.0f, entry->first item=%.0f, between items=%.0f, last item->exit=%.0f\n", c[3],
+                c[0] / n, c[1] / n, c[2] / n, c[4] / n, c[5] / n, c[6] / n, c[7] / n, c[8] / n, c[9] / n, c[10] / n, c[11] / n);
         cudaFree(h->sieve_prof.p);
     }
     for (DevBuf* b : {&h->d_base, &h->d_base_inv, &h->d_base_strand, &h->d_batch_geo, &h->cols, &h->col_prefix, &h->thread_rec, &h->warp_rec, &h->tile_nact, &h->tri_buf, &h->bitmap, &h->chunk_counts, &h->tile_counts, &h->tile_prefix, &h->primes, &h->status, &h->agg,

@@ -110,6 +110,15 @@ __device__ __forceinline__ u32 first_hit(u32 p, u32 c, u32 r, bool is_strand0, u
 // inverse of an odd p modulo 64 (one Newton step from x0 = p, which is already correct modulo 8)
 __device__ __forceinline__ u32 inv_mod64(u32 p) { return p * (2u - p * p); }
 
+// one slot from the phase-B work queue.  Inline PTX on purpose: the compiler rewrites `if (lane == 0) atomicAdd(&ctr, 1)` into
+// its warp-aggregated form (leader ATOMS.ADD + SHFL of the result to all lanes), and that SHFL waits for the atomic right
+// where it was issued -- which defeats pulling ahead of time
+__device__ __forceinline__ u32 queue_pull(u32* ctr) {
+    u32 r;
+    asm volatile("atom.shared.inc.u32 %0, [%1], 0x3FFFFFFF;" : "=r"(r) : "r"((u32)__cvta_generic_to_shared(ctr)));   // .inc with a limit below 2^32 - 1: ptxas warp-aggregates .add (and .inc 0xFFFFFFFF) too
+    return r;
+}
+
 // the sieve kernel's dynamic shared memory: the tile followed by a 128-byte scratch line (one word per bank) that
 // absorbs the cross-offs of lanes that are outside the tile in a given iteration (see the dense phase)
 constexpr u32 kSieveScratchBytes = 128;
@@ -158,24 +167,37 @@ __global__ void __launch_bounds__(THREADS, (THREADS <= 768) ? 2 : 1) k_sieve(con
         //        slots [0, lead)              the first `lead` batches of 32 consecutive sparse primes, one prime per lane
         //        slots [lead, lead + n_dense) one dense prime each (p < tile/104), whole warp, bank-conflict free
         //        slots [lead + n_dense, ..)   the remaining sparse batches (few hits per lane)
+        long long pc1w = 0, plast = 0;
+        unsigned long long pgap0 = 0, pgap = 0;
+        if (prof) pc1w = clock64();
         const u32 nact = __ldg(P.tile_nact + t);
         const u32 n_dense = min(P.n_warp_wide, nact);
         const u32 n_batches = (nact - n_dense + 31u) >> 5;
         const u32 n_items = n_dense + n_batches;
         const u32 lead = min(P.sparse_lead, n_batches);
-        // the queue counter lives in the pipe the cross-offs saturate: a pull takes several hundred cycles to come back, so
-        // each warp asks for its next slot before it starts on the current one
+        // the queue counter AND the shuffle that broadcasts it go through the pipe the cross-offs keep full: either takes
+        // several hundred cycles to come back.  So the queue runs two items ahead: while a warp works on slot k, the
+        // broadcast of slot k + 1 and the pull of slot k + 2 are in flight (instrumented: 520 cycles between two items
+        // of a warp with the pull one ahead and the shuffle on the critical path, 10 % of phase B)
+        // (pulling the first slot before phase A, with nact loaded there too, costs 8 registers -- 64, the limit of a
+        // 1024-thread CTA -- and the cross-off loops 15 %: measured 2.015 -> 2.317 ms)
         u32 pulled = 0;
-        if (lane == 0) pulled = atomicAdd(&s_next, 1u);
+        if (lane == 0) pulled = queue_pull(&s_next);
+        u32 slot = __shfl_sync(0xFFFFFFFFu, pulled, 0);
+        if (lane == 0) pulled = queue_pull(&s_next);
         for (;;) {
-            const u32 slot = __shfl_sync(0xFFFFFFFFu, pulled, 0);
             if (slot >= n_items) break;
-            if (lane == 0) pulled = atomicAdd(&s_next, 1u);
+            const u32 cur = slot;
+            slot = __shfl_sync(0xFFFFFFFFu, pulled, 0);      // consumed after this item
+            if (lane == 0) pulled = queue_pull(&s_next);
             // item < n_dense: dense prime `item`; else sparse batch item - n_dense
-            const u32 item = (slot < lead) ? slot + n_dense : (slot < lead + n_dense) ? slot - lead : slot;
+            const u32 item = (cur < lead) ? cur + n_dense : (cur < lead + n_dense) ? cur - lead : cur;
             long long pi0 = 0;
             u32 pcls = 0;
-            if (prof) pi0 = clock64();
+            if (prof) {
+                pi0 = clock64();
+                if (plast == 0) pgap0 += (unsigned long long)(pi0 - pc1w); else pgap += (unsigned long long)(pi0 - plast);
+            }
             if (item < n_dense) {
                 // dense prime (p <= tile/72): lane -> (strand j, sub-sequence s), word stride p (byte stride 4p),
                 // constant mask; every lane has count = H-1 .. H+1 >= 17 hits (H = tile / 4p).
@@ -295,14 +317,24 @@ __global__ void __launch_bounds__(THREADS, (THREADS <= 768) ? 2 : 1) k_sieve(con
                     }
                 }
             }
-            if (prof) pw[pcls] += (unsigned long long)(clock64() - pi0);
+            if (prof) {
+                plast = clock64();
+                pw[pcls] += (unsigned long long)(plast - pi0);
+            }
         }
+        long long pend = 0;
+        if (prof) pend = clock64();
         __syncthreads();
         if (prof) {
             pc2 = clock64();
-            if (lane == 0)
+            if (lane == 0) {
                 for (u32 c = 0; c < 4; ++c)
                     if (pw[c]) atomicAdd(P.prof + 4 + c, pw[c]);
+                atomicAdd(P.prof + 8, (unsigned long long)(pc2 - pend));   // this warp's wait for the slowest one
+                atomicAdd(P.prof + 9, pgap0);                              // entry of B -> first item
+                atomicAdd(P.prof + 10, pgap);                              // between items (queue)
+                atomicAdd(P.prof + 11, (unsigned long long)(pend - (plast ? plast : pc1w)));   // last item -> loop exit
+            }
         }
 
         // ---- phase C: edge masks, popcounts, coalesced write-out of the bitmap tile
