@@ -388,6 +388,13 @@ int set_kernel_attributes(pss_handle* h) {
     CU_TRY(h, cudaFuncSetAttribute(k_sieve<1024, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
     CU_TRY(h, cudaFuncSetAttribute(k_compact_lut, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kClSmemBytes));
     CU_TRY(h, cudaFuncSetAttribute(k_compact_warp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kCwSmemBytes));
+    CU_TRY(h, cudaFuncSetAttribute(k_bitmap_moments2w, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMom2wSmemBytes));
+    const void* momw[] = {(const void*)k_bitmap_moments_tabw<1, false>, (const void*)k_bitmap_moments_tabw<2, false>,
+                          (const void*)k_bitmap_moments_tabw<3, false>, (const void*)k_bitmap_moments_tabw<4, false>,
+                          (const void*)k_bitmap_moments_tabw<5, false>, (const void*)k_bitmap_moments_tabw<2, true>,
+                          (const void*)k_bitmap_moments_tabw<3, true>,  (const void*)k_bitmap_moments_tabw<4, true>,
+                          (const void*)k_bitmap_moments_tabw<5, true>};
+    for (const void* f : momw) CU_TRY(h, cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMomwSmemBytes));
     return PSS_OK;
 }
 
@@ -836,7 +843,23 @@ int launch_bscan_t(pss_handle* h, const BScanParams& bp) {
 
 template <int K, bool MULTI>
 int launch_moments_t(pss_handle* h, const BScanParams& bp) {
-    if (h->reduce_moments >= 2) {   // byte-table form (default); PSS_REDUCE_MOMENTS=1 selects the per-prime walk
+    static const bool moments_wide = env_u32("PSS_MOMENTS_WIDE", 1) != 0;
+    // position-specific byte tables (128 KiB, one 768-thread CTA per SM): k >= 4 only (k = 1 and all powers 1..2 read one or
+    // two fields of an entry and are as fast with the small table, k = 2 has its own kernel, k = 3 measured 0.50 / 0.63 ms
+    // against 0.51 / 0.58 ms for the single power / all powers), and only where every SM gets at
+    // least two rounds of warp tiles -- below that the 128 KiB table fill per CTA costs more than the shorter loop saves
+    // (tools/moments_probe.py: 46 / 54 / 69 us against 48 / 64 / 78 us at 9.8e8 for k = 4, 5 and all powers 1..5; 24 - 30
+    // against 20 - 24 us at 8.6e7)
+    const u64 n_warp_tiles = (u64)bp.n_tiles * (kBsThreads / 32);
+    if (h->reduce_moments >= 2 && moments_wide && K >= 4 && n_warp_tiles >= 2ull * h->sm_count * (kMomwThreads / 32)) {
+        const u32 grid_w = std::min<u32>((bp.n_tiles * (kBsThreads / 32) + kMomwThreads / 32 - 1) / (kMomwThreads / 32), (u32)h->sm_count);
+        if (h->dry) return PSS_OK;
+        k_bitmap_moments_tabw<K, MULTI><<<grid_w, kMomwThreads, kMomwSmemBytes, h->stream>>>(bp);
+        CU_TRY(h, cudaGetLastError());
+        h->launches++;
+        return PSS_OK;
+    }
+    if (h->reduce_moments >= 2) {   // byte-table form; PSS_REDUCE_MOMENTS=1 selects the per-prime walk
         int occ_t = 1;
         PSS_TRY(occ_of(h, k_bitmap_moments_tab<K, MULTI>, kBsThreads, 0, &occ_t));
         const u32 grid_t = std::min<u32>(bp.n_tiles, (u32)(h->sm_count * occ_t));
@@ -1011,7 +1034,14 @@ int bitmap_reduce(pss_handle* h, u32 K, bool multi, bool defer_sync = false) {
     bp.col_prefix = static_cast<const u64*>(h->col_prefix.p);
     CU_TRY(h, mark(h, 4));
     if (!h->dry) CU_TRY(h, cudaMemsetAsync(bp.cols, 0, (size_t)ncols * bp.col_stride * sizeof(u64), h->stream));
-    if (K == 2 && !multi && h->reduce_moments) {
+    static const bool moments2_wide = env_u32("PSS_MOMENTS2_WIDE", 1) != 0;
+    if (K == 2 && !multi && h->reduce_moments && moments2_wide) {
+        // one 1024-thread CTA per SM (128 KiB of tables); a scan tile is 8 warp tiles whatever the CTA size
+        const u32 grid = std::min<u32>((bp.n_tiles * (kBsThreads / 32) + kMom2wThreads / 32 - 1) / (kMom2wThreads / 32), (u32)h->sm_count);
+        if (!h->dry) k_bitmap_moments2w<<<grid, kMom2wThreads, kMom2wSmemBytes, h->stream>>>(bp);
+        CU_TRY(h, cudaGetLastError());
+        h->launches++;
+    } else if (K == 2 && !multi && h->reduce_moments) {
         int occ = 1;
         PSS_TRY(occ_of(h, k_bitmap_moments2, kBsThreads, 0, &occ));
         const u32 grid = std::min<u32>(bp.n_tiles, (u32)(h->sm_count * occ));

@@ -1079,6 +1079,126 @@ __global__ void __launch_bounds__(kBsThreads, 3) k_bitmap_moments_tab(const __gr
     }
 }
 
+// ---- the same pass with position-specific byte tables (default; PSS_MOMENTS_WIDE=0 selects the kernel above) --------------
+// Entry (q, v): sigma_i = sum of (R[j] + 30 q)^i over the set bits of v -- the moments of byte v AT byte position q about the
+// WORD origin -- packed so that the four entries of a word add up field by field without overflow (maxima with every bit of
+// the word set: sigma_1 1920 < 2^12, sigma_2 153 440 < 2^18, sigma_3 13 795 200 < 2^24, sigma_4 1 322 586 272 < 2^31,
+// sigma_5 132 046 281 600 < 2^38):
+//     .x = sigma_4      (.y, .z) as one u64 = sigma_5 | sigma_3 << 38      .w = sigma_1 | sigma_2 << 12
+// so the word moments are w_0 = POPC, w_1..w_5 = the fields of the sum: 4 lookups (PRMT + LDS.128 each), 3 + 3 + 6 adds, 5
+// field extractions -- all the byte-index weighting of the kernel above (14 weighted sums, 15 field extractions, 15
+// multiply-adds per word) is gone.  Layout as in k_bitmap_moments2w: 256-byte rows, row v of a table pair = 8 replicas of
+// (q even, v) then 8 replicas of (q odd, v), lane l reads replica l & 7 (the eight lanes of an LDS.128 phase hit eight
+// different 16-byte bank groups); 2 x 64 KiB, one 768-thread CTA per SM (85 registers per thread available).
+constexpr int kMomwThreads = 768;
+constexpr size_t kMomwSmemBytes = 2 * 65536;
+
+template <int Q>
+__device__ __forceinline__ uint4 lutw_at(const char* tab, u32 w, u32 lane16) {
+    u32 d;
+    asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(w), "r"(lane16), "n"(0x5504 + 0x10 * Q));   // v << 8 | (lane & 7) << 4
+    uint4 e = *reinterpret_cast<const uint4*>(tab + d + (Q >> 1) * 65536 + (Q & 1) * 128);
+    // keep it ONE LDS.128 even where a power configuration ignores some fields: narrower loads of the same entry would put
+    // the four lanes that share a replica on one bank (measured: k = 3 at 0.79 ms against 0.51 ms)
+    asm volatile("" : "+r"(e.x), "+r"(e.y), "+r"(e.z), "+r"(e.w));
+    return e;
+}
+
+template <int K, bool MULTI>
+__global__ void __launch_bounds__(kMomwThreads, 1) k_bitmap_moments_tabw(const __grid_constant__ BScanParams P) {
+    constexpr int NWARP = kMomwThreads / 32, TILE_WARPS = kBsThreads / 32, WPT = kWordsPerThread, WARP_WORDS = 32 * WPT;
+    extern __shared__ uint4 momw_smem[];
+    char* const tab = reinterpret_cast<char*>(momw_smem);
+    for (u32 idx = threadIdx.x; idx < 1024u; idx += kMomwThreads) {
+        const u32 v = idx & 255u, q = idx >> 8;
+        u64 sg[6] = {0, 0, 0, 0, 0, 0};
+#pragma unroll
+        for (u32 j = 0; j < 8; ++j)
+            if ((v >> j) & 1u) {
+                const u64 r = wheel_residue(j) + 30u * q;
+                u64 pw = 1;
+#pragma unroll
+                for (int i = 0; i < 6; ++i) { sg[i] += pw; pw *= r; }
+            }
+        const u64 yz = sg[5] | (sg[3] << 38);
+        const uint4 e = make_uint4((u32)sg[4], (u32)yz, (u32)(yz >> 32), (u32)sg[1] | ((u32)sg[2] << 12));
+        uint4* row = reinterpret_cast<uint4*>(tab + (q >> 1) * 65536u + v * 256u + (q & 1u) * 128u);
+        for (u32 k = 0; k < 8; ++k) row[(k + v) & 7u] = e;
+    }
+    __syncthreads();
+    const u32 lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    const u32 lane16 = (lane & 7u) << 4;
+    const u64 n_warp_tiles = (u64)P.n_tiles * TILE_WARPS;
+    const u64 warp_stride = (u64)gridDim.x * NWARP;
+    for (u64 wt = (u64)blockIdx.x * NWARP + warp; wt < n_warp_tiles; wt += warp_stride) {
+        const u32 tile = (u32)(wt / TILE_WARPS);
+        const u64 word0 = wt * WARP_WORDS + (u64)lane * WPT;      // this thread's first word
+        const uint4* g4 = reinterpret_cast<const uint4*>(P.bitmap + word0);
+        // D(e,i) = sum over the thread's words of (word index)^e * w_i(word); same accumulator widths as the kernel above
+        u32 D00 = 0, D01 = 0, D02 = 0, D03 = 0, D10 = 0, D11 = 0, D12 = 0, D13 = 0, D20 = 0, D21 = 0, D22 = 0, D30 = 0, D31 = 0,
+            D40 = 0, D41 = 0, D50 = 0;
+        u64 D04 = 0, D05 = 0, D14 = 0, D23 = 0, D32 = 0;
+#pragma unroll 1
+        for (int g = 0; g < WPT / 4; ++g) {
+            uint4 vv = make_uint4(0, 0, 0, 0);
+            if (word0 + 4ull * g + 4 <= P.n_words) vv = __ldg(g4 + g);
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                const u32 w = c == 0 ? vv.x : c == 1 ? vv.y : c == 2 ? vv.z : vv.w;
+                const u32 wi = 4u * (u32)g + (u32)c, wi2 = wi * wi, wi3 = wi2 * wi, wi4 = wi2 * wi2, wi5 = wi4 * wi;   // <= 23^5
+                const uint4 e0 = lutw_at<0>(tab, w, lane16), e1 = lutw_at<1>(tab, w, lane16), e2 = lutw_at<2>(tab, w, lane16),
+                            e3 = lutw_at<3>(tab, w, lane16);
+                const u32 w0 = __popc(w);
+                const u32 sw = e0.w + e1.w + e2.w + e3.w;
+                const u32 w1 = sw & 0xFFFu;
+                D00 += w0; D01 += w1;
+                D10 += wi * w0;
+                if constexpr (K >= 2) {
+                    const u32 w2 = sw >> 12;
+                    D02 += w2; D11 += wi * w1; D20 += wi2 * w0;
+                    if constexpr (K >= 3) {
+                        const u64 syz = (((u64)e0.z << 32) | e0.y) + (((u64)e1.z << 32) | e1.y) + (((u64)e2.z << 32) | e2.y) +
+                                        (((u64)e3.z << 32) | e3.y);
+                        const u32 w3 = (u32)(syz >> 38);
+                        D03 += w3; D12 += wi * w2; D21 += wi2 * w1; D30 += wi3 * w0;
+                        if constexpr (K >= 4) {
+                            const u32 w4 = e0.x + e1.x + e2.x + e3.x;
+                            D04 += w4; D13 += wi * w3; D22 += wi2 * w2; D31 += wi3 * w1; D40 += wi4 * w0;
+                            if constexpr (K >= 5) {
+                                const u64 w5 = syz & ((1ull << 38) - 1ull);
+                                D05 += w5; D14 += (u64)wi * w4; D23 += (u64)wi2 * w3; D32 += (u64)wi3 * w2; D41 += wi4 * w1; D50 += wi5 * w0;
+                            }
+                        }
+                    }
+                }
+            }
+        }
+        // thread moments about the thread origin (word i sits at 120 i):  M_j = sum_i C(j,i) 120^(j-i) D(j-i, i)
+        const u32 M0 = D00;
+        const u32 M1 = D01 + 120u * D10;
+        const u64 M2 = (u64)D02 + 240ull * D11 + 14400ull * D20;
+        const u64 M3 = (u64)D03 + 360ull * D12 + 43200ull * D21 + 1728000ull * D30;
+        const u64 M4 = D04 + 480ull * D13 + 86400ull * D22 + 6912000ull * D31 + 207360000ull * D40;
+        const unsigned __int128 M5 = (unsigned __int128)D05 + (unsigned __int128)D14 * 600u + (unsigned __int128)D23 * 144000u +
+                                     (unsigned __int128)D32 * 17280000u + (unsigned __int128)D41 * 1036800000u +
+                                     (unsigned __int128)D50 * 24883200000ull;
+        BsMomFn<K> mf{0u, M1, M2, M3, M4, (u64)M5, (u32)(M5 >> 64)};
+        u32 cnt = M0;
+        const u64 B = (P.B_start + 4ull * word0) * 30ull;
+        const bool has_small = (wt == 0 && lane == 0 && P.n_small > 0);
+        const u64 gthread = wt * 32 + lane;
+        const u32 m0 = cnt;
+        if (has_small) cnt += P.n_small;
+        P.thread_rec[gthread] = cnt;
+        moments_emit<0, K, MULTI>(P, mf, m0, (u32)B, (u32)(B >> 32), has_small, gthread, wt, tile, lane);
+        cnt = __reduce_add_sync(0xFFFFFFFFu, cnt);
+        if (lane == 0) {
+            P.warp_rec[wt] = cnt;
+            atomicAdd(reinterpret_cast<unsigned long long*>(P.cols + tile), (unsigned long long)cnt);
+        }
+    }
+}
+
 // s_lut[(byte q of w) * 32 + lane] through its 32-bit shared address (lut_lane = &s_lut[lane])
 __device__ __forceinline__ u32 lut_at(u32 lut_lane, u32 w, int q) {
     u32 b, e;
@@ -1143,6 +1263,97 @@ __global__ void __launch_bounds__(kBsThreads) k_bitmap_moments2(const __grid_con
             const u32 m0 = W & 127u;
             const u32 m1 = ((W >> 7) & 1023u) + 30u * (V & 127u);                    // about the word origin
             const u32 m2 = (W >> 17) + 60u * ((V >> 7) & 1023u) + 900u * (U & 127u);
+            M0 += m0;
+            A1 += m1;
+            A2 += m2;
+            C1 += (u32)i * m0;
+            C2 += (u32)(i * i) * m0;
+            D1 += (u32)i * m1;
+        }
+        const u32 M1 = A1 + 120u * C1;
+        const u64 M2 = (u64)A2 + 240ull * D1 + 14400ull * C2;
+        // thread sum = M0 * B^2 + 2 B M1 + M2
+        const u64 B = (P.B_start + 4ull * word0) * 30ull;
+        const u32 blo = (u32)B, bhi = (u32)(B >> 32);
+        u32 acc[4] = {0, 0, 0, 0};
+        {
+            Big<2> b1;  b1.v[0] = blo;  b1.v[1] = bhi;
+            Big<3> b2;  big_mul_p<3, 2>(b2, b1, blo, bhi);
+            Big<4> t;   big_mul_p<4, 3>(t, b2, M0, 0u);
+            acc_add<0, 4, 4>(acc, t.v);
+            Big<2> m;   m.v[0] = 2u * M1;  m.v[1] = 0u;
+            Big<3> x;   big_mul_p<3, 2>(x, m, blo, bhi);
+            acc_add<0, 4, 3>(acc, x.v);
+            const u32 m2v[2] = {(u32)M2, (u32)(M2 >> 32)};
+            acc_add<0, 4, 2>(acc, m2v);
+        }
+        u32 cnt = M0;
+        if (wt == 0 && lane == 0 && P.n_small > 0) {
+            for (u32 i = 0; i < P.n_small; ++i) square_acc4(acc, (u32)P.small_primes[i], 0u);
+            cnt += P.n_small;
+        }
+        bs_reduce_tail<2, false>(P, acc, cnt, wt, tile, lane);
+    }
+}
+
+// ---- the same pass with position-specific byte tables (default; PSS_MOMENTS2_WIDE=0 selects the kernel above) -------------
+// Four tables, one per byte position q of a word: entry (q, v) = sum r' | sum r'^2 << 12 over the set bits of v with
+// r' = wheel residue + 30 q, i.e. the moments about the WORD origin, so the four entries of a word simply add up (fields sized
+// for the sum: 2368 < 2^12, 453 152 < 2^19) and the count is a POPC.  That removes the byte-index weighting (V, U and the
+// field arithmetic around them: ~36 -> ~20 instructions per word).  Layout: 256-byte rows, row v of a table PAIR holds the 32
+// per-lane replicas of (q even, v) in its first 128 bytes and those of (q odd, v) in the second, so the address of a lookup
+// is (v << 8 | lane << 2) + constant: ONE PRMT builds it from the bitmap word and the lane offset, the constant goes into
+// the LDS immediate.  2 x 64 KiB of shared memory, one 1024-thread CTA per SM; records bit-identical to the kernel above.
+constexpr int kMom2wThreads = 1024;
+constexpr size_t kMom2wSmemBytes = 2 * 65536;
+
+template <int Q>
+__device__ __forceinline__ u32 lut4_at(const char* tab, u32 w, u32 lane4) {
+    u32 d;
+    asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(w), "r"(lane4), "n"(0x5504 + 0x10 * Q));   // v << 8 | lane << 2
+    return *reinterpret_cast<const u32*>(tab + d + (Q >> 1) * 65536 + (Q & 1) * 128);
+}
+
+__global__ void __launch_bounds__(kMom2wThreads, 1) k_bitmap_moments2w(const __grid_constant__ BScanParams P) {
+    constexpr int NWARP = kMom2wThreads / 32, TILE_WARPS = kBsThreads / 32, WPT = kWordsPerThread, WARP_WORDS = 32 * WPT;
+    extern __shared__ uint4 mom2w_smem[];
+    char* const tab = reinterpret_cast<char*>(mom2w_smem);
+    {
+        const u32 v = threadIdx.x & 255u, q = threadIdx.x >> 8;     // 1024 threads: one (position, byte value) each
+        u32 r1 = 0, r2 = 0;
+#pragma unroll
+        for (u32 j = 0; j < 8; ++j)
+            if ((v >> j) & 1u) {
+                const u32 r = wheel_residue(j) + 30u * q;
+                r1 += r; r2 += r * r;
+            }
+        const u32 e = r1 | (r2 << 12);
+        u32* row = reinterpret_cast<u32*>(tab + (q >> 1) * 65536u + v * 256u + (q & 1u) * 128u);
+        for (u32 k = 0; k < 32; ++k) row[(k + v) & 31u] = e;
+    }
+    __syncthreads();
+    const u32 lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    const u32 lane4 = lane << 2;
+    const u64 n_warp_tiles = (u64)P.n_tiles * TILE_WARPS;
+    const u64 warp_stride = (u64)gridDim.x * NWARP;
+    for (u64 wt = (u64)blockIdx.x * NWARP + warp; wt < n_warp_tiles; wt += warp_stride) {
+        const u32 tile = (u32)(wt / TILE_WARPS);
+        const u64 word0 = wt * WARP_WORDS + (u64)lane * WPT;      // this thread's first word
+        const uint4* g4 = reinterpret_cast<const uint4*>(P.bitmap + word0);
+        uint4 v[WPT / 4];
+#pragma unroll
+        for (int q = 0; q < WPT / 4; ++q) {
+            v[q] = make_uint4(0, 0, 0, 0);
+            if (word0 + 4ull * q + 4 <= P.n_words) v[q] = __ldg(g4 + q);
+        }
+        // M1 = sum m1 + 120 sum i m0,  M2 = sum m2 + 240 sum i m1 + 14400 sum i^2 m0 (all partial sums fit 32 bits)
+        u32 M0 = 0, A1 = 0, A2 = 0, C1 = 0, C2 = 0, D1 = 0;
+#pragma unroll
+        for (int i = 0; i < WPT; ++i) {
+            const uint4 vv = v[i >> 2];
+            const u32 w = (i & 3) == 0 ? vv.x : (i & 3) == 1 ? vv.y : (i & 3) == 2 ? vv.z : vv.w;
+            const u32 W = lut4_at<0>(tab, w, lane4) + lut4_at<1>(tab, w, lane4) + lut4_at<2>(tab, w, lane4) + lut4_at<3>(tab, w, lane4);
+            const u32 m0 = __popc(w), m1 = W & 4095u, m2 = W >> 12;    // about the word origin
             M0 += m0;
             A1 += m1;
             A2 += m2;

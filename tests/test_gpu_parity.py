@@ -456,6 +456,35 @@ def test_moment_reduce_matches_walk_and_oracle(orc):
         h.close()
 
 
+def test_wide_table_block_sums_match_chain_at_scale():
+    """the position-specific byte tables (k_bitmap_moments2w for k = 2, k_bitmap_moments_tabw for k >= 4 once every SM has two
+    rounds of warp tiles: ranges of 6.6e8 integers and more) against the per-prime power chain (PSS_REDUCE_MOMENTS=0) on the
+    same ranges, below and above 2^32, and through a search whose hit sits inside such a range (thread / warp records)"""
+    from pss_b200 import _lib, search
+    os.environ["PSS_REDUCE_MOMENTS"] = "0"
+    try:
+        h_chain = _lib.Handle(-1)
+    finally:
+        del os.environ["PSS_REDUCE_MOMENTS"]
+    h_tab = _lib.Handle(-1)
+    for lo, hi in [(0, 700_000_000), (2 ** 36 + 12345, 2 ** 36 + 700_000_000), (3, 1_400_000_011)]:
+        for power, multi in [(2, False), (4, False), (5, False), (4, True), (5, True), (3, False)]:
+            assert h_tab.slice_sieve_sums(lo, hi, power, multi) == h_chain.slice_sieve_sums(lo, hi, power, multi), (lo, hi, power, multi)
+    n_hit, n_max = 20_000_123, 36_000_000
+    for power, multi in [(4, False), (5, False), (5, True), (2, False)]:
+        ref = search.search(1, n_hit, power=power, all_powers=multi, handle=h_chain)
+        target = ref.powers[-1].final_sum
+        a = search.search(target, n_max, power=power, all_powers=multi, handle=h_tab)
+        b = search.search(target, n_max, power=power, all_powers=multi, handle=h_chain)
+        assert a.first() == (n_hit, power) == b.first()
+        assert a.last_prime == b.last_prime
+        for pa, pb in zip(a.powers, b.powers):
+            assert (pa.final_sum, pa.cross_n, pa.cross_prime, pa.sum_at_cross, pa.sum_before_cross) == \
+                   (pb.final_sum, pb.cross_n, pb.cross_prime, pb.sum_at_cross, pb.sum_before_cross)
+    h_chain.close()
+    h_tab.close()
+
+
 def test_fused_slices_compose(handle, orc):
     """fused multi-GPU decomposition on one device: slice_sieve_sums / slice_scan_bitmap with carries"""
     from pss_b200 import search

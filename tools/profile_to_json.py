@@ -81,9 +81,9 @@ def main():
             if name in k["kernel"]:
                 return k
         return None
-    pairs = {"k_sieve": ["k_sieve"], "k_bitmap_moments2+k_scan_columns": ["k_bitmap_moments2", "k_scan_columns"],
+    pairs = {"k_sieve": ["k_sieve"], "k_bitmap_moments2+k_scan_columns": ["k_bitmap_moments2w", "k_scan_columns"],
              "k_bitmap_scan<compare>": ["k_bitmap_scan<2, 0, 1>"], "k_bitmap_scan<reduce>+k_scan_columns": ["k_bitmap_scan<2, 0, 0>", "k_scan_columns"],
-             "k_bitmap_moments_tab+k_scan_columns": ["k_bitmap_moments_tab<5, 1>", "k_scan_columns"],
+             "k_bitmap_moments_tab+k_scan_columns": ["k_bitmap_moments_tabw<5, 1>", "k_scan_columns"],
              "k_compact": ["k_compact"], "k_compact_lut": ["k_compact_lut"],
              "k_power_tiles+k_scan_columns+k_power_walk": ["k_power_tiles<2, 0, 16>", "k_scan_columns", "k_power_walk<2, 0, 1, 16>"]}
     for label, names in pairs.items():
