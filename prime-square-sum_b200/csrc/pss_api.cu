@@ -844,14 +844,13 @@ int launch_bscan_t(pss_handle* h, const BScanParams& bp) {
 template <int K, bool MULTI>
 int launch_moments_t(pss_handle* h, const BScanParams& bp) {
     static const bool moments_wide = env_u32("PSS_MOMENTS_WIDE", 1) != 0;
-    // position-specific byte tables (128 KiB, one 768-thread CTA per SM): k >= 4 only (k = 1 and all powers 1..2 read one or
-    // two fields of an entry and are as fast with the small table, k = 2 has its own kernel, k = 3 measured 0.50 / 0.63 ms
-    // against 0.51 / 0.58 ms for the single power / all powers), and only where every SM gets at
-    // least two rounds of warp tiles -- below that the 128 KiB table fill per CTA costs more than the shorter loop saves
-    // (tools/moments_probe.py: 46 / 54 / 69 us against 48 / 64 / 78 us at 9.8e8 for k = 4, 5 and all powers 1..5; 24 - 30
-    // against 20 - 24 us at 8.6e7)
+    // position-specific byte tables (128 KiB, one 768-thread CTA per SM; 64-bit entries for k <= 3, 128-bit for k = 4, 5; k = 2
+    // alone has its own kernel): only where every SM gets at least two rounds of warp tiles -- below that the 128 KiB table
+    // fill per CTA costs more than the shorter loop saves (tools/moments_probe.py: 46 / 54 / 69 us against 48 / 64 / 78 us at
+    // 9.8e8 for k = 4, 5 and all powers 1..5; 24 - 30 against 20 - 24 us at 8.6e7).  PSS_MOMENTS_WIDE_MIN_K raises the lowest k.
     const u64 n_warp_tiles = (u64)bp.n_tiles * (kBsThreads / 32);
-    if (h->reduce_moments >= 2 && moments_wide && K >= 4 && n_warp_tiles >= 2ull * h->sm_count * (kMomwThreads / 32)) {
+    static const u32 moments_wide_min_k = env_u32("PSS_MOMENTS_WIDE_MIN_K", 1);
+    if (h->reduce_moments >= 2 && moments_wide && K >= (int)moments_wide_min_k && n_warp_tiles >= 2ull * h->sm_count * (kMomwThreads / 32)) {
         const u32 grid_w = std::min<u32>((bp.n_tiles * (kBsThreads / 32) + kMomwThreads / 32 - 1) / (kMomwThreads / 32), (u32)h->sm_count);
         if (h->dry) return PSS_OK;
         k_bitmap_moments_tabw<K, MULTI><<<grid_w, kMomwThreads, kMomwSmemBytes, h->stream>>>(bp);

@@ -1104,8 +1104,20 @@ __device__ __forceinline__ uint4 lutw_at(const char* tab, u32 w, u32 lane16) {
     return e;
 }
 
+// k <= 3: the three moments fit one 64-bit entry (sigma_1 | sigma_2 << 12 | sigma_3 << 30, 54 bits), 16 replicas of 8 bytes per
+// half row: the 16 lanes of an LDS.64 phase read 16 different bank pairs
+template <int Q>
+__device__ __forceinline__ u64 lutn_at(const char* tab, u32 w, u32 lane8) {
+    u32 d;
+    asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(w), "r"(lane8), "n"(0x5504 + 0x10 * Q));    // v << 8 | (lane & 15) << 3
+    uint2 e = *reinterpret_cast<const uint2*>(tab + d + (Q >> 1) * 65536 + (Q & 1) * 128);
+    asm volatile("" : "+r"(e.x), "+r"(e.y));     // one LDS.64 whatever fields the power configuration uses
+    return ((u64)e.y << 32) | e.x;
+}
+
 template <int K, bool MULTI>
 __global__ void __launch_bounds__(kMomwThreads, 1) k_bitmap_moments_tabw(const __grid_constant__ BScanParams P) {
+    constexpr bool NARROW = K <= 3;
     constexpr int NWARP = kMomwThreads / 32, TILE_WARPS = kBsThreads / 32, WPT = kWordsPerThread, WARP_WORDS = 32 * WPT;
     extern __shared__ uint4 momw_smem[];
     char* const tab = reinterpret_cast<char*>(momw_smem);
@@ -1120,14 +1132,21 @@ __global__ void __launch_bounds__(kMomwThreads, 1) k_bitmap_moments_tabw(const _
 #pragma unroll
                 for (int i = 0; i < 6; ++i) { sg[i] += pw; pw *= r; }
             }
-        const u64 yz = sg[5] | (sg[3] << 38);
-        const uint4 e = make_uint4((u32)sg[4], (u32)yz, (u32)(yz >> 32), (u32)sg[1] | ((u32)sg[2] << 12));
-        uint4* row = reinterpret_cast<uint4*>(tab + (q >> 1) * 65536u + v * 256u + (q & 1u) * 128u);
-        for (u32 k = 0; k < 8; ++k) row[(k + v) & 7u] = e;
+        char* const row_b = tab + (q >> 1) * 65536u + v * 256u + (q & 1u) * 128u;
+        if constexpr (NARROW) {
+            const u64 e = sg[1] | (sg[2] << 12) | (sg[3] << 30);
+            u64* row = reinterpret_cast<u64*>(row_b);
+            for (u32 k = 0; k < 16; ++k) row[(k + v) & 15u] = e;
+        } else {
+            const u64 yz = sg[5] | (sg[3] << 38);
+            const uint4 e = make_uint4((u32)sg[4], (u32)yz, (u32)(yz >> 32), (u32)sg[1] | ((u32)sg[2] << 12));
+            uint4* row = reinterpret_cast<uint4*>(row_b);
+            for (u32 k = 0; k < 8; ++k) row[(k + v) & 7u] = e;
+        }
     }
     __syncthreads();
     const u32 lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
-    const u32 lane16 = (lane & 7u) << 4;
+    const u32 lane16 = NARROW ? (lane & 15u) << 3 : (lane & 7u) << 4;
     const u64 n_warp_tiles = (u64)P.n_tiles * TILE_WARPS;
     const u64 warp_stride = (u64)gridDim.x * NWARP;
     for (u64 wt = (u64)blockIdx.x * NWARP + warp; wt < n_warp_tiles; wt += warp_stride) {
@@ -1146,9 +1165,25 @@ __global__ void __launch_bounds__(kMomwThreads, 1) k_bitmap_moments_tabw(const _
             for (int c = 0; c < 4; ++c) {
                 const u32 w = c == 0 ? vv.x : c == 1 ? vv.y : c == 2 ? vv.z : vv.w;
                 const u32 wi = 4u * (u32)g + (u32)c, wi2 = wi * wi, wi3 = wi2 * wi, wi4 = wi2 * wi2, wi5 = wi4 * wi;   // <= 23^5
+                const u32 w0 = __popc(w);
+                if constexpr (NARROW) {
+                    const u64 sn = lutn_at<0>(tab, w, lane16) + lutn_at<1>(tab, w, lane16) + lutn_at<2>(tab, w, lane16) +
+                                   lutn_at<3>(tab, w, lane16);
+                    const u32 w1 = (u32)sn & 0xFFFu;
+                    D00 += w0; D01 += w1;
+                    D10 += wi * w0;
+                    if constexpr (K >= 2) {
+                        const u32 w2 = (u32)(sn >> 12) & 0x3FFFFu;
+                        D02 += w2; D11 += wi * w1; D20 += wi2 * w0;
+                        if constexpr (K >= 3) {
+                            const u32 w3 = (u32)(sn >> 30);
+                            D03 += w3; D12 += wi * w2; D21 += wi2 * w1; D30 += wi3 * w0;
+                        }
+                    }
+                    continue;
+                }
                 const uint4 e0 = lutw_at<0>(tab, w, lane16), e1 = lutw_at<1>(tab, w, lane16), e2 = lutw_at<2>(tab, w, lane16),
                             e3 = lutw_at<3>(tab, w, lane16);
-                const u32 w0 = __popc(w);
                 const u32 sw = e0.w + e1.w + e2.w + e3.w;
                 const u32 w1 = sw & 0xFFFu;
                 D00 += w0; D01 += w1;

@@ -457,8 +457,8 @@ def test_moment_reduce_matches_walk_and_oracle(orc):
 
 
 def test_wide_table_block_sums_match_chain_at_scale():
-    """the position-specific byte tables (k_bitmap_moments2w for k = 2, k_bitmap_moments_tabw for k >= 4 once every SM has two
-    rounds of warp tiles: ranges of 6.6e8 integers and more) against the per-prime power chain (PSS_REDUCE_MOMENTS=0) on the
+    """the position-specific byte tables (k_bitmap_moments2w for k = 2, k_bitmap_moments_tabw for every other k <= 5 once every
+    SM has two rounds of warp tiles: ranges of 6.6e8 integers and more) against the per-prime power chain (PSS_REDUCE_MOMENTS=0) on the
     same ranges, below and above 2^32, and through a search whose hit sits inside such a range (thread / warp records)"""
     from pss_b200 import _lib, search
     os.environ["PSS_REDUCE_MOMENTS"] = "0"
@@ -468,10 +468,10 @@ def test_wide_table_block_sums_match_chain_at_scale():
         del os.environ["PSS_REDUCE_MOMENTS"]
     h_tab = _lib.Handle(-1)
     for lo, hi in [(0, 700_000_000), (2 ** 36 + 12345, 2 ** 36 + 700_000_000), (3, 1_400_000_011)]:
-        for power, multi in [(2, False), (4, False), (5, False), (4, True), (5, True), (3, False)]:
+        for power, multi in [(2, False), (4, False), (5, False), (4, True), (5, True), (3, False), (1, False), (2, True), (3, True)]:
             assert h_tab.slice_sieve_sums(lo, hi, power, multi) == h_chain.slice_sieve_sums(lo, hi, power, multi), (lo, hi, power, multi)
     n_hit, n_max = 20_000_123, 36_000_000
-    for power, multi in [(4, False), (5, False), (5, True), (2, False)]:
+    for power, multi in [(4, False), (5, False), (5, True), (2, False), (3, False), (3, True), (1, False)]:
         ref = search.search(1, n_hit, power=power, all_powers=multi, handle=h_chain)
         target = ref.powers[-1].final_sum
         a = search.search(target, n_max, power=power, all_powers=multi, handle=h_tab)
