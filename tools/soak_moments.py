@@ -27,8 +27,12 @@ n = n_orc = 0
 while time.time() - t0 < budget:
     top = rng.choice([10 ** 4, 10 ** 6, 10 ** 8, 2 ** 32, 10 ** 11, 2 ** 40])
     width = rng.choice([1, 30, 2880, 10 ** 5, 3 * 10 ** 6, 4 * 10 ** 7])
+    wide = rng.random() < 0.04
+    if wide:                     # wide enough for the position-specific tables of k != 2 (two rounds of warp tiles per SM)
+        width = rng.choice([7 * 10 ** 8, 15 * 10 ** 8]) + rng.randrange(0, 10 ** 6)
+        top = max(top, 2 * width)
     lo = rng.randrange(0, max(1, top - width))
-    hi = min(2 ** 40, lo + rng.randrange(1, width + 1))
+    hi = min(2 ** 40, lo + (width if wide else rng.randrange(1, width + 1)))
     power, multi = rng.choice(modes)
     a = h_tab.slice_sieve_sums(lo, hi, power, multi)
     b = h_chain.slice_sieve_sums(lo, hi, power, multi)
