@@ -1627,7 +1627,7 @@ __global__ void __launch_bounds__(1024) k_scan_columns(const u64* in, u64* out, 
     const u32 rows_per_warp = (rows + 31u) / 32u;
     const u32 r0 = min(rows, warp * rows_per_warp), r1 = min(rows, r0 + rows_per_warp);
     u64 sum = 0;
-#pragma unroll 4
+#pragma unroll 8
     for (u32 r = r0; r < r1; ++r) {
         const u32 i = r * 32u + lane;
         sum += (i < n) ? col[i] : 0ull;
@@ -1648,7 +1648,8 @@ __global__ void __launch_bounds__(1024) k_scan_columns(const u64* in, u64* out, 
     }
     __syncthreads();
     u64 run = s_warp[warp];
-#pragma unroll 2
+    // (the loads do not depend on the running sum: unrolled so that eight of them are in flight per warp)
+#pragma unroll 8
     for (u32 r = r0; r < r1; ++r) {
         const u32 i = r * 32u + lane;
         const u64 v = (i < n) ? col[i] : 0ull;
