@@ -262,11 +262,15 @@ struct BsCmpFn {
             for (int i = 2; i < W; ++i) small = small && (run[OFF + i] == 0u);
             const u64 S = ((u64)run[OFF + 1] << 32) | run[OFF];
             if (inw && small && S <= P->tri_max_value) {
+                // d < 2^62, so r0 = trunc(sqrt((double) d)) < 2^32 is floor(sqrt d) - 1, floor or floor + 1 (the conversion of d
+                // moves the root by < 2^-22, the rounding of the root by less): d is a square iff it is r0^2, (r0 + 1)^2 or
+                // (r0 - 1)^2 -- one 32 x 32 multiply and three compares instead of correction loops of 64-bit multiplies
                 const u64 d = 8ull * S + 1ull;
-                u64 r = (u64)sqrt((double)d);
-                while (r * r > d) --r;
-                while ((r + 1) * (r + 1) <= d) ++r;
-                if (r * r == d) {
+                const u32 r0 = (u32)(u64)sqrt((double)d);
+                const u64 e = d - (u64)r0 * r0, two_r = 2ull * r0;
+                const bool at = (e == 0ull), above = (e == two_r + 1ull), below_ = (e + two_r == 1ull);
+                if (at || above || below_) {
+                    const u64 r = (u64)r0 + (above ? 1ull : 0ull) - (below_ ? 1ull : 0ull);
                     const u64 m = (r - 1) >> 1;
                     if (m >= P->tri_m_min && m <= P->tri_m_max) {
                         const u32 slot = atomicAdd(P->tri_count, 1u);
