@@ -165,38 +165,56 @@ PSS_HD constexpr u32 binom(int n, int k) {
     return r;
 }
 
-// out[0..W) = sum_j C(k,j) B^(k-j) M_j  (Horner in B; W = sum_limbs(k) limbs, nothing can overflow them)
-template <int KK, int K>
-__device__ __forceinline__ void expand_moments(u32* out, const BsMomFn<K>& f, u32 m0, u32 blo, u32 bhi) {
-    constexpr int W = sum_limbs(KK);
-    Big<W> a;
-    big_zero(a);
-    a.v[0] = m0;
+// out[0..W) = sum_j C(k,j) B^(k-j) M_j  (Horner in B; W = sum_limbs(k) limbs, nothing can overflow them).
+// The running value after step j, a_j = sum_{i<=j} C(k,i) B^(j-i) M_i, is at most 10 * 768 * 2^(40 j) (every binomial ratio
+// C(k,i) / C(j,i) is <= 10 for k <= 5, a thread holds <= 768 primes, all below 2^40), so step j only multiplies the
+// ceil((14 + 40 (j-1)) / 32) limbs that can be non-zero and produces ceil((14 + 40 j) / 32): 2 + 4 + 6 + 10 + 12 limb
+// products for k = 5 instead of 2 + 8 + 14 + 16 + 16.
+template <int KK>
+PSS_HD constexpr int horner_limbs(int j) {
+    return ((14 + 40 * j + 31) / 32 < sum_limbs(KK)) ? (14 + 40 * j + 31) / 32 : sum_limbs(KK);
+}
+
+template <int J, int KK, int K>
+__device__ __forceinline__ void horner_steps(Big<sum_limbs(KK)>& a, const BsMomFn<K>& f, u32 blo, u32 bhi) {
+    if constexpr (J <= KK) {
+        constexpr int LI = horner_limbs<KK>(J - 1), LO = horner_limbs<KK>(J);
+        Big<LI> in;
 #pragma unroll
-    for (int j = 1; j <= KK; ++j) {
-        Big<W> nx;
-        big_mul_p<W, W>(nx, a, blo, bhi);
-        // t = C(KK, j) * M_j  (at most 72 bits)
+        for (int i = 0; i < LI; ++i) in.v[i] = a.v[i];
+        Big<LO> nx;
+        big_mul_p<LO, LI>(nx, in, blo, bhi);
+        // t = C(KK, J) * M_J  (at most 72 bits)
         u64 lo = 0;
         u32 hi = 0;
-        if (j == 1) lo = f.m1;
-        if (j == 2) lo = f.m2;
-        if (j == 3) lo = f.m3;
-        if (j == 4) lo = f.m4;
-        if (j == 5) { lo = f.m5lo; hi = f.m5hi; }
-        const u32 c = binom(KK, j);
+        if (J == 1) lo = f.m1;
+        if (J == 2) lo = f.m2;
+        if (J == 3) lo = f.m3;
+        if (J == 4) lo = f.m4;
+        if (J == 5) { lo = f.m5lo; hi = f.m5hi; }
+        const u32 c = binom(KK, J);
         const u64 p0 = (lo & 0xFFFFFFFFull) * c;
         const u64 p1 = (lo >> 32) * c + (p0 >> 32);
         const u64 p2 = (u64)hi * c + (p1 >> 32);
         const u32 t[3] = {(u32)p0, (u32)p1, (u32)p2};
         u64 cy = 0;
 #pragma unroll
-        for (int i = 0; i < W; ++i) {
+        for (int i = 0; i < LO; ++i) {
             const u64 v = (u64)nx.v[i] + (i < 3 ? (u64)t[i] : 0ull) + cy;
             a.v[i] = (u32)v;
             cy = v >> 32;
         }
+        horner_steps<J + 1, KK, K>(a, f, blo, bhi);
     }
+}
+
+template <int KK, int K>
+__device__ __forceinline__ void expand_moments(u32* out, const BsMomFn<K>& f, u32 m0, u32 blo, u32 bhi) {
+    constexpr int W = sum_limbs(KK);
+    Big<W> a;
+    big_zero(a);
+    a.v[0] = m0;
+    horner_steps<1, KK, K>(a, f, blo, bhi);
 #pragma unroll
     for (int i = 0; i < W; ++i) out[i] = a.v[i];
 }
