@@ -114,3 +114,63 @@ def test_compaction_byte_table_lists_residues_in_order():
         assert dec == res and (hi >> 16) == len(res)
     # (bytes with five to seven primes are common near the origin -- 2.5 % of the first 1e5 bytes -- and vanish quickly as
     # the density falls; the kernel stores the first four with predicated instructions and takes a branch for the rest)
+
+
+# ---- position-specific tables (k_bitmap_moments2w, k_bitmap_moments_tabw) ------------------------------------------------
+def sigma(v, q, i):
+    """moment i of byte value v AT byte position q of a word, about the word origin"""
+    return sum((R[j] + 30 * q) ** i for j in range(8) if (v >> j) & 1)
+
+
+def entry128(v, q):   # .x = sigma_4, (.y, .z) = sigma_5 | sigma_3 << 38, .w = sigma_1 | sigma_2 << 12
+    yz = sigma(v, q, 5) | (sigma(v, q, 3) << 38)
+    return (sigma(v, q, 4), yz & M32, yz >> 32, sigma(v, q, 1) | (sigma(v, q, 2) << 12))
+
+
+def entry64(v, q):    # sigma_1 | sigma_2 << 12 | sigma_3 << 30
+    return sigma(v, q, 1) | (sigma(v, q, 2) << 12) | (sigma(v, q, 3) << 30)
+
+
+def test_position_table_fields_cannot_overflow():
+    """the four entries of a word are ADDED field by field: every field must hold the sum for the all-ones word"""
+    tot = [sum(sigma(0xFF, q, i) for q in range(4)) for i in range(6)]
+    assert tot[1] < 2 ** 12 and tot[2] < 2 ** 18 and tot[3] < 2 ** 24 and tot[4] < 2 ** 31 and tot[5] < 2 ** 38
+    for q in range(4):
+        for v in range(256):
+            e = entry128(v, q)
+            assert all(0 <= c <= M32 for c in e) and (e[2] << 32 | e[1]) < 2 ** 63
+            assert entry64(v, q) < 2 ** 54
+            assert sigma(v, q, 1) | (sigma(v, q, 2) << 12) < 2 ** 31          # the 32-bit entry of the k = 2 kernel
+
+
+def test_position_tables_give_the_word_moments():
+    rng = random.Random(7)
+    words = [0, M32, 1, 1 << 31, 0x80000001] + [rng.getrandbits(32) for _ in range(400)]
+    for w in words:
+        direct = [sum(o ** i for o in offsets_of_word(w)) for i in range(6)]
+        es = [entry128((w >> (8 * q)) & 0xFF, q) for q in range(4)]
+        sx = sum(e[0] for e in es) & M32
+        syz = sum((e[2] << 32) | e[1] for e in es) & (2 ** 64 - 1)
+        sw = sum(e[3] for e in es) & M32
+        got = [bin(w).count("1"), sw & 0xFFF, sw >> 12, syz >> 38, sx, syz & (2 ** 38 - 1)]
+        assert got == direct, hex(w)
+        sn = sum(entry64((w >> (8 * q)) & 0xFF, q) for q in range(4)) & (2 ** 64 - 1)
+        assert [sn & 0xFFF, (sn >> 12) & 0x3FFFF, sn >> 30] == direct[1:4], hex(w)
+        s2 = sum(sigma((w >> (8 * q)) & 0xFF, q, 1) | (sigma((w >> (8 * q)) & 0xFF, q, 2) << 12) for q in range(4)) & M32
+        assert [s2 & 0xFFF, s2 >> 12] == direct[1:3], hex(w)
+
+
+def test_horner_step_widths_hold_the_running_value():
+    """expand_moments: after step j the running value  sum_{i<=j} C(k,i) B^(j-i) M_i  must fit ceil((14 + 40 j) / 32) limbs for
+    the largest base (B + o < 2^40) and a thread full of primes at the top of its block"""
+    from math import comb
+    B = 2 ** 40 - 2880
+    offs = list(range(2880 - 768, 2880))          # 768 offsets, all as large as they can be
+    M = [sum(o ** i for o in offs) for i in range(6)]
+    for k in range(1, 6):
+        a = M[0]
+        for j in range(1, k + 1):
+            a = a * B + comb(k, j) * M[j]
+            limbs = min((14 + 40 * j + 31) // 32, (40 * k + 36 + 31) // 32)
+            assert a < 2 ** (32 * limbs), (k, j)
+        assert a == sum((B + o) ** k for o in offs)
