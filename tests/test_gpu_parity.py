@@ -77,6 +77,21 @@ def test_sieve_tunings_vs_oracle(orc, tile, threads, npat):
     h.close()
 
 
+@pytest.mark.parametrize("lead", [0, 3, 40])
+def test_sieve_queue_orders_vs_oracle(orc, lead):
+    """phase B's work queue: the sparse batches before the dense primes (default), after them (0), or split (3, 40) -- every
+    slot -> item mapping crosses off the same composites"""
+    from pss_b200 import _lib
+    os.environ["PSS_SPARSE_LEAD"] = str(lead)
+    try:
+        h = _lib.Handle(-1)
+    finally:
+        del os.environ["PSS_SPARSE_LEAD"]
+    for lo, hi in [(0, 8_000_000), (10 ** 9, 10 ** 9 + 8_000_000), (22_790_000_000, 22_801_763_490)]:
+        assert np.array_equal(h.generate_primes(lo, hi).astype(np.uint64), orc.c_primes_range(lo, hi)), (lead, lo, hi)
+    h.close()
+
+
 @pytest.mark.parametrize("env", [None, "PSS_COMPACT_WALK", "PSS_COMPACT_BLOCK"])
 def test_compaction_kernels_vs_oracle(orc, env):
     """The three stream-compaction kernels (byte-table form = default, per-prime walk, block-synchronous) write the same
