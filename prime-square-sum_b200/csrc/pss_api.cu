@@ -23,6 +23,7 @@
 
 #include "../../include/pss_b200.h"
 #include "pss_bscan.cuh"
+#include "pss_trihead.cuh"
 #include "pss_peer.cuh"
 #include "pss_scan.cuh"
 #include "pss_sieve.cuh"
@@ -139,6 +140,7 @@ struct pss_handle {
     // sieve workspace / state of the last sieve
     DevBuf bitmap, chunk_counts, tile_counts, tile_prefix, tile_nact;
     u64 nact_key[6] = {0, 0, 0, 0, 0, 0};   // geometry the cached tile_nact table was computed for
+    DevBuf tri_head;     // head pass of the triangular predicate: per-word prefix records + the head's prime count
     DevBuf sieve_prof;   // PSS_SIEVE_PROF=1: k_sieve cycle counters, printed by pss_close
     u64 sv_lo = 0, sv_hi = 0, sv_B_start = 0, sv_total = 0, sv_c235 = 0;
     u32 sv_tile_bytes = 0, sv_n_tiles = 0;
@@ -1481,7 +1483,7 @@ int pss_close(pss_handle* h) {
                 c[0] / n, c[1] / n, c[2] / n, c[4] / n, c[5] / n, c[6] / n, c[7] / n, c[8] / n, c[9] / n, c[10] / n, c[11] / n);
         cudaFree(h->sieve_prof.p);
     }
-    for (DevBuf* b : {&h->d_base, &h->d_base_inv, &h->d_base_strand, &h->d_batch_geo, &h->cols, &h->col_prefix, &h->thread_rec, &h->warp_rec, &h->tile_nact, &h->tri_buf, &h->bitmap, &h->chunk_counts, &h->tile_counts, &h->tile_prefix, &h->primes, &h->status, &h->agg,
+    for (DevBuf* b : {&h->d_base, &h->d_base_inv, &h->d_base_strand, &h->d_batch_geo, &h->cols, &h->col_prefix, &h->thread_rec, &h->warp_rec, &h->tile_nact, &h->tri_buf, &h->tri_head, &h->bitmap, &h->chunk_counts, &h->tile_counts, &h->tile_prefix, &h->primes, &h->status, &h->agg,
                       &h->incl, &h->misc, &h->prefix_out, &h->user_vals})
         if (b->p) cudaFree(b->p);
     for (auto& p : h->d_pat)
@@ -1830,6 +1832,40 @@ int pss_search_tri(pss_handle* h, uint64_t n_min, uint64_t n_max, uint32_t power
         bp.tri_out = static_cast<u64*>(h->tri_buf.p);
         bp.tri_count = &dm->ticket;   // reused as the match counter (zeroed by k_init_misc)
         bp.tri_cap = cap;
+        static const bool tri_head = env_u32("PSS_TRI_HEAD", 1) != 0;
+        if (tri_head && power == 2 && !h->compare_exhaustive) {
+            // word-parallel head pass over the first 32 warp tiles (every sum that can equal a tri(m) < 2^59 lies there); the
+            // scan kernel below then only classifies, walks what the head did not cover and finishes S(n_max)
+            TriHeadParams tp;
+            memset(&tp, 0, sizeof tp);
+            tp.bitmap = bp.bitmap; tp.n_words = bp.n_words; tp.B_start = bp.B_start;
+            const u64 warp_tile_words = 32ull * kWordsPerThread;
+            tp.n_head_words = (u32)std::min<u64>(kTriHeadWords, ((bp.n_words + warp_tile_words - 1) / warp_tile_words) * warp_tile_words);
+            {   // no sum beyond x can be <= tri(m_max) once x^3 / (12 ln x) exceeds it (at least x / (3 ln x) primes in (x/2, x],
+                // each squared >= x^2 / 4); only a size hint -- whatever the head does not cover is tested by the scan kernel
+                double x = 1000.0;
+                while (x * x * x / (12.0 * std::log(x)) <= (double)bp.tri_max_value && x < 4e6) x *= 1.25;
+                const u64 hint_words = (u64)(x / 120.0) + 1;
+                const u64 hint = ((hint_words + warp_tile_words - 1) / warp_tile_words) * warp_tile_words;
+                tp.n_head_words = (u32)std::min<u64>(tp.n_head_words, hint);
+            }
+            tp.n_small = bp.n_small;
+            for (u32 i = 0; i < bp.n_small; ++i) tp.small_primes[i] = bp.small_primes[i];
+            PSS_TRY(ensure(h, h->tri_head, (size_t)kTriHeadWords * (sizeof(u32) + sizeof(u64)) + 16));
+            tp.sum = static_cast<u64*>(h->tri_head.p);
+            tp.head_n = tp.sum + kTriHeadWords;
+            tp.cnt = reinterpret_cast<u32*>(tp.head_n + 1);
+            tp.n_min = n_min; tp.n_max = n_max;
+            tp.tri_m_min = bp.tri_m_min; tp.tri_m_max = bp.tri_m_max; tp.tri_max_value = bp.tri_max_value;
+            tp.tri_out = bp.tri_out; tp.tri_count = bp.tri_count; tp.tri_cap = bp.tri_cap;
+            const u32 grid = (tp.n_head_words + 255u) / 256u;
+            k_tri_head_sums<<<grid, 256, 0, h->stream>>>(tp);
+            k_tri_head_scan<<<1, 1024, 0, h->stream>>>(tp);
+            k_tri_head_test<<<grid, 256, 0, h->stream>>>(tp);
+            CU_TRY(h, cudaGetLastError());
+            h->launches += 3;
+            bp.tri_head_n = tp.head_n;
+        }
         PSS_TRY(launch_bscan_tri(h, bp, power));
     }
     CU_TRY(h, mark(h, 7));

@@ -63,6 +63,7 @@ struct BScanParams {
     u64* tri_out;            // (n, m) pairs
     u32* tri_count;
     u32 tri_cap;
+    const u64* tri_head_n;   // null, or: the first *tri_head_n primes were tested by the word-parallel head pass (pss_trihead.cuh)
 };
 
 // Words are staged BIT-REVERSED: the lowest prime of a word is its most significant set bit m (one FLO).
@@ -256,6 +257,7 @@ struct BsCmpFn {
     u32 eq_li[NP];     // tile-local index with S == target (in window), 0xFFFFFFFF if none
     bool below[NP];    // previous partial sum < target
     u32 cur_lo, cur_hi;
+    u64 tri_head_n = 0;   // triangular predicate: primes with index <= tri_head_n were tested by the head pass
 
     template <int E>
     __device__ __forceinline__ void apply(const Big<pow_limbs(E)>& pe) {
@@ -279,7 +281,7 @@ struct BsCmpFn {
 #pragma unroll
             for (int i = 2; i < W; ++i) small = small && (run[OFF + i] == 0u);
             const u64 S = ((u64)run[OFF + 1] << 32) | run[OFF];
-            if (inw && small && S <= P->tri_max_value) {
+            if (inw && small && S <= P->tri_max_value && tile_n0 + li > tri_head_n) {
                 // d < 2^62, so r0 = trunc(sqrt((double) d)) < 2^32 is floor(sqrt d) - 1, floor or floor + 1 (the conversion of d
                 // moves the root by < 2^-22, the rounding of the root by less): d is a square iff it is r0^2, (r0 + 1)^2 or
                 // (r0 - 1)^2 -- one 32 x 32 multiply and three compares instead of correction loops of 64-bit multiplies
@@ -394,6 +396,7 @@ __global__ void __launch_bounds__(kBsThreads, bs_min_blocks<K, MULTI>()) k_bitma
     const u64 n_warp_tiles = (u64)P.n_tiles * NWARP;
     const u64 warp_stride = (u64)gridDim.x * NWARP;
     const u64 n_first = (MODE != kBsReduce && P.n_first_dev) ? *P.n_first_dev : P.n_first;
+    const u64 tri_head_n = (MODE == kBsTri && P.tri_head_n) ? *P.tri_head_n : 0ull;
 
     // normalised prefix of scan tile t (carry-in + deferred-carry column prefixes), uniform across the warp
     auto tile_prefix = [&](u32 t, u32* out) {
@@ -644,7 +647,8 @@ __global__ void __launch_bounds__(kBsThreads, bs_min_blocks<K, MULTI>()) k_bitma
 #pragma unroll
                     for (int i = 2; i < Lay::width(0); ++i) beyond = beyond || (wpre[i] != 0u);
                     beyond = beyond || ((((u64)wpre[1] << 32) | wpre[0]) > P.tri_max_value);
-                    if (simple && beyond) warp_done = true;
+                    // ... and a warp tile whose last prime lies inside the head pass has been tested there
+                    if (simple && (beyond || tile_n0 + wli0 + wcnt <= tri_head_n + 1ull)) warp_done = true;
                 }
             }
 
@@ -705,21 +709,24 @@ __global__ void __launch_bounds__(kBsThreads, bs_min_blocks<K, MULTI>()) k_bitma
                         //  (S_before, S(n_max)]: no bracket there means no bracket up to n_max)
                         walk = bracket;
                         coop = owns_nmax && !bracket;
-                    } else if (owns_nmax) {
-                        // triangular predicate: the n_max block is always walked
                     } else {
+                        // triangular predicate: a block needs its primes tested unless its prefix is already beyond
+                        // tri(m_max) or the head pass covered it; the n_max block then only owes S(n_max) and p_(n_max),
+                        // which the warp computes together (below) instead of one lane walking ~135 .. 418 primes
                         bool beyond = false;
 #pragma unroll
                         for (int i = 2; i < Lay::width(0); ++i) beyond = beyond || (run[i] != 0u);
                         beyond = beyond || ((((u64)run[1] << 32) | run[0]) > P.tri_max_value);
-                        walk = !beyond;
+                        const bool covered = beyond || (tile_n0 + li0 + have <= tri_head_n + 1ull);
+                        walk = !covered;
+                        coop = owns_nmax && covered;
                     }
                 }
                 a = li0 + skip0;
                 u64 last_p = 0;
                 const u32 coop_mask = __ballot_sync(0xFFFFFFFFu, coop);
                 if (__any_sync(0xFFFFFFFFu, walk) || coop_mask) stage();   // the bitmap is only read where a walk is needed
-                if constexpr (MODE == kBsCompare) {
+                {
                     if (coop_mask) {
                         // ---- S_k(n_max) and p_(n_max) by the whole warp.  One thread of the grid holds n_max; walking its
                         //      block alone is a serial chain of up to ~400 primes (the longest latency of a pruned query), so
@@ -810,9 +817,11 @@ __global__ void __launch_bounds__(kBsThreads, bs_min_blocks<K, MULTI>()) k_bitma
                     };
                     if (skip0 != 0) {
                         BsCmpFn<K, MULTI, PMODE, true> fn{run, &P, tile_n0, li0, quota, skip0, 0, {}, {}, {}, 0, 0};
+                        fn.tri_head_n = tri_head_n;
                         run_walk(fn);
                     } else {
                         BsCmpFn<K, MULTI, PMODE, false> fn{run, &P, tile_n0, li0, quota, 0, 0, {}, {}, {}, 0, 0};
+                        fn.tri_head_n = tri_head_n;
                         run_walk(fn);
                     }
                     if (owns_nmax) {   // exactly one thread in the grid: S(n_max) and p_{n_max}

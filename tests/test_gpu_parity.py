@@ -275,6 +275,15 @@ def test_tri_predicate(handle, orc, golden):
         sums = orc.c_prefix_sums(primes, k)
         exp = [{"m": orc.qtri(s), "n": i + 1} for i, s in enumerate(sums) if orc.qtri(s) is not None and 1 <= orc.qtri(s) <= 2 ** 28]
         assert search.for_any_tri(200000, 2 ** 28, power=k) == sorted(exp, key=lambda d: (d["m"], d["n"])), k
+    # windows in n and m (k = 2: word-parallel head pass + scan kernel; the window edges fall inside the head, at its end
+    # and beyond it)
+    sums2 = orc.c_prefix_sums(primes, 2)
+    allhits = [(i + 1, orc.qtri(s)) for i, s in enumerate(sums2) if orc.qtri(s) is not None]
+    assert len(allhits) >= 2
+    for n_lo, n_hi, m_lo, m_hi in [(1, 6, 1, 10 ** 7), (7, 7, 36, 36), (8, 85, 1, 10 ** 7), (86, 86, 3169, 3169), (1, 200000, 37, 2 ** 29 - 1),
+                                   (5000, 150000, 1, 2 ** 28), (1, 11263, 1, 10 ** 7), (11264, 200000, 1, 10 ** 7), (87, 200000, 1, 2 ** 28)]:
+        exp = sorted(({"m": m, "n": n} for n, m in allhits if n_lo <= n <= n_hi and m_lo <= m <= m_hi), key=lambda d: (d["m"], d["n"]))
+        assert search.for_any_tri(n_hi, m_hi, n_min=n_lo, m_min=m_lo) == exp, (n_lo, n_hi, m_lo, m_hi)
     # within tri(1e7) the only hits of primesum(n,2) are (7,36) and (86,3169)
     assert search.for_any_tri(10 ** 6, 10 ** 7) == [{"m": 36, "n": 7}, {"m": 3169, "n": 86}]
 
