@@ -724,8 +724,136 @@ __global__ void __launch_bounds__(kBsThreads, bs_min_blocks<K, MULTI>()) k_bitma
                 }
                 a = li0 + skip0;
                 u64 last_p = 0;
+                if (__any_sync(0xFFFFFFFFu, walk || coop)) stage();   // the bitmap is only read where a walk is needed
+                bool localised = false;
+                if constexpr (MODE == kBsCompare && !MULTI) {
+                    // ---- the block that brackets the target, localised by the whole warp.  Walking it alone is a serial chain
+                    //      of up to 418 compared primes (tools/hit_probe.py: +0.09 ms for a hit in the densest block).  Lane 0
+                    //      takes the primes below 7 (first block of a range only), lane 1 + i word i of the owner's block:
+                    //      count prefix -> which primes lie at or below n_max -> their power sums -> multi-limb scan ->
+                    //      the ONE chunk whose (S_before, S_after] holds the target is walked by its lane (<= 32 primes);
+                    //      every in-window prime before it compares below, every one after it above.
+                    const u32 loc_mask = P.exhaustive ? 0u : __ballot_sync(0xFFFFFFFFu, walk);
+                    if (loc_mask) {
+                        const int owner = __ffs(loc_mask) - 1;
+                        const u32 o_quota = __shfl_sync(0xFFFFFFFFu, quota, owner);
+                        const u32 o_skip = __shfl_sync(0xFFFFFFFFu, skip0, owner);
+                        const u32 o_li0 = __shfl_sync(0xFFFFFFFFu, li0, owner);
+                        const u32 vb_lo = __shfl_sync(0xFFFFFFFFu, (u32)value_base, owner);
+                        const u32 vb_hi = __shfl_sync(0xFFFFFFFFu, (u32)(value_base >> 32), owner);
+                        const bool o_small = __shfl_sync(0xFFFFFFFFu, has_small ? 1u : 0u, owner) != 0u;
+                        const u64 vb = ((u64)vb_hi << 32) | vb_lo;
+                        u32 o_run[TOTAL];
+#pragma unroll
+                        for (int i = 0; i < TOTAL; ++i) o_run[i] = __shfl_sync(0xFFFFFFFFu, run[i], owner);
+                        u32 w = 0, c = 0;
+                        if (lane == 0) c = o_small ? P.n_small : 0u;
+                        else if ((int)lane <= WPT) { w = my_warp_words[owner * PAD + (int)lane - 1]; c = __popc(w); }
+                        u32 incl_c = c;
+#pragma unroll
+                        for (int d = 1; d < 32; d <<= 1) {
+                            const u32 up = __shfl_up_sync(0xFFFFFFFFu, incl_c, d);
+                            if (lane >= (u32)d) incl_c += up;
+                        }
+                        const u32 pre = incl_c - c;
+                        const u32 take = (o_quota > pre) ? min(c, o_quota - pre) : 0u;
+                        u32 part[TOTAL];
+#pragma unroll
+                        for (int i = 0; i < TOTAL; ++i) part[i] = 0;
+                        {
+                            BsAccFn<K, MULTI> pf{part};
+                            if (lane == 0) {
+                                for (u32 t = 0; t < take; ++t) pf((u32)P.small_primes[t], 0u);
+                            } else {
+                                u32 ww = w;
+                                for (u32 t = 0; t < take; ++t) {
+                                    const u32 m = msb_index(ww);
+                                    ww ^= (1u << m);
+                                    const u64 pv = vb + 120u * (lane - 1u) + msb_value_offset(m);
+                                    pf((u32)pv, (u32)(pv >> 32));
+                                }
+                            }
+                        }
+                        u32 sa[TOTAL];                       // inclusive scan of the chunk sums -> S after the chunk
+#pragma unroll
+                        for (int i = 0; i < TOTAL; ++i) sa[i] = part[i];
+#pragma unroll
+                        for (int d = 1; d < 32; d <<= 1) {
+                            OpShflUpAdd op{sa, d, lane >= (u32)d};
+                            for_each_power<0, Lay>(op);
+                        }
+                        u32 sb[TOTAL];                       // S before the chunk
+#pragma unroll
+                        for (int i = 0; i < TOTAL; ++i) {
+                            const u32 up = __shfl_up_sync(0xFFFFFFFFu, sa[i], 1);
+                            sb[i] = lane ? up : 0u;
+                        }
+                        {
+                            OpAdd o1{sa, o_run};
+                            for_each_power<0, Lay>(o1);
+                            OpAdd o2{sb, o_run};
+                            for_each_power<0, Lay>(o2);
+                        }
+                        int cb[NP], ca[NP];
+                        {
+                            OpCmpInit o1{sb, P.target, P.target_over_mask, cb};
+                            for_each_power<0, Lay>(o1);
+                            OpCmpInit o2{sa, P.target, P.target_over_mask, ca};
+                            for_each_power<0, Lay>(o2);
+                        }
+                        const bool mine = take > 0 && cb[0] < 0 && ca[0] >= 0;
+                        const u32 bmask = __ballot_sync(0xFFFFFFFFu, mine);
+                        u32 r_nlt = 0, r_eq = 0xFFFFFFFFu;
+                        if (mine) {
+                            const u32 c_skip = (o_skip > pre) ? min(o_skip - pre, take) : 0u;
+                            auto chunk_walk = [&](auto& fn) {
+                                fn.n_lt[0] = 0;
+                                fn.eq_li[0] = 0xFFFFFFFFu;
+                                fn.below[0] = true;
+                                if (lane == 0) {
+                                    bool go = true;
+                                    for (u32 t = 0; t < take && go; ++t) go = fn((u32)P.small_primes[t], 0u);
+                                } else {
+                                    u32 ww = w;
+                                    bool go = true;
+                                    while (ww && go) {
+                                        const u32 m = msb_index(ww);
+                                        ww ^= (1u << m);
+                                        const u64 pv = vb + 120u * (lane - 1u) + msb_value_offset(m);
+                                        go = fn((u32)pv, (u32)(pv >> 32));
+                                    }
+                                }
+                                r_nlt = fn.n_lt[0];
+                                r_eq = fn.eq_li[0];
+                            };
+                            if (c_skip != 0) {
+                                BsCmpFn<K, MULTI, kModeCompare, true> fn{sb, &P, tile_n0, o_li0 + pre, take, c_skip, 0, {}, {}, {}, 0, 0};
+                                chunk_walk(fn);
+                            } else {
+                                BsCmpFn<K, MULTI, kModeCompare, false> fn{sb, &P, tile_n0, o_li0 + pre, take, 0, 0, {}, {}, {}, 0, 0};
+                                chunk_walk(fn);
+                            }
+                        }
+                        __syncwarp();
+                        const int b = bmask ? (__ffs(bmask) - 1) : 0;
+                        const u32 b_pre = __shfl_sync(0xFFFFFFFFu, pre, b);
+                        r_nlt = __shfl_sync(0xFFFFFFFFu, r_nlt, b);
+                        r_eq = __shfl_sync(0xFFFFFFFFu, r_eq, b);
+                        if ((int)lane == owner) {
+                            n_in = quota - skip0;
+                            if (bmask) {
+                                n_lt[0] = ((b_pre > skip0) ? (b_pre - skip0) : 0u) + r_nlt;
+                                eq_li[0] = r_eq;
+                            } else {
+                                n_lt[0] = n_in;     // the crossing lies beyond this thread's quota (n_max): all of the window is below
+                            }
+                            localised = true;
+                            walk = false;
+                            coop = owns_nmax;       // S(n_max) and p_(n_max) by the warp-wide finish below
+                        }
+                    }
+                }
                 const u32 coop_mask = __ballot_sync(0xFFFFFFFFu, coop);
-                if (__any_sync(0xFFFFFFFFu, walk) || coop_mask) stage();   // the bitmap is only read where a walk is needed
                 {
                     if (coop_mask) {
                         // ---- S_k(n_max) and p_(n_max) by the whole warp.  One thread of the grid holds n_max; walking its
@@ -832,7 +960,7 @@ __global__ void __launch_bounds__(kBsThreads, bs_min_blocks<K, MULTI>()) k_bitma
                             for (int i = 0; i < PSS_LIMBS; ++i)
                                 P.results[jj].final_sum[i] = (i < Lay::width(jj)) ? run[Lay::offset(jj) + i] : 0u;
                     }
-                } else if (quota > 0) {
+                } else if (quota > 0 && !localised) {
                     n_in = quota - skip0;
 #pragma unroll
                     for (int jj = 0; jj < NP; ++jj) n_lt[jj] = (c0[jj] < 0) ? n_in : 0u;
