@@ -378,7 +378,9 @@ __device__ __forceinline__ void bs_reduce_tail(const BScanParams& P, u32* acc, u
 // dependent IMAD/carry chains)
 template <int K, bool MULTI>
 constexpr int bs_min_blocks() {
-    return MULTI ? (K >= 4 ? 2 : 3) : (K >= 6 ? 3 : 1);
+    // (k <= 2, one power: three CTAs as before the warp-wide localisation code was added -- it needs 91 registers if left alone,
+    //  which costs the exhaustive compare its third CTA: 4.81 -> 5.13 ms)
+    return MULTI ? (K >= 4 ? 2 : 3) : (K >= 6 ? 3 : (K <= 2 ? 3 : 1));
 }
 
 template <int K, bool MULTI, int MODE>
